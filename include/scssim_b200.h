@@ -1,0 +1,159 @@
+/* scssim_b200 — C ABI of the B200-native `scssim genreads` hot path.
+ *
+ * Drop-in boundary. Each entry point replaces one stage call that the reference's
+ * main() makes on its global singletons (/root/reference/src/scssim.cpp:46-66):
+ *
+ *   reference call (file:line)                                    replaced by
+ *   ------------------------------------------------------------  -----------------------------
+ *   parseArgs_genReads -> Config (src/scssim.cpp:285-404)          scs_params / scs_create
+ *   new ThreadPool(t); pool_init() (src/scssim.cpp:49-50)          scs_create (CUDA streams, Philox seed)
+ *   genome.loadData() (src/scssim.cpp:53, lib/genome/Genome.cpp:18)  scs_load_genome / scs_set_genome
+ *   profile.train(file) (src/scssim.cpp:56, lib/profile/Profile.cpp:1432)  scs_load_profile
+ *   malbac.createFrags() (src/scssim.cpp:59, lib/malbac/Malbac.cpp:143)    scs_create_frags
+ *   malbac.amplify() (src/scssim.cpp:62, lib/malbac/Malbac.cpp:173)        scs_amplify
+ *   malbac.yieldReads() (src/scssim.cpp:65, lib/malbac/Malbac.cpp:410)     scs_yield_reads[_sink]
+ *   SeqWriter::write (lib/seqwriter/SeqWriter.cpp:41-54)                   scs_sink_fn
+ *
+ * Plain pointers and sizes only; no exceptions and no exit() cross this boundary. Every function
+ * returns 0 on success or a negative SCS_E_* code; scs_last_error(ctx) gives the message the
+ * reference would have printed before exit(1). There is no CPU fallback: without a CUDA device
+ * scs_create fails with SCS_E_CUDA.
+ */
+#ifndef SCSSIM_B200_H
+#define SCSSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCS_OK 0
+#define SCS_E_ARG (-1)        /* bad argument / flag validation (src/scssim.cpp:349-393) */
+#define SCS_E_IO (-2)         /* cannot open / malformed input file */
+#define SCS_E_CUDA (-3)       /* CUDA runtime error or no device */
+#define SCS_E_STATE (-4)      /* stage called out of order */
+#define SCS_E_UNSUPPORTED (-5)
+#define SCS_E_NOMEM (-6)
+
+typedef struct scs_ctx scs_ctx;
+
+/* The genreads flags (src/scssim.cpp:289-293 defaults) plus the extra, non-reference knobs. */
+typedef struct scs_params {
+    int64_t primers;      /* -p, default 100000, >= 1000 */
+    double gamma;         /* -r, default 1e-9, (0, 1e-8] */
+    double coverage;      /* -c, default 5, > 0 */
+    int32_t isize;        /* -s, default 260 */
+    int32_t paired;       /* -l PE -> 1 (default), SE -> 0 */
+    uint64_t seed;        /* Philox key (extra flag --seed) */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t rank;         /* shard index in [0, world) */
+    int32_t world;        /* number of shards (GPUs) */
+    int32_t reserved;
+    uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (128 MiB) */
+} scs_params;
+
+void scs_default_params(scs_params* p);
+
+int scs_create(const scs_params* p, scs_ctx** out);
+void scs_destroy(scs_ctx* ctx);
+const char* scs_last_error(const scs_ctx* ctx);   /* ctx may be NULL: error of the last failed scs_create */
+
+/* .profile parser + CDF -> threshold tables (Profile::train(file), Profile.cpp:1432-1436) */
+int scs_load_profile(scs_ctx* ctx, const char* path);
+int scs_read_length(const scs_ctx* ctx);
+
+/* FASTA ingest + 2-bit pack on the device (Genome::loadData, Fragment::createSequence) */
+int scs_load_genome(scs_ctx* ctx, const char* fasta_path);
+/* Same, from host buffers: n sequences of ASCII bases. names[i] is the sequence name
+ * (`<chr>_<k>_<len>`, Malbac.cpp:413-419). */
+int scs_set_genome(scs_ctx* ctx, int n, const char* const* names, const char* const* seqs, const uint64_t* lens);
+
+/* Collective hook for world > 1: sum `n` u64 / f64 values over all ranks in place. The caller
+ * supplies it (torch.distributed/NCCL in bench.py, ncclAllReduce in the CLI). Unused when world == 1. */
+typedef int (*scs_allreduce_u64_fn)(void* user, uint64_t* buf, size_t n);
+typedef int (*scs_allreduce_f64_fn)(void* user, double* buf, size_t n);
+int scs_set_collectives(scs_ctx* ctx, scs_allreduce_u64_fn fu, scs_allreduce_f64_fn fd, void* user);
+
+int scs_create_frags(scs_ctx* ctx);   /* Genome::splitToFrags, Genome.cpp:753-782 */
+int scs_amplify(scs_ctx* ctx);        /* Malbac::amplify, Malbac.cpp:173-201 */
+
+/* FASTQ sink: called on the calling thread, in file order, with bytes that already sit in pinned
+ * host memory. file = 0 for <prefix>.fq / <prefix>_1.fq, 1 for <prefix>_2.fq. Return non-zero to abort. */
+typedef int (*scs_sink_fn)(void* user, int file, const char* data, size_t nbytes);
+int scs_yield_reads_sink(scs_ctx* ctx, scs_sink_fn sink, void* user);
+/* Malbac::yieldReads: writes <prefix>_1.fq/_2.fq (PE) or <prefix>.fq (SE). For world > 1 rank r
+ * writes <prefix>.rank<r>... shard files whose concatenation in rank order is the full output. */
+int scs_yield_reads(scs_ctx* ctx, const char* prefix);
+/* Read allocation only (Malbac::setReadCounts); scs_yield_reads* call it themselves if needed. */
+int scs_set_read_counts(scs_ctx* ctx);
+
+typedef struct scs_stats {
+    uint64_t n_sequences, genome_bases;
+    uint64_t n_frags, n_semis, n_fulls;        /* this rank */
+    uint64_t n_semis_global, n_fulls_global;
+    uint64_t reads_requested;                  /* Malbac.cpp:420, individual reads */
+    uint64_t records;                          /* FASTQ records written by this rank (both files) */
+    uint64_t fastq_bytes[2];
+    uint64_t total_primers_left;
+    uint64_t kernel_launches;                  /* kernels of this library launched so far */
+    double ms_pack, ms_amplify, ms_alloc, ms_reads;   /* CUDA-event times of the last run of each stage */
+    double ms_reads_kernels;                   /* plan+scan+emit kernels only, summed over slabs */
+    double ms_emit_kernel;                     /* emit kernel only, summed */
+    uint64_t emit_launches;
+    uint64_t genome_window_bytes;              /* algorithmic HBM read bytes of the emit kernel */
+} scs_stats;
+int scs_get_stats(const scs_ctx* ctx, scs_stats* out);
+
+/* ---- replay ("recorded draws", BASELINE north_star correctness part 1) -------------------------
+ * Tapes are the u32 logs of the patched reference run with -t 1; marks give, per entity, the tape
+ * position of its first "real"-engine and "int"-engine draw (written by the CPU oracle). All
+ * pointers are host memory, copied to the device by the call. */
+typedef struct scs_replay {
+    const uint32_t* wreal; uint64_t n_wreal;
+    const uint32_t* wint; uint64_t n_wint;
+    const uint32_t* mrand; uint64_t n_mrand;
+    const uint32_t* mreal; uint64_t n_mreal;
+    const double* gcf; uint64_t n_gcf;
+    /* marks[d]: n_marks[d] triples (entity, off_real, off_int), domain numbering of scs_domain */
+    const uint64_t* marks[8]; uint64_t n_marks[8];
+} scs_replay;
+enum scs_domain { SCS_D_FRAG = 0, SCS_D_POIS = 1, SCS_D_AMPF = 2, SCS_D_AMPS = 3, SCS_D_GCF = 4, SCS_D_MULTM = 5, SCS_D_MULTC = 6, SCS_D_READ = 7 };
+int scs_set_replay(scs_ctx* ctx, const scs_replay* r);
+
+/* ---- test hooks (SURVEY.md §8b "Inner seam 3") ------------------------------------------------- */
+/* Copy device arrays to host for parity tests. what: */
+enum scs_dump { SCS_DUMP_FRAGS = 0,    /* i64 x5: seq, start0, len, strand, primers */
+                SCS_DUMP_SEMIS = 1,    /* u64 x6: gstart, rc, len, gc, primers, nerr */
+                SCS_DUMP_FULLS = 2,    /* u64 x6 */
+                SCS_DUMP_COUNTS = 3,   /* u32 per full amplicon: readNumbers */
+                SCS_DUMP_WEIGHTS = 4,  /* f64 per full amplicon (normalised) */
+                SCS_DUMP_PRIMER_COUNTS = 5, /* i64 x 65536 */
+                SCS_DUMP_FULL_SEQ = 6  /* ASCII sequences of full amplicons, '\n' separated (arg = max count) */ };
+/* Returns the number of bytes needed/written (negative on error). If buf is NULL only sizes. */
+int64_t scs_dump(scs_ctx* ctx, int what, void* buf, uint64_t cap);
+
+/* Profile::predict on the device for `n_reads` source windows of read_length ASCII bases each,
+ * drawing from explicit per-read tapes (real[i*stride_real ...], ints[i*stride_int ...]). out_seq and
+ * out_qual receive out_stride bytes per read; out_len the produced lengths. */
+int scs_test_predict(scs_ctx* ctx, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real,
+                     const uint32_t* ints, uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len);
+/* One Philox4x32-10 block on the device (known-answer test). */
+int scs_test_philox(scs_ctx* ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* det_log on the device for n doubles. */
+int scs_test_det_log(scs_ctx* ctx, const double* x, int n, double* out);
+/* Threshold form of one CDF row: which/idx as in the profile (0 ins, 1 del, 2 isize, 3 subs1, 4 subs2,
+ * 5 quality), row = bin. Writes up to cap u32 thresholds, returns the row's entry count; *eff gets the
+ * number of entries that take part in the search (see DESIGN.md "thresholds"). Host-only (no GPU). */
+int scs_profile_thresholds(const scs_ctx* ctx, int which, int idx, int row, uint32_t* out, int cap, int* eff);
+
+/* Host-side shard arithmetic (no GPU needed): contiguous range [*lo, *hi) of `n` units for `rank`. */
+void scs_shard_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi);
+
+const char* scs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

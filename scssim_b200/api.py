@@ -1,0 +1,329 @@
+"""ctypes binding of libscssim_b200.so — the host-side mirror of the reference's `genreads` stages.
+
+The reference drives the path through global singletons (/root/reference/src/scssim.cpp:46-66):
+``genome.loadData(); profile.train(path); malbac.createFrags(); malbac.amplify();
+malbac.yieldReads()``. :class:`GenReads` exposes the same calls with the same argument meaning
+(flags of ``parseArgs_genReads``, src/scssim.cpp:285-404) and raises :class:`ScsError` carrying the
+message the reference would have printed before ``exit(1)``.
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import of the
+library, and every compute call fails without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscssim_b200.so")
+
+SCS_OK, SCS_E_ARG, SCS_E_IO, SCS_E_CUDA, SCS_E_STATE, SCS_E_UNSUPPORTED, SCS_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
+D_FRAG, D_POIS, D_AMPF, D_AMPS, D_GCF, D_MULTM, D_MULTC, D_READ = range(8)
+DUMP_FRAGS, DUMP_SEMIS, DUMP_FULLS, DUMP_COUNTS, DUMP_WEIGHTS, DUMP_PRIMER_COUNTS, DUMP_FULL_SEQ = range(7)
+
+
+class ScsError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code, self.msg = code, msg
+
+
+class Params(C.Structure):
+    _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
+                ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
+                ("world", C.c_int32), ("reserved", C.c_int32), ("slab_bytes", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_sequences", C.c_uint64), ("genome_bases", C.c_uint64), ("n_frags", C.c_uint64), ("n_semis", C.c_uint64),
+                ("n_fulls", C.c_uint64), ("n_semis_global", C.c_uint64), ("n_fulls_global", C.c_uint64),
+                ("reads_requested", C.c_uint64), ("records", C.c_uint64), ("fastq_bytes", C.c_uint64 * 2),
+                ("total_primers_left", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_pack", C.c_double),
+                ("ms_amplify", C.c_double), ("ms_alloc", C.c_double), ("ms_reads", C.c_double),
+                ("ms_reads_kernels", C.c_double), ("ms_emit_kernel", C.c_double), ("emit_launches", C.c_uint64),
+                ("genome_window_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if name == "fastq_bytes" else v
+        return d
+
+
+class Replay(C.Structure):
+    _fields_ = [("wreal", C.c_void_p), ("n_wreal", C.c_uint64), ("wint", C.c_void_p), ("n_wint", C.c_uint64),
+                ("mrand", C.c_void_p), ("n_mrand", C.c_uint64), ("mreal", C.c_void_p), ("n_mreal", C.c_uint64),
+                ("gcf", C.c_void_p), ("n_gcf", C.c_uint64), ("marks", C.c_void_p * 8), ("n_marks", C.c_uint64 * 8)]
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+AR_U64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t)
+AR_F64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
+
+# every symbol include/scssim_b200.h declares
+EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", "scs_load_profile", "scs_read_length",
+           "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_create_frags", "scs_amplify",
+           "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
+           "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
+           "scs_version"]
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the genreads path is CUDA-only; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.scs_last_error.restype = C.c_char_p
+        L.scs_last_error.argtypes = [C.c_void_p]
+        L.scs_version.restype = C.c_char_p
+        L.scs_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
+        L.scs_destroy.argtypes = [C.c_void_p]
+        L.scs_load_profile.argtypes = [C.c_void_p, C.c_char_p]
+        L.scs_read_length.argtypes = [C.c_void_p]
+        L.scs_load_genome.argtypes = [C.c_void_p, C.c_char_p]
+        L.scs_set_genome.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.scs_set_collectives.argtypes = [C.c_void_p, AR_U64_FN, AR_F64_FN, C.c_void_p]
+        for f in ("scs_create_frags", "scs_amplify", "scs_set_read_counts"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.scs_yield_reads_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
+        L.scs_yield_reads.argtypes = [C.c_void_p, C.c_char_p]
+        L.scs_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.scs_set_replay.argtypes = [C.c_void_p, C.POINTER(Replay)]
+        L.scs_dump.restype = C.c_int64
+        L.scs_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.scs_test_predict.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.scs_test_philox.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.scs_test_det_log.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.scs_profile_thresholds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.scs_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.scs_shard_range.restype = None
+        _lib = L
+    return _lib
+
+
+def shard_range(n: int, rank: int, world: int):
+    lo, hi = C.c_uint64(), C.c_uint64()
+    lib().scs_shard_range(n, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+@dataclass
+class ReplayTapes:
+    """Draw logs of `oracle/_ref/bin/scssim_replay -t 1` plus the per-entity offsets the CPU oracle wrote."""
+    wreal: np.ndarray
+    wint: np.ndarray
+    mrand: np.ndarray
+    mreal: np.ndarray
+    gcf: np.ndarray
+    marks: list  # 8 arrays (n,3) uint64
+
+    @staticmethod
+    def load(tape_prefix: str, dump_prefix: str) -> "ReplayTapes":
+        t = lambda n: np.fromfile(f"{tape_prefix}.{n}.bin", dtype=np.uint32)
+        marks = [np.fromfile(f"{dump_prefix}.marks{d}.u64", dtype=np.uint64).reshape(-1, 3) for d in range(8)]
+        return ReplayTapes(t("wreal"), t("wint"), t("mrand"), t("mreal"),
+                           np.fromfile(f"{tape_prefix}.gcf.bin", dtype=np.float64), marks)
+
+
+class GenReads:
+    """One `scssim genreads` run on one GPU (one shard when world > 1)."""
+
+    def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
+                 layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
+                 slab_bytes: int = 0):
+        if layout not in ("SE", "PE"):
+            raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
+        L = lib()
+        p = Params()
+        L.scs_default_params(C.byref(p))
+        p.primers, p.gamma, p.coverage, p.isize = primers, gamma, coverage, isize
+        p.paired, p.seed, p.device, p.rank, p.world, p.slab_bytes = int(layout == "PE"), seed, device, rank, world, slab_bytes
+        self._h = C.c_void_p()
+        rc = L.scs_create(C.byref(p), C.byref(self._h))
+        if rc != SCS_OK:
+            raise ScsError(rc, L.scs_last_error(None).decode())
+        self.paired = layout == "PE"
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise ScsError(int(rc), lib().scs_last_error(self._h).decode())
+        return rc
+
+    # --- the reference's stage calls -------------------------------------------------------------
+    def load_profile(self, path: str):          # profile.train(file)
+        self._ck(lib().scs_load_profile(self._h, path.encode()))
+        return self
+
+    @property
+    def read_length(self) -> int:
+        return lib().scs_read_length(self._h)
+
+    def load_genome(self, fasta_path: str):     # genome.loadData()
+        self._ck(lib().scs_load_genome(self._h, fasta_path.encode()))
+        return self
+
+    def set_genome(self, named_seqs):
+        """named_seqs: list of (name, uint8 ASCII array)."""
+        n = len(named_seqs)
+        names = (C.c_char_p * n)(*[nm.encode() for nm, _ in named_seqs])
+        arrs = [np.ascontiguousarray(s, dtype=np.uint8) for _, s in named_seqs]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_uint64 * n)(*[len(a) for a in arrs])
+        self._ck(lib().scs_set_genome(self._h, n, names, ptrs, lens))
+        return self
+
+    def set_replay(self, t: ReplayTapes):
+        r = Replay()
+        keep = [np.ascontiguousarray(a) for a in (t.wreal, t.wint, t.mrand, t.mreal, t.gcf)]
+        for name, a in zip(("wreal", "wint", "mrand", "mreal", "gcf"), keep):
+            setattr(r, name, a.ctypes.data)
+            setattr(r, "n_" + name, len(a))
+        mk = [np.ascontiguousarray(m, dtype=np.uint64) for m in t.marks]
+        for d in range(8):
+            r.marks[d] = mk[d].ctypes.data
+            r.n_marks[d] = len(mk[d])
+        self._ck(lib().scs_set_replay(self._h, C.byref(r)))
+        return self
+
+    def set_collectives(self, allreduce_u64, allreduce_f64):
+        """allreduce_*(np.ndarray) -> None, in place (sum over ranks)."""
+        def fu(_u, buf, n):
+            a = np.ctypeslib.as_array(buf, shape=(n,))
+            allreduce_u64(a)
+            return 0
+
+        def fd(_u, buf, n):
+            a = np.ctypeslib.as_array(buf, shape=(n,))
+            allreduce_f64(a)
+            return 0
+        self._cb = (AR_U64_FN(fu), AR_F64_FN(fd))
+        self._ck(lib().scs_set_collectives(self._h, self._cb[0], self._cb[1], None))
+        return self
+
+    def create_frags(self):                     # malbac.createFrags()
+        self._ck(lib().scs_create_frags(self._h))
+        return self
+
+    def amplify(self):                          # malbac.amplify()
+        self._ck(lib().scs_amplify(self._h))
+        return self
+
+    def set_read_counts(self):
+        self._ck(lib().scs_set_read_counts(self._h))
+        return self
+
+    def yield_reads(self, prefix: str):         # malbac.yieldReads() -> <prefix>_1.fq/_2.fq | <prefix>.fq
+        self._ck(lib().scs_yield_reads(self._h, prefix.encode()))
+        return self
+
+    def yield_reads_bytes(self):
+        """FASTQ text of both files as bytes (tests; small runs)."""
+        parts = ([], [])
+
+        def sink(_u, f, data, n):
+            parts[f].append(C.string_at(data, n))
+            return 0
+        cb = SINK_FN(sink)
+        self._ck(lib().scs_yield_reads_sink(self._h, cb, None))
+        return b"".join(parts[0]), b"".join(parts[1])
+
+    def yield_reads_discard(self):
+        """Run the read stage with output landing in the pinned host ring only (bench)."""
+        self._ck(lib().scs_yield_reads_sink(self._h, C.cast(None, SINK_FN), None))
+        return self
+
+    def yield_reads_into(self, bufs):
+        """Copy FASTQ bytes into caller-provided host arrays (one per file); returns bytes written per file."""
+        pos = [0, 0]
+        ptrs = [b.ctypes.data for b in bufs]
+        caps = [b.nbytes for b in bufs]
+
+        def sink(_u, f, data, n):
+            if pos[f] + n > caps[f]:
+                return 1
+            C.memmove(ptrs[f] + pos[f], data, n)
+            pos[f] += n
+            return 0
+        cb = SINK_FN(sink)
+        self._ck(lib().scs_yield_reads_sink(self._h, cb, None))
+        return pos
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(lib().scs_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    # --- test hooks -------------------------------------------------------------------------------
+    def dump(self, what: int) -> np.ndarray:
+        n = self._ck(lib().scs_dump(self._h, what, None, 0))
+        buf = np.zeros(max(int(n), 1), dtype=np.uint8)
+        self._ck(lib().scs_dump(self._h, what, buf.ctypes.data, buf.nbytes))
+        buf = buf[:n]
+        if what == DUMP_FRAGS:
+            return buf.view(np.int64).reshape(-1, 5)
+        if what in (DUMP_SEMIS, DUMP_FULLS):
+            return buf.view(np.uint64).reshape(-1, 6)
+        if what == DUMP_COUNTS:
+            return buf.view(np.uint32)
+        if what == DUMP_WEIGHTS:
+            return buf.view(np.float64)
+        if what == DUMP_PRIMER_COUNTS:
+            return buf.view(np.int64)
+        return buf
+
+    def test_predict(self, src: np.ndarray, is_read1: bool, real: np.ndarray, ints: np.ndarray, out_stride: int = 384):
+        """src: (n, RL) uint8 ASCII; real/ints: (n, stride) uint32 tapes. Returns (seqs, quals, lens)."""
+        n = src.shape[0]
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        real = np.ascontiguousarray(real, dtype=np.uint32)
+        ints = np.ascontiguousarray(ints, dtype=np.uint32)
+        oseq = np.zeros((n, out_stride), dtype=np.uint8)
+        oqual = np.zeros((n, out_stride), dtype=np.uint8)
+        olen = np.zeros(n, dtype=np.int32)
+        self._ck(lib().scs_test_predict(self._h, src.ctypes.data_as(C.c_char_p), n, int(is_read1), real.ctypes.data, real.shape[1],
+                                        ints.ctypes.data, ints.shape[1], oseq.ctypes.data, oqual.ctypes.data, out_stride,
+                                        olen.ctypes.data))
+        return oseq, oqual, olen
+
+    def test_philox(self, ctr, key):
+        c = (C.c_uint32 * 4)(*ctr)
+        k = (C.c_uint32 * 2)(*key)
+        o = (C.c_uint32 * 4)()
+        self._ck(lib().scs_test_philox(self._h, c, k, o))
+        return list(o)
+
+    def test_det_log(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros_like(x)
+        self._ck(lib().scs_test_det_log(self._h, x.ctypes.data, len(x), out.ctypes.data))
+        return out
+
+    def thresholds(self, which: int, idx: int = 0, row: int = 0):
+        out = np.zeros(4096, dtype=np.uint32)
+        eff = C.c_int()
+        n = self._ck(lib().scs_profile_thresholds(self._h, which, idx, row, out.ctypes.data, 4096, C.byref(eff)))
+        return out[:n].copy(), eff.value

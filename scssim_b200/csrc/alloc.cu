@@ -1,0 +1,201 @@
+// K3 amplicon_weights + alloc_reads: GC-bias-weighted allocation of reads to full amplicons.
+//
+// Replaces Amplicon::getWeightedLength (/root/reference/lib/amplicon/Amplicon.cpp:396-400),
+// Profile::getGCFactor (lib/profile/Profile.cpp:1503-1513), Malbac::setReadCounts
+// (lib/malbac/Malbac.cpp:370-408) and randIndx_hp / batchSampling (lib/mydefine/MyDefine.cpp:191-272).
+//
+// The reference's multinomial for the remainder works on chunks of 1000 consecutive amplicons with
+// a serial FP64 running sum inside each chunk; that structure is kept (one thread builds a chunk's
+// CDF in the reference's summation order, then all of the chunk's samples are drawn in parallel by
+// binary search on it), so the decisions are the reference's for the same draws.
+#include <algorithm>
+#include <cmath>
+
+#include "ctx.h"
+
+namespace scs {
+
+constexpr uint32_t kChunk = 1000;   // min(1000, ac/threads) with threads = 1, MyDefine.cpp:206
+static const double kEpsH = 2.2204e-16;
+
+__device__ __forceinline__ double draw_r(uint32_t x) {   // randomDouble(ZERO_FINAL, 1)
+    return __dadd_rn(2.2204e-16, __dmul_rn(__dadd_rn(1.0, -2.2204e-16), (double)x / 4294967296.0));
+}
+
+__global__ void __launch_bounds__(256) weights_kernel(DrawSrc src, const double* __restrict__ gcf_tape, uint64_t global0, uint64_t n,
+                                                      const uint64_t* __restrict__ desc, const uint32_t* __restrict__ gc,
+                                                      const double* __restrict__ gcMeans, double gcStd, double* __restrict__ w) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t len = unpack_desc(desc[i]).len;
+    uint32_t pct = 100u * gc[i] / len;   // Amplicon.cpp:398
+    double f = 0.0;
+    if (pct <= 100u) {
+        if (gcf_tape) f = gcf_tape[global0 + i];
+        else {
+            // Marsaglia polar normal on Philox draws, redrawn until >= 0 (Profile.cpp:1508-1511)
+            Stream s; s.init(src, D_GCF, global0 + i, 0);
+            double mean = gcMeans[pct]; uint32_t k = 0;
+            for (;;) {
+                double u1 = __dadd_rn((double)s.at(E_REAL, k), 0.5) / 4294967296.0;
+                double u2 = __dadd_rn((double)s.at(E_REAL, k + 1), 0.5) / 4294967296.0;
+                k += 2;
+                double v1 = __dadd_rn(__dmul_rn(2.0, u1), -1.0), v2 = __dadd_rn(__dmul_rn(2.0, u2), -1.0);
+                double q = __dadd_rn(__dmul_rn(v1, v1), __dmul_rn(v2, v2));
+                if (q >= 1.0 || q == 0.0) continue;
+                double fac = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, det_log(q)), q));
+                double v = __dadd_rn(mean, __dmul_rn(gcStd, __dmul_rn(v1, fac)));
+                if (v >= 0) { f = v; break; }
+            }
+        }
+    }
+    w[i] = __ddiv_rn(__dmul_rn(f, (double)len), 1000000.0);   // fragSize^2, Config.cpp:41
+}
+
+// serial sum of each chunk of kChunk weights (reference summation order inside a chunk)
+__global__ void __launch_bounds__(128) chunk_sum_kernel(const double* __restrict__ w, uint64_t n, double* __restrict__ sums) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t s = c * kChunk;
+    if (s >= n) return;
+    uint64_t e = min(n, s + kChunk);
+    double t = 0.0;
+    for (uint64_t i = s; i < e; i++) t = __dadd_rn(t, w[i]);
+    sums[c] = t;
+}
+
+__global__ void __launch_bounds__(256) normalize_floor_kernel(double* __restrict__ w, uint64_t n, double denom, double reads, uint32_t* __restrict__ counts,
+                                                              unsigned long long* __restrict__ total) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long rc = 0;
+    if (i < n) {
+        double v = __ddiv_rn(w[i], denom);
+        w[i] = v;
+        rc = (unsigned int)__dmul_rn(v, reads);   // Malbac.cpp:390
+        counts[i] = (uint32_t)rc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rc += __shfl_down_sync(0xffffffffu, rc, o);
+    if ((threadIdx.x & 31) == 0 && rc) atomicAdd(total, rc);
+}
+
+// per chunk: cdf[k] = cdf[k-1] + w[k]/total (serial, MyDefine.cpp:224-226)
+__global__ void __launch_bounds__(128) chunk_cdf_kernel(const double* __restrict__ w, uint64_t n, const double* __restrict__ totals, double* __restrict__ cdf) {
+    uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t s = c * kChunk;
+    if (s >= n) return;
+    uint64_t e = min(n, s + kChunk);
+    double tot = totals[c], prev = 0.0;
+    for (uint64_t i = s; i < e; i++) { prev = __dadd_rn(prev, __ddiv_rn(w[i], tot)); cdf[i] = prev; }
+}
+
+// one thread per sample: chunk by binary search on the sample prefix, index by binary search on the chunk CDF
+__global__ void __launch_bounds__(256) chunk_sample_kernel(DrawSrc src, uint64_t chunk_global0, uint64_t n_amp, uint64_t n_chunks,
+                                                           const uint64_t* __restrict__ sample_prefix, uint64_t n_samples,
+                                                           const double* __restrict__ cdf, uint32_t* __restrict__ counts) {
+    uint64_t sidx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= n_samples) return;
+    uint64_t lo = 0, hi = n_chunks;   // last chunk with prefix <= sidx
+    while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (sample_prefix[mid] <= sidx) lo = mid; else hi = mid; }
+    uint64_t c = lo, i = sidx - sample_prefix[c];
+    Stream s; s.init(src, D_MULTC, chunk_global0 + c, chunk_global0 + c);
+    double r = draw_r(s.at(E_REAL, (uint32_t)i));
+    uint64_t a0 = c * kChunk; uint32_t m = (uint32_t)min((uint64_t)kChunk, n_amp - a0);
+    const double* row = cdf + a0;
+    uint32_t l = 0, h = m;   // first k with r <= row[k], else m-1 (randIndx, MyDefine.cpp:274-282)
+    while (l < h) { uint32_t mid = (l + h) >> 1; if (r <= row[mid]) h = mid; else l = mid + 1; }
+    if (l >= m) l = m - 1;
+    atomicAdd(&counts[a0 + l], 1u);
+}
+
+__global__ void __launch_bounds__(256) odd_flags_kernel(const uint32_t* __restrict__ counts, uint64_t n, uint32_t* __restrict__ flags) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = counts[i] & 1u;
+}
+// PE: odd counts alternately +1 / -1 in list order (Malbac.cpp:398-407); then slots = pairs (PE) or reads (SE)
+__global__ void __launch_bounds__(256) parity_slots_kernel(uint32_t* __restrict__ counts, uint64_t n, const uint64_t* __restrict__ odd_prefix, uint64_t odd_before,
+                                                           int paired, uint32_t* __restrict__ slots) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = counts[i];
+    if (paired) {
+        if (v & 1u) { v = (((odd_before + odd_prefix[i]) & 1ull) == 0) ? v + 1 : v - 1; counts[i] = v; }
+        slots[i] = v >> 1;
+    } else slots[i] = v;
+}
+
+int set_read_counts(scs_ctx* c) {
+    if (!c->amplified) return c->fail(SCS_E_STATE, "scs_set_read_counts: call scs_amplify first");
+    if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_set_read_counts: no profile loaded");
+    if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "scs_set_read_counts: multi-rank allocation is not wired yet");
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
+    const uint64_t n = c->fulls.n;
+    // Malbac::yieldReads: reads = refLen * coverage / readLength (Malbac.cpp:420), individual reads
+    c->reads_requested = (uint64_t)((double)c->ref_len_half * c->P.coverage / (double)c->prof.readLength);
+    c->stats.reads_requested = c->reads_requested;
+    SCS_CUDA(c, c->weights.reserve(n + 1)); SCS_CUDA(c, c->counts.reserve(n + 1)); SCS_CUDA(c, c->slot_base.reserve(n + 2));
+    c->n_slots = 0;
+    if (n == 0) { c->have_counts = true; return SCS_OK; }   // the reference crashes on an empty amplicon list; we emit nothing
+    DevBuf<double> gcm; SCS_CUDA(c, gcm.reserve(101));
+    SCS_CUDA(c, cudaMemcpyAsync(gcm.p, c->prof.gcMeans, 101 * 8, cudaMemcpyHostToDevice, c->st));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    weights_kernel<<<nb, 256, 0, c->st>>>(draw_src(c, D_GCF), c->replay.on ? c->replay.gcf.p : nullptr, 0, n, c->fulls.desc.p, c->fulls.gc.p, gcm.p,
+                                          c->prof.gcStd, c->weights.p); SCS_LAUNCHED(c);
+    const uint64_t nch = (n + kChunk - 1) / kChunk;
+    DevBuf<double> dsums; SCS_CUDA(c, dsums.reserve(nch + 1));
+    std::vector<double> hs(nch);
+    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p); SCS_LAUNCHED(c);
+    SCS_CUDA(c, cudaMemcpyAsync(hs.data(), dsums.p, nch * 8, cudaMemcpyDeviceToHost, c->st));
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    double S = 0; for (uint64_t k = 0; k < nch; k++) S += hs[k];
+    DevBuf<unsigned long long> dtot; SCS_CUDA(c, dtot.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(dtot.p, 0, 8, c->st));
+    normalize_floor_kernel<<<nb, 256, 0, c->st>>>(c->weights.p, n, kEpsH + S, (double)(long)c->reads_requested, c->counts.p, dtot.p); SCS_LAUNCHED(c);
+    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p); SCS_LAUNCHED(c);
+    unsigned long long floorSum = 0;
+    SCS_CUDA(c, cudaMemcpyAsync(&floorSum, dtot.p, 8, cudaMemcpyDeviceToHost, c->st));
+    SCS_CUDA(c, cudaMemcpyAsync(hs.data(), dsums.p, nch * 8, cudaMemcpyDeviceToHost, c->st));
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    // randIndx_hp (MyDefine.cpp:203-247): whole samples per chunk, then the leftover one by one over the chunk CDF
+    unsigned long rem = (unsigned long)((long)c->reads_requested - (long)floorSum);
+    std::vector<uint64_t> ns(nch + 1, 0); unsigned long cnt = 0;
+    for (uint64_t k = 0; k < nch; k++) { ns[k] = (unsigned int)(hs[k] * (double)rem); cnt += ns[k]; }
+    rem -= cnt;
+    if (rem > 0) {
+        std::vector<double> probs(nch);
+        probs[0] = hs[0]; for (uint64_t k = 1; k < nch; k++) probs[k] = probs[k - 1] + hs[k];
+        uint64_t i = 0;
+        while (rem-- > 0) {
+            uint32_t x = host_draw(c, D_MULTM, E_REAL, 0, 0, i++);
+            double r = kEpsH + (1.0 - kEpsH) * ((double)x / 4294967296.0);
+            uint64_t k = std::lower_bound(probs.begin(), probs.end(), r) - probs.begin();   // first k with r <= probs[k]
+            if (k >= nch) k = nch - 1;
+            ns[k] += 1;
+        }
+    }
+    uint64_t nsamp = 0;
+    std::vector<uint64_t> pref(nch + 1);
+    for (uint64_t k = 0; k < nch; k++) { pref[k] = nsamp; nsamp += ns[k]; }
+    pref[nch] = nsamp;
+    if (nsamp) {
+        DevBuf<double> cdf; SCS_CUDA(c, cdf.reserve(n + 1));
+        DevBuf<uint64_t> dpref; SCS_CUDA(c, dpref.reserve(nch + 1));
+        SCS_CUDA(c, cudaMemcpyAsync(dpref.p, pref.data(), (nch + 1) * 8, cudaMemcpyHostToDevice, c->st));
+        chunk_cdf_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p, cdf.p); SCS_LAUNCHED(c);
+        chunk_sample_kernel<<<(unsigned)((nsamp + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_MULTC), 0, n, nch, dpref.p, nsamp, cdf.p, c->counts.p); SCS_LAUNCHED(c);
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    }
+    DevBuf<uint32_t> tmp; SCS_CUDA(c, tmp.reserve(n + 1));
+    DevBuf<uint64_t> oddp; SCS_CUDA(c, oddp.reserve(n + 1));
+    if (c->P.paired) {
+        odd_flags_kernel<<<nb, 256, 0, c->st>>>(c->counts.p, n, tmp.p); SCS_LAUNCHED(c);
+        if (int rc = exclusive_scan_u32(c, tmp.p, oddp.p, n, nullptr)) return rc;
+    }
+    parity_slots_kernel<<<nb, 256, 0, c->st>>>(c->counts.p, n, oddp.p, 0, c->P.paired, tmp.p); SCS_LAUNCHED(c);
+    if (int rc = exclusive_scan_u32(c, tmp.p, c->slot_base.p, n, &c->n_slots)) return rc;
+    SCS_CUDA(c, cudaMemcpyAsync(c->slot_base.p + n, &c->n_slots, 8, cudaMemcpyHostToDevice, c->st));
+    cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_alloc = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->have_counts = true;
+    return SCS_OK;
+}
+
+}  // namespace scs

@@ -1,0 +1,429 @@
+// K1 assign_primers + K2 amplify: MALBAC whole-genome amplification on the device.
+//
+// Replaces Malbac::amplify / setPrimers / amplifyFrags / amplifySemiAmplicons
+// (/root/reference/lib/malbac/Malbac.cpp:173-201,236-283,318-368), poissRand
+// (lib/mydefine/MyDefine.cpp:69-80), Fragment::amplify (lib/fragment/Fragment.cpp:52-137),
+// Amplicon::amplify (lib/amplicon/Amplicon.cpp:156-240) and the linked-list splicing
+// (Amplicon.cpp:574-585, Malbac.cpp:105-141).
+//
+// Design: a template (fragment or semi amplicon) is an oriented genome window + a sparse overlay of
+// substitutions; no sequence is ever materialised. One warp owns one template and walks its primers
+// in order (they are sequentially dependent through the attached-site bitmap and the draw cursors);
+// the 50 primer-site tries and the ~1500 per-base error draws of each primer are evaluated
+// lane-parallel with ballots picking the first event in the reference's order. Products go to
+// per-template slots (exclusive scan of the primer counts) and a second small kernel compacts them
+// into the reference's list order (reverse creation order inside a batch, batches appended).
+#include <algorithm>
+#include <cmath>
+
+#include "ctx.h"
+
+namespace scs {
+
+constexpr int kAmpMin = 1000, kAmpMax = 2000;   // Config.cpp:39-40
+constexpr int kMaxErrPerAmp = 96;                // per-amplicon staging (own + inherited substitutions)
+
+struct AmpParams {
+    uint32_t thr_ber;        // error iff x < thr_ber   (p < ber, ber = 3.4e-4, Config.cpp:46)
+    uint64_t entity_base;    // (round << 40) | global index of this rank's template 0
+    uint64_t mark_base;      // replay: index of template 0's mark inside the domain's mark array
+};
+
+// ---------------------------------------------------------------------------------- K1
+// k ~ Poisson(lambda) by Knuth's product method in log space, exactly the reference's loop.
+__global__ void __launch_bounds__(256) assign_primers_kernel(DrawSrc src, uint64_t entity_base, uint64_t mark_base, const uint64_t* __restrict__ desc,
+                                                             uint64_t n, double expected, double totalLen, uint32_t mask, uint32_t* __restrict__ primers,
+                                                             unsigned long long* __restrict__ count) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long k = 0;
+    if (t < n) {
+        Tmpl T = unpack_desc(desc[t]);
+        double lambda = __dmul_rn(expected, __ddiv_rn(__dmul_rn(1.0, (double)T.len), totalLen));
+        Stream s; s.init(src, D_POIS, entity_base + t, mark_base + t);
+        double log1 = 0.0, log2 = -lambda; long long x = -1; uint32_t i = 0;
+        do {
+            uint32_t d = s.at(E_REAL, i++);
+            double u = (double)d / 4294967296.0;
+            log1 = __dadd_rn(log1, det_log(u));
+            x++;
+        } while (log1 >= log2);
+        k = (unsigned long long)x;
+        primers[t] = (uint32_t)k & mask;
+    }
+    // block reduction of k
+    __shared__ unsigned long long ws[8];
+    unsigned long long v = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long s = 0; for (int w = 0; w < 8; w++) s += ws[w]; if (s) atomicAdd(count, s); }
+}
+
+// ---------------------------------------------------------------------------------- K2
+__device__ __forceinline__ uint32_t tmpl_base(const Genome& g, const Tmpl& T, const uint32_t* __restrict__ errs, uint32_t nerr, uint32_t i) {
+    uint32_t b = window_base(g, T.gstart, T.rc, i);
+    for (uint32_t e = 0; e < nerr; e++) { uint32_t v = errs[e]; if (err_pos(v) == i) b = err_base(v); }
+    return b;
+}
+
+// GC count of template window [s, s+l): popcount over packed words (+ overlay fix-up by the caller)
+__device__ __forceinline__ uint32_t window_gc_raw(const Genome& g, const Tmpl& T, uint32_t s, uint32_t l, int lane) {
+    uint64_t lo = T.rc ? (T.gstart - (s + l - 1)) : (T.gstart + s);   // genome interval [lo, lo+l)
+    uint64_t hi = lo + l;
+    uint64_t w0 = lo >> 5, w1 = (hi - 1) >> 5;
+    uint32_t cnt = 0;
+    for (uint64_t w = w0 + lane; w <= w1; w += 32) {
+        uint64_t x = __ldg(g.words + w);
+        uint64_t m = (x ^ (x >> 1)) & 0x5555555555555555ull;   // 1 where the base is C or G
+        uint64_t b0 = w << 5;
+        if (b0 < lo) m &= ~0ull << (2 * (lo - b0));
+        if (b0 + 32 > hi) m &= ~0ull >> (2 * (b0 + 32 - hi));
+        cnt += __popcll(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    return cnt;
+}
+
+template <bool FROM_FRAG, int BITMAP_WORDS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc src, AmpParams ap, uint64_t n_tmpl, const uint64_t* __restrict__ desc,
+                                                             const uint32_t* __restrict__ primers, const uint64_t* __restrict__ errref,
+                                                             const uint64_t* __restrict__ slot_off, uint64_t* __restrict__ out_desc,
+                                                             uint32_t* __restrict__ out_gc, uint64_t* __restrict__ out_errref,
+                                                             uint32_t* __restrict__ created, uint32_t* err_pool, unsigned long long* err_top,
+                                                             uint64_t err_cap, int* __restrict__ flags, long long* primer_counts,
+                                                             unsigned long long* __restrict__ ticket) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* bitmap = smem + (size_t)warp * BITMAP_WORDS;
+    uint32_t* errbuf = smem + (size_t)WARPS * BITMAP_WORDS + (size_t)warp * kMaxErrPerAmp;
+    for (;;) {
+        // dynamic work: chunks of 32 consecutive templates per warp
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(ticket, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        uint64_t t0 = chunk * 32ull;
+        if (t0 >= n_tmpl) break;
+        uint64_t tl = t0 + lane;
+        uint32_t myp = 0; uint64_t myd = 0;
+        if (tl < n_tmpl) { myp = primers[tl]; myd = desc[tl]; if (unpack_desc(myd).len < (uint32_t)(kAmpMin + 27)) myp = 0; }
+        if (tl < n_tmpl && myp == 0) created[tl] = 0;
+        uint32_t work = __ballot_sync(0xffffffffu, myp != 0);
+        while (work) {
+            int src_lane = __ffs(work) - 1; work &= work - 1;
+            const uint64_t t = t0 + src_lane;
+            const uint32_t primerNum = __shfl_sync(0xffffffffu, myp, src_lane);
+            const Tmpl T = unpack_desc(__shfl_sync(0xffffffffu, myd, src_lane));
+            const uint32_t* terr = nullptr; uint32_t tnerr = 0;
+            if (!FROM_FRAG) { uint64_t er = errref[t]; tnerr = (uint32_t)(er & 0xFFFF); terr = err_pool + (er >> 16); }
+            const uint64_t slot0 = slot_off[t];
+            Stream S; S.init(src, FROM_FRAG ? D_AMPF : D_AMPS, ap.entity_base + t, ap.mark_base + t);
+            const uint32_t bw = (T.len + 31) >> 5;
+            for (uint32_t w = lane; w < bw; w += 32) bitmap[w] = 0;
+            __syncwarp();
+            uint32_t ci = 0, cr = 0, made = 0;
+            for (uint32_t pi = 0; pi < primerNum; pi++) {
+                // ---- primer site: up to 50 tries (Fragment.cpp:73-95); try k uses int draw ci+k-1 and real draw cr+k-1
+                uint32_t spos = 0, alen = 0; int acc = 0;
+                for (uint32_t tb = 0; tb < 50 && !acc; tb += 32) {
+                    uint32_t k = tb + lane;   // 0-based try
+                    bool ok = false; uint32_t sp = 0, al = 0; uint32_t pidx = 0;
+                    if (k < 50) {
+                        sp = uni_trunc(S.at(E_INT, ci + k), 27, T.len - 27);
+                        al = uni_trunc(S.at(E_REAL, cr + k), kAmpMin, kAmpMax + 1 - kAmpMin);
+                        ok = (sp + al <= T.len) && !((bitmap[sp >> 5] >> (sp & 31)) & 1u);
+                        if (ok) {
+                            for (int q = 0; q < 8; q++) pidx = pidx * 4 + tmpl_base(g, T, terr, tnerr, sp + q);
+                            ok = primer_counts[pidx] > 0;
+                        }
+                    }
+                    uint32_t cand = __ballot_sync(0xffffffffu, ok);
+                    while (cand && !acc) {
+                        int wl = __ffs(cand) - 1; cand &= cand - 1;
+                        int got = 0;
+                        if (lane == wl) {   // updatePrimerCount(s, -1), Malbac.cpp:91-103
+                            long long old = atomicAdd((unsigned long long*)&primer_counts[pidx], (unsigned long long)-1ll);
+                            if (old > 0) got = 1; else atomicAdd((unsigned long long*)&primer_counts[pidx], 1ull);
+                        }
+                        got = __shfl_sync(0xffffffffu, got, wl);
+                        if (got) { acc = 1; spos = __shfl_sync(0xffffffffu, sp, wl); alen = __shfl_sync(0xffffffffu, al, wl); ci += tb + wl + 1; cr += tb + wl + 1; }
+                    }
+                }
+                if (!acc) { ci += 51; cr += 51; break; }   // 51st try draws, then the template is abandoned
+                if (lane == 0) bitmap[spos >> 5] |= 1u << (spos & 31);
+                // ---- GC content of the window (countGC, MyDefine.cpp:434-452)
+                int gc = (int)window_gc_raw(g, T, spos, alen, lane);
+                if (!FROM_FRAG) for (uint32_t e = 0; e < tnerr; e++) {
+                    uint32_t v = terr[e], p = err_pos(v);
+                    if (p >= spos && p < spos + alen) {
+                        uint32_t raw = window_base(g, T.gstart, T.rc, p), nb = err_base(v);
+                        gc += (int)((nb == 1u) | (nb == 2u)) - (int)((raw == 1u) | (raw == 2u));
+                    }
+                }
+                // ---- per-base polymerase errors, j = 8 .. alen-1 (Fragment.cpp:105-123)
+                // draw d on the real stream belongs to position j = 8 + (d - dbase)
+                uint32_t nown = 0; uint32_t dbase = cr, dcur = cr; const uint32_t dend_pos = alen;   // position limit
+                for (;;) {
+                    uint32_t jcur = 8 + (dcur - dbase);
+                    if (jcur >= dend_pos) break;
+                    uint32_t blk = (dcur >> 2) + lane; uint32_t o[4];
+                    S.block(E_REAL, blk, o);
+                    uint32_t hit = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t d = blk * 4 + q;
+                        if (d >= dcur && (8 + (d - dbase)) < dend_pos && o[q] < ap.thr_ber) hit |= 1u << q;
+                    }
+                    uint32_t any = __ballot_sync(0xffffffffu, hit != 0);
+                    if (!any) { dcur = ((dcur >> 2) + 32) << 2; continue; }
+                    int hl = __ffs(any) - 1;
+                    uint32_t hq = __shfl_sync(0xffffffffu, hit, hl);
+                    uint32_t dh = ((dcur >> 2) + hl) * 4 + (__ffs(hq) - 1);
+                    uint32_t j = 8 + (dh - dbase);
+                    uint32_t base = tmpl_base(g, T, terr, tnerr, spos + j);
+                    uint32_t nb, extra = 0;
+                    if (FROM_FRAG) { do { nb = S.at(E_INT, ci++) >> 30; } while (nb == base); }               // Fragment.cpp:110
+                    else { do { nb = S.at(E_REAL, dh + 1 + extra) >> 30; extra++; } while (nb == base); }       // Amplicon.cpp:213
+                    gc += (int)((nb == 1u) | (nb == 2u)) - (int)((base == 1u) | (base == 2u));
+                    if (nown < kMaxErrPerAmp) { if (lane == 0) errbuf[nown] = pack_err(j, nb); } else if (lane == 0) atomicOr(flags, 1);
+                    nown++;
+                    dcur = dh + 1 + extra; dbase += extra;
+                }
+                cr = dbase + (alen - 8);
+                if (nown > kMaxErrPerAmp) nown = kMaxErrPerAmp;
+                __syncwarp();
+                // ---- emit the product into slot (slot0 + made)
+                uint64_t ngstart; uint32_t nrc;
+                if (FROM_FRAG) {   // semi-amplicon template U = reverse complement of the copied window
+                    nrc = T.rc ^ 1u; ngstart = T.rc ? (T.gstart - spos - alen + 1) : (T.gstart + spos + alen - 1);
+                } else {           // full amplicon = window of U
+                    nrc = T.rc; ngstart = T.rc ? (T.gstart - spos) : (T.gstart + spos);
+                }
+                // error overlay of the product: inherited (semi errors inside the window) then own
+                uint32_t ninh = 0;
+                if (!FROM_FRAG) {
+                    for (uint32_t e = 0; e < tnerr; e++) {
+                        uint32_t v = terr[e], p = err_pos(v);
+                        if (p >= spos && p < spos + alen) {
+                            bool over = false;
+                            for (uint32_t q = 0; q < nown; q++) over |= (err_pos(errbuf[q]) == p - spos);
+                            if (!over) { if (nown + ninh < kMaxErrPerAmp) { if (lane == 0) errbuf[nown + ninh] = pack_err(p - spos, err_base(v)); ninh++; } else if (lane == 0) atomicOr(flags, 1); }
+                        }
+                    }
+                    __syncwarp();
+                }
+                uint32_t ntot = nown + ninh;
+                unsigned long long eoff = 0;
+                if (ntot) {
+                    if (lane == 0) eoff = atomicAdd(err_top, (unsigned long long)ntot);
+                    eoff = __shfl_sync(0xffffffffu, eoff, 0);
+                    if (eoff + ntot > err_cap) { if (lane == 0) atomicOr(flags, 2); ntot = 0; eoff = 0; }
+                    for (uint32_t q = lane; q < ntot; q += 32) {
+                        uint32_t v = errbuf[q];
+                        // own errors of a semi are recorded in copied-window coordinates; its template is the reverse complement
+                        if (FROM_FRAG) v = pack_err(alen - 1 - err_pos(v), 3u - err_base(v));
+                        err_pool[eoff + q] = v;
+                    }
+                }
+                if (lane == 0) {
+                    uint64_t slot = slot0 + made;
+                    out_desc[slot] = pack_desc(ngstart, nrc, alen);
+                    out_gc[slot] = (uint32_t)max(0, gc);
+                    out_errref[slot] = ((uint64_t)eoff << 16) | ntot;
+                }
+                made++;
+                __syncwarp();
+            }
+            if (lane == 0) created[t] = made;
+        }
+    }
+}
+
+// move products from per-template slots into list order: batch position = total-1-(creation rank)
+__global__ void __launch_bounds__(256) compact_products_kernel(uint64_t n_tmpl, const uint32_t* __restrict__ created, const uint64_t* __restrict__ cprefix,
+                                                               const uint64_t* __restrict__ slot_off, const uint64_t* __restrict__ tdesc,
+                                                               const uint32_t* __restrict__ tgc, const uint64_t* __restrict__ terr, uint64_t local_total,
+                                                               uint64_t* __restrict__ ldesc, uint32_t* __restrict__ lgc, uint64_t* __restrict__ lerr,
+                                                               uint32_t* __restrict__ lprimers, uint64_t list_base) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tmpl) return;
+    uint32_t m = created[t];
+    if (!m) return;
+    uint64_t s0 = slot_off[t], r0 = cprefix[t];
+    for (uint32_t i = 0; i < m; i++) {
+        uint64_t dst = list_base + (local_total - 1 - (r0 + i));
+        ldesc[dst] = tdesc[s0 + i]; lgc[dst] = tgc[s0 + i]; lerr[dst] = terr[s0 + i];
+        if (lprimers) lprimers[dst] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------- host driver
+namespace {
+
+struct Round {
+    scs_ctx* c; Genome g; uint32_t thr_ber;
+    DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
+    DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created;
+
+    int allreduce_u64(uint64_t* v, size_t n) {
+        if (c->P.world <= 1) return SCS_OK;
+        if (!c->ar_u64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
+        return c->ar_u64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
+    }
+
+    // Malbac::setPrimers (Malbac.cpp:236-283)
+    int set_primers(bool onlyFrags, int round) {
+        uint64_t nF = c->frag_hi - c->frag_lo, nS = onlyFrags ? 0 : c->semis.n;
+        // global template count and total length (lengths are integers: the FP64 sum is exact in any order)
+        uint64_t g3[3] = {0, 0, 0};
+        g3[0] = c->frags.size();
+        for (auto& f : c->frags) g3[1] += (uint64_t)f.len;
+        uint64_t loc[2] = {nS, 0};
+        if (nS) {
+            // sum of semi lengths: small host reduction over the descriptors would cost a copy; use a device pass
+            std::vector<uint64_t> h(nS);
+            SCS_CUDA(c, cudaMemcpyAsync(h.data(), c->semis.desc.p, nS * 8, cudaMemcpyDeviceToHost, c->st));
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            for (uint64_t i = 0; i < nS; i++) loc[1] += unpack_desc(h[i]).len;
+        }
+        if (int rc = allreduce_u64(loc, 2)) return rc;
+        uint64_t templateNum = g3[0] + loc[0];
+        double totalLen = (double)(g3[1] + loc[1]);
+        uint64_t expected = (uint64_t)((double)c->total_primers * c->P.gamma * (double)templateNum);
+        SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
+        // global template index: fragments first, then semis in list order (this rank's semis sit at their global list index)
+        uint64_t ebase = (uint64_t)round << 40;
+        if (nF) {
+            assign_primers_kernel<<<(unsigned)((nF + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ebase + c->frag_lo, mark_base(D_POIS, round) + c->frag_lo,
+                                                                                  c->frag_desc.p, nF, (double)expected, totalLen, 0xFFFFFFFFu, c->frag_primers.p, dcount.p);
+            SCS_LAUNCHED(c);
+        }
+        if (nS) {
+            if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "multi-rank semi indexing requires single-batch layout");   // replaced below by per-batch launches
+            assign_primers_kernel<<<(unsigned)((nS + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ebase + c->frags.size(), mark_base(D_POIS, round) + c->frags.size(),
+                                                                                  c->semis.desc.p, nS, (double)expected, totalLen, 0xFFFu, c->semis.primers.p, dcount.p);
+            SCS_LAUNCHED(c);
+        }
+        uint64_t count = 0;
+        SCS_CUDA(c, cudaMemcpyAsync(&count, dcount.p, 8, cudaMemcpyDeviceToHost, c->st));
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        if (int rc = allreduce_u64(&count, 1)) return rc;
+        c->total_primers -= count;   // unsigned wrap as in the reference (unsigned long, Malbac.h:29)
+        return SCS_OK;
+    }
+
+    // index of the first mark of `round` inside the replay mark array of a domain
+    uint64_t mark_base(int domain, int round) {
+        if (!c->replay.on) return 0;
+        const std::vector<uint64_t>& m = c->replay.hmarks[domain];
+        uint64_t n = m.size() / 3, lo = 0, hi = n;   // marks are sorted by entity = round<<40 | index
+        uint64_t key = (uint64_t)round << 40;
+        while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (m[3 * mid] < key) lo = mid + 1; else hi = mid; }
+        return lo;
+    }
+
+    // one amplification pass over `n` templates; products appended to `dst`
+    template <bool FROM_FRAG>
+    int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, uint64_t tmpl_global0, AmpList& dst,
+             std::vector<uint64_t>& batch_total, std::vector<uint64_t>& batch_before, std::vector<uint64_t>& batch_local) {
+        uint64_t total_slots = 0;
+        SCS_CUDA(c, slot_off.reserve(n + 1)); SCS_CUDA(c, cprefix.reserve(n + 1)); SCS_CUDA(c, created.reserve(n + 1));
+        uint64_t made_total = 0;
+        if (n) {
+            if (int rc = exclusive_scan_u32(c, primers, slot_off.p, n, &total_slots)) return rc;
+            SCS_CUDA(c, tdesc.reserve(total_slots + 1)); SCS_CUDA(c, terr.reserve(total_slots + 1)); SCS_CUDA(c, tgc.reserve(total_slots + 1));
+            // error pool: own errors ~ ber * 2000 per product, inherited about as many; 8x head-room, retried on overflow
+            uint64_t etop = 0;
+            SCS_CUDA(c, cudaMemcpyAsync(&etop, c->err_top.p, 8, cudaMemcpyDeviceToHost, c->st));
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            uint64_t need = etop + total_slots * 12 + 4096;
+            SCS_CUDA(c, c->err_pool.reserve(need, etop, c->st));
+            SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(ticket.p, 0, 8, c->st));
+            AmpParams ap; ap.thr_ber = thr_ber; ap.entity_base = ((uint64_t)round << 40) + tmpl_global0;
+            ap.mark_base = mark_base(FROM_FRAG ? D_AMPF : D_AMPS, round) + tmpl_global0;
+            int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (FROM_FRAG) {
+                constexpr int W = 4, BW = (100000 + 32) / 32 + 1;
+                size_t sm = (size_t)W * (BW + kMaxErrPerAmp) * 4;
+                auto kern = amplify_kernel<true, BW, W>;
+                SCS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                kern<<<sms * 4, W * 32, sm, c->st>>>(g, draw_src(c, D_AMPF), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
+                                                     c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p);
+            } else {
+                constexpr int W = 8, BW = (kAmpMax + 32) / 32 + 1;
+                size_t sm = (size_t)W * (BW + kMaxErrPerAmp) * 4;
+                auto kern = amplify_kernel<false, BW, W>;
+                kern<<<sms * 8, W * 32, sm, c->st>>>(g, draw_src(c, D_AMPS), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
+                                                     c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p);
+            }
+            SCS_LAUNCHED(c);
+            int hflags = 0;
+            SCS_CUDA(c, cudaMemcpyAsync(&hflags, flags.p, 4, cudaMemcpyDeviceToHost, c->st));
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            if (hflags & 2) return c->fail(SCS_E_NOMEM, "amplify: error pool overflow");
+            if (hflags & 1) return c->fail(SCS_E_UNSUPPORTED, "amplify: more than 96 substitutions on one amplicon");
+            if (int rc = exclusive_scan_u32(c, created.p, cprefix.p, n, &made_total)) return rc;
+        }
+        // list geometry across ranks: this rank's creations are a contiguous run of the batch's creation order
+        std::vector<uint64_t> per_rank((size_t)std::max(1, c->P.world), 0);
+        per_rank[c->P.rank] = made_total;
+        if (int rc = allreduce_u64(per_rank.data(), per_rank.size())) return rc;
+        uint64_t gtot = 0, before = 0;
+        for (int r = 0; r < (int)per_rank.size(); r++) { if (r < c->P.rank) before += per_rank[r]; gtot += per_rank[r]; }
+        batch_total.push_back(gtot); batch_before.push_back(before); batch_local.push_back(made_total);
+        uint64_t old = dst.n;
+        SCS_CUDA(c, dst.desc.reserve(old + made_total + 1, old, c->st)); SCS_CUDA(c, dst.gc.reserve(old + made_total + 1, old, c->st));
+        SCS_CUDA(c, dst.errref.reserve(old + made_total + 1, old, c->st));
+        if (FROM_FRAG) SCS_CUDA(c, dst.primers.reserve(old + made_total + 1, old, c->st));
+        if (made_total) {
+            compact_products_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(n, created.p, cprefix.p, slot_off.p, tdesc.p, tgc.p, terr.p, made_total,
+                                                                                   dst.desc.p, dst.gc.p, dst.errref.p, FROM_FRAG ? dst.primers.p : nullptr, old);
+            SCS_LAUNCHED(c);
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        }
+        dst.n = old + made_total; dst.batch_end.push_back(dst.n);
+        return SCS_OK;
+    }
+};
+
+}  // namespace
+
+int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
+    if (!c->have_frags) return c->fail(SCS_E_STATE, "scs_amplify: call scs_create_frags first");
+    if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "scs_amplify: multi-rank amplification is not wired yet");
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
+    Round R; R.c = c; R.g.words = c->genome_words.p; R.g.n_bases = c->genome_bases;
+    R.thr_ber = (uint32_t)std::min<uint64_t>(count_unit_lt(3.4e-4), 0xFFFFFFFFull);
+    SCS_CUDA(c, R.dcount.reserve(1)); SCS_CUDA(c, R.ticket.reserve(1)); SCS_CUDA(c, R.flags.reserve(1));
+    // createPrimers (Malbac.cpp:36-81): 4^8 primer types, -p copies each
+    std::vector<long long> pc(65536, (long long)c->P.primers);
+    SCS_CUDA(c, c->primer_counts.reserve(65536));
+    SCS_CUDA(c, cudaMemcpyAsync(c->primer_counts.p, pc.data(), 65536 * 8, cudaMemcpyHostToDevice, c->st));
+    c->total_primers = 65536ull * (uint64_t)c->P.primers;
+    SCS_CUDA(c, c->err_top.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(c->err_top.p, 0, 8, c->st));
+    SCS_CUDA(c, c->err_pool.reserve(4096));
+    c->semis.clear(); c->fulls.clear();
+    c->semi_batch_total.clear(); c->semi_batch_before.clear(); c->semi_batch_local.clear();
+    c->full_batch_total.clear(); c->full_batch_before.clear(); c->full_batch_local.clear();
+    const uint64_t nF = c->frag_hi - c->frag_lo;
+    int rc;
+    if ((rc = R.set_primers(true, 0))) return rc;
+    if ((rc = R.pass<true>(0, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->frag_lo, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+    for (int i = 0; i < 5; i++) {
+        if (c->total_primers == 0) break;
+        if ((rc = R.set_primers(false, i + 1))) return rc;
+        if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, 0, c->fulls, c->full_batch_total, c->full_batch_before, c->full_batch_local))) return rc;
+        if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->frag_lo, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+    }
+    cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_amplify = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->stats.n_semis = c->semis.n; c->stats.n_fulls = c->fulls.n;
+    c->stats.n_semis_global = 0; for (auto v : c->semi_batch_total) c->stats.n_semis_global += v;
+    c->stats.n_fulls_global = 0; for (auto v : c->full_batch_total) c->stats.n_fulls_global += v;
+    c->stats.total_primers_left = c->total_primers;
+    c->amplified = true; c->have_counts = false;
+    return SCS_OK;
+}
+
+}  // namespace scs

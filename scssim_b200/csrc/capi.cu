@@ -1,0 +1,274 @@
+// extern "C" surface of libscssim_b200.so (see include/scssim_b200.h for the reference call each
+// function replaces). Thin: argument validation with the reference's messages, stage ordering, dumps.
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.h"
+
+using namespace scs;
+
+static std::string g_create_error;
+
+extern "C" {
+
+const char* scs_version(void) { return "scssim_b200 0.1 (sm_100a)"; }
+
+void scs_default_params(scs_params* p) {
+    memset(p, 0, sizeof(*p));
+    p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->slab_bytes = 0;
+}
+
+int scs_create(const scs_params* p, scs_ctx** out) {
+    if (!p || !out) { g_create_error = "scs_create: null argument"; return SCS_E_ARG; }
+    *out = nullptr;
+    // validation of parseArgs_genReads (src/scssim.cpp:355-393), same messages
+    if (p->primers < 1000) { g_create_error = "Error: the value of parameter \"primers\" should be at least 1000!"; return SCS_E_ARG; }
+    if (p->gamma <= 0 || p->gamma > 1e-8) { g_create_error = "Error: the value of parameter \"gamma\" should be in 0~1e-8!"; return SCS_E_ARG; }
+    if (p->coverage <= 0) { g_create_error = "Error: sequencing coverage not properly specified!"; return SCS_E_ARG; }
+    if (p->world < 1 || p->rank < 0 || p->rank >= p->world) { g_create_error = "scs_create: bad rank/world"; return SCS_E_ARG; }
+    scs_ctx* c = new scs_ctx();
+    c->P = *p;
+    if (p->device >= 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n <= p->device) {
+            g_create_error = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") + "); the genreads path has no CPU fallback";
+            delete c; return SCS_E_CUDA;
+        }
+        if (cudaSetDevice(p->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+            g_create_error = std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()); delete c; return SCS_E_CUDA;
+        }
+        c->have_device = true;
+    }
+    *out = c;
+    return SCS_OK;
+}
+
+void scs_destroy(scs_ctx* c) {
+    if (!c) return;
+    if (c->have_device) {
+        cudaSetDevice(c->P.device);
+        cudaDeviceSynchronize();
+        for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) if (c->slab_host[b][f]) cudaFreeHost(c->slab_host[b][f]);
+        if (c->st) cudaStreamDestroy(c->st);
+        if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    }
+    delete c;
+}
+
+const char* scs_last_error(const scs_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int scs_load_profile(scs_ctx* c, const char* path) {
+    if (!c || !path) return SCS_E_ARG;
+    if (!c->prof.load(path, c->P.paired != 0, c->P.isize)) return c->fail(SCS_E_IO, c->prof.error);
+    c->have_profile = true; c->have_counts = false;
+    return upload_profile(c);
+}
+int scs_read_length(const scs_ctx* c) { return (c && c->have_profile) ? c->prof.readLength : -1; }
+
+int scs_load_genome(scs_ctx* c, const char* path) {
+    if (!c || !path) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
+    cudaSetDevice(c->P.device);
+    return genome_from_fasta(c, path);
+}
+int scs_set_genome(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens) {
+    if (!c || !names || !seqs || !lens) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
+    cudaSetDevice(c->P.device);
+    return genome_from_host(c, n, names, seqs, lens);
+}
+
+int scs_set_collectives(scs_ctx* c, scs_allreduce_u64_fn fu, scs_allreduce_f64_fn fd, void* user) {
+    if (!c) return SCS_E_ARG;
+    c->ar_u64 = fu; c->ar_f64 = fd; c->ar_user = user;
+    return SCS_OK;
+}
+
+int scs_create_frags(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return create_frags(c); }
+int scs_amplify(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return amplify(c); }
+int scs_set_read_counts(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return set_read_counts(c); }
+int scs_yield_reads_sink(scs_ctx* c, scs_sink_fn sink, void* user) {
+    if (!c) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device);
+    return yield_reads(c, sink, user);
+}
+
+namespace { struct FileSink { FILE* f[2]; }; }
+static int file_sink(void* user, int file, const char* data, size_t n) {
+    FileSink* s = (FileSink*)user;
+    return fwrite(data, 1, n, s->f[file]) == n ? 0 : 1;
+}
+int scs_yield_reads(scs_ctx* c, const char* prefix) {   // Malbac.cpp:426-435: <prefix>_1.fq/_2.fq or <prefix>.fq
+    if (!c || !prefix) return SCS_E_ARG;
+    std::string base = prefix;
+    if (c->P.world > 1) base += ".rank" + std::to_string(c->P.rank);
+    FileSink s{{nullptr, nullptr}};
+    std::string n1 = c->P.paired ? base + "_1.fq" : base + ".fq", n2 = base + "_2.fq";
+    s.f[0] = fopen(n1.c_str(), "wb");
+    if (!s.f[0]) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n1);
+    if (c->P.paired) { s.f[1] = fopen(n2.c_str(), "wb"); if (!s.f[1]) { fclose(s.f[0]); return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n2); } }
+    setvbuf(s.f[0], nullptr, _IOFBF, 8 << 20); if (s.f[1]) setvbuf(s.f[1], nullptr, _IOFBF, 8 << 20);
+    int rc = scs_yield_reads_sink(c, file_sink, &s);
+    fclose(s.f[0]); if (s.f[1]) fclose(s.f[1]);
+    return rc;
+}
+
+int scs_get_stats(const scs_ctx* c, scs_stats* out) {
+    if (!c || !out) return SCS_E_ARG;
+    *out = c->stats;
+    out->n_frags = c->frags.size();
+    return SCS_OK;
+}
+
+int scs_set_replay(scs_ctx* c, const scs_replay* r) {
+    if (!c || !r) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device);
+    ReplayDev& R = c->replay;
+    const size_t pad = 8192;   // lanes may read a few draws past an entity's last one
+    auto up = [&](DevBuf<uint32_t>& b, const uint32_t* p, uint64_t n) -> cudaError_t {
+        cudaError_t e = b.reserve(n + pad); if (e != cudaSuccess) return e;
+        e = cudaMemset(b.p, 0, (n + pad) * 4); if (e != cudaSuccess) return e;
+        return n ? cudaMemcpy(b.p, p, n * 4, cudaMemcpyHostToDevice) : cudaSuccess;
+    };
+    SCS_CUDA(c, up(R.wreal, r->wreal, r->n_wreal)); SCS_CUDA(c, up(R.wint, r->wint, r->n_wint));
+    SCS_CUDA(c, up(R.mrand, r->mrand, r->n_mrand)); SCS_CUDA(c, up(R.mreal, r->mreal, r->n_mreal));
+    R.h_mrand.assign(r->mrand, r->mrand + r->n_mrand); R.h_mreal.assign(r->mreal, r->mreal + r->n_mreal);
+    SCS_CUDA(c, R.gcf.reserve(r->n_gcf + 16));
+    if (r->n_gcf) SCS_CUDA(c, cudaMemcpy(R.gcf.p, r->gcf, r->n_gcf * 8, cudaMemcpyHostToDevice));
+    for (int d = 0; d < 8; d++) {
+        std::vector<uint64_t>& h = R.hmarks[d];
+        h.assign(r->marks[d], r->marks[d] + 3 * r->n_marks[d]);
+        if (d == SCS_D_READ) {   // dropped slots never started an entity: make the table dense by slot id
+            uint64_t mx = 0; for (uint64_t i = 0; i < r->n_marks[d]; i++) mx = std::max(mx, h[3 * i] + 1);
+            std::vector<uint64_t> dense(3 * mx, 0);
+            for (uint64_t i = 0; i < r->n_marks[d]; i++) { uint64_t e = h[3 * i]; dense[3 * e] = e; dense[3 * e + 1] = h[3 * i + 1]; dense[3 * e + 2] = h[3 * i + 2]; }
+            h.swap(dense);
+        }
+        R.n_marks[d] = h.size() / 3;
+        SCS_CUDA(c, R.marks[d].reserve(h.size() + 16));
+        if (!h.empty()) SCS_CUDA(c, cudaMemcpy(R.marks[d].p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+    }
+    R.on = true;
+    return SCS_OK;
+}
+
+int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
+    if (!c) return SCS_E_ARG;
+    if (what == SCS_DUMP_FRAGS) {
+        uint64_t need = c->frags.size() * 5 * 8;
+        if (!buf) return (int64_t)need;
+        if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
+        std::vector<uint32_t> pr(c->frag_hi - c->frag_lo);
+        if (!pr.empty() && c->have_device) cudaMemcpy(pr.data(), c->frag_primers.p, pr.size() * 4, cudaMemcpyDeviceToHost);
+        int64_t* o = (int64_t*)buf;
+        for (size_t i = 0; i < c->frags.size(); i++) {
+            const HostFrag& f = c->frags[i];
+            o[5 * i] = f.seq; o[5 * i + 1] = f.start0; o[5 * i + 2] = f.len; o[5 * i + 3] = f.strand;
+            o[5 * i + 4] = (i >= c->frag_lo && i < c->frag_hi) ? (int64_t)pr[i - c->frag_lo] : -1;
+        }
+        return (int64_t)need;
+    }
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device);
+    if (what == SCS_DUMP_SEMIS || what == SCS_DUMP_FULLS) {
+        AmpList& L = what == SCS_DUMP_SEMIS ? c->semis : c->fulls;
+        uint64_t need = L.n * 6 * 8;
+        if (!buf) return (int64_t)need;
+        if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
+        std::vector<uint64_t> d(L.n), e(L.n); std::vector<uint32_t> g(L.n), p(L.n, 0);
+        if (L.n) {
+            cudaMemcpy(d.data(), L.desc.p, L.n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(e.data(), L.errref.p, L.n * 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(g.data(), L.gc.p, L.n * 4, cudaMemcpyDeviceToHost);
+            if (what == SCS_DUMP_SEMIS) cudaMemcpy(p.data(), L.primers.p, L.n * 4, cudaMemcpyDeviceToHost);
+        }
+        uint64_t* o = (uint64_t*)buf;
+        for (uint64_t i = 0; i < L.n; i++) { Tmpl t = unpack_desc(d[i]); o[6 * i] = t.gstart; o[6 * i + 1] = t.rc; o[6 * i + 2] = t.len; o[6 * i + 3] = g[i]; o[6 * i + 4] = p[i]; o[6 * i + 5] = e[i] & 0xFFFF; }
+        return (int64_t)need;
+    }
+    if (what == SCS_DUMP_COUNTS || what == SCS_DUMP_WEIGHTS) {
+        if (!c->have_counts) return c->fail(SCS_E_STATE, "scs_dump: read counts not computed");
+        uint64_t es = what == SCS_DUMP_COUNTS ? 4 : 8, need = c->fulls.n * es;
+        if (!buf) return (int64_t)need;
+        if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
+        if (need) cudaMemcpy(buf, what == SCS_DUMP_COUNTS ? (void*)c->counts.p : (void*)c->weights.p, need, cudaMemcpyDeviceToHost);
+        return (int64_t)need;
+    }
+    if (what == SCS_DUMP_PRIMER_COUNTS) {
+        uint64_t need = 65536 * 8;
+        if (!buf) return (int64_t)need;
+        if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
+        if (!c->amplified) return c->fail(SCS_E_STATE, "scs_dump: not amplified");
+        cudaMemcpy(buf, c->primer_counts.p, need, cudaMemcpyDeviceToHost);
+        return (int64_t)need;
+    }
+    if (what == SCS_DUMP_FULL_SEQ) {
+        int64_t w = 0;
+        int rc = dump_full_seqs(c, (char*)buf, cap, &w);
+        return rc ? rc : w;
+    }
+    return c->fail(SCS_E_ARG, "scs_dump: unknown selector");
+}
+
+int scs_test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
+                     uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len) {
+    if (!c) return SCS_E_ARG;
+    if (c->have_device) cudaSetDevice(c->P.device);
+    return test_predict(c, src, n_reads, is_read1, real, stride_real, ints, stride_int, out_seq, out_qual, out_stride, out_len);
+}
+
+static __global__ void philox_test_kernel(const uint32_t* ck, uint32_t* out) { philox4x32_10(ck[0], ck[1], ck[2], ck[3], ck[4], ck[5], out); }
+static __global__ void det_log_test_kernel(const double* x, int n, double* out) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = det_log(x[i]); }
+
+int scs_test_philox(scs_ctx* c, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!c) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device);
+    DevBuf<uint32_t> d; SCS_CUDA(c, d.reserve(16));
+    uint32_t h[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
+    SCS_CUDA(c, cudaMemcpy(d.p, h, 24, cudaMemcpyHostToDevice));
+    philox_test_kernel<<<1, 1, 0, c->st>>>(d.p, d.p + 8); SCS_LAUNCHED(c);
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    SCS_CUDA(c, cudaMemcpy(out, d.p + 8, 16, cudaMemcpyDeviceToHost));
+    return SCS_OK;
+}
+int scs_test_det_log(scs_ctx* c, const double* x, int n, double* out) {
+    if (!c) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device);
+    DevBuf<double> a, b; SCS_CUDA(c, a.reserve(n + 1)); SCS_CUDA(c, b.reserve(n + 1));
+    SCS_CUDA(c, cudaMemcpy(a.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    det_log_test_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(a.p, n, b.p); SCS_LAUNCHED(c);
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    SCS_CUDA(c, cudaMemcpy(out, b.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SCS_OK;
+}
+
+int scs_profile_thresholds(const scs_ctx* c, int which, int idx, int row, uint32_t* out, int cap, int* eff) {
+    if (!c || !c->have_profile) return SCS_E_STATE;
+    const HostProfile& P = c->prof;
+    const uint32_t* src = nullptr; int n = 0, e = 0;
+    switch (which) {
+        case 0: src = P.insThr.thr.data(); n = (int)P.insThr.thr.size(); e = P.insThr.eff; break;
+        case 1: src = P.delThr.thr.data(); n = (int)P.delThr.thr.size(); e = P.delThr.eff; break;
+        case 2: if (!P.hasISize) return SCS_E_STATE; src = P.iSizeThr.thr.data(); n = (int)P.iSizeThr.thr.size(); e = P.iSizeThr.eff; break;
+        case 3: case 4: {
+            const std::vector<uint32_t>& t = which == 3 ? P.subsThr1 : P.subsThr2;
+            if (t.empty() || idx < 0 || idx >= P.kmerCount || row < 0 || row >= P.bins) return SCS_E_ARG;
+            src = &t[((size_t)idx * P.bins + row) * 4]; n = 4; e = (int)src[3]; break;
+        }
+        case 5:
+            if (idx < 0 || idx >= 16 || row < 0 || row >= P.bins) return SCS_E_ARG;
+            src = &P.qualThr[((size_t)idx * P.bins + row) * kQualN]; n = kQualN; e = P.qualEff[(size_t)idx * P.bins + row]; break;
+        default: return SCS_E_ARG;
+    }
+    if (eff) *eff = e;
+    for (int i = 0; i < n && i < cap; i++) out[i] = (which == 3 || which == 4) && i == 3 ? 0xFFFFFFFFu : src[i];
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// Context object behind the C ABI: owns every device / pinned allocation of one genreads run.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/scssim_b200.h"
+#include "device_common.cuh"
+#include "profile_host.h"
+
+namespace scs {
+
+// growable device array (host-managed capacity)
+template <class T> struct DevBuf {
+    T* p = nullptr; size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    // ensure capacity >= n, keeping the first `keep` elements
+    cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = n + n / 8 + 1024;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) { cudaFree(q); return e; } cudaStreamSynchronize(st); }
+        if (p) cudaFree(p);
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+};
+
+struct HostFrag { int32_t seq; int64_t start0; int32_t len; int32_t strand; };
+
+// amplicon list (semi or full), structure of arrays, list order = the reference's -t 1 order
+struct AmpList {
+    DevBuf<uint64_t> desc;     // gstart | rc | len
+    DevBuf<uint32_t> gc;
+    DevBuf<uint64_t> errref;   // err pool offset << 16 | count
+    DevBuf<uint32_t> primers;  // semis only
+    uint64_t n = 0;
+    std::vector<uint64_t> batch_end;
+    void clear() { desc.release(); gc.release(); errref.release(); primers.release(); n = 0; batch_end.clear(); }
+};
+
+struct ReplayDev {
+    bool on = false;
+    DevBuf<uint32_t> wreal, wint, mrand, mreal;
+    DevBuf<double> gcf;
+    DevBuf<uint64_t> marks[8];
+    std::vector<uint64_t> hmarks[8];   // host copies (entity, off_real, off_int)
+    uint64_t n_marks[8] = {0};
+    std::vector<uint32_t> h_mrand, h_mreal;
+};
+
+// device-resident threshold tables
+struct DevProfile {
+    DevBuf<uint32_t> subs1, subs2, qual, ins, del, isize;
+    DevBuf<uint8_t> qualEff;
+    DevBuf<uint32_t> qualDiag;   // [4][bins][kDiagW] compact diagonal rows for shared memory
+    DevBuf<uint32_t> qualDiagMeta;   // [4][bins]: lo | (n << 8)
+    int diagW = 0; bool diagOK = false;
+};
+
+}  // namespace scs
+
+struct scs_ctx {
+    scs_params P;
+    bool have_device = false;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::string err;
+    scs::HostProfile prof; bool have_profile = false;
+    scs::DevProfile dprof;
+
+    // genome
+    std::vector<std::string> seq_names; std::vector<uint64_t> seq_len, seq_goff;   // goff in bases, 32-aligned
+    scs::DevBuf<uint64_t> genome_words; uint64_t genome_bases = 0; bool have_genome = false;
+    uint64_t ref_len_half = 0;
+
+    // fragments
+    std::vector<scs::HostFrag> frags; uint64_t frag_lo = 0, frag_hi = 0;   // this rank's global range
+    scs::DevBuf<uint64_t> frag_desc; scs::DevBuf<uint32_t> frag_primers; bool have_frags = false;
+
+    scs::AmpList semis, fulls;
+    scs::DevBuf<uint32_t> err_pool; scs::DevBuf<unsigned long long> err_top;   // err_top[0] = next free slot
+    scs::DevBuf<long long> primer_counts; uint64_t total_primers = 0;
+    bool amplified = false;
+    // global (all ranks) list geometry, per batch
+    std::vector<uint64_t> semi_batch_total, semi_batch_before, full_batch_total, full_batch_before;   // totals and this rank's creation prefix
+    std::vector<uint64_t> semi_batch_local, full_batch_local;
+
+    // read allocation
+    scs::DevBuf<double> weights; scs::DevBuf<uint32_t> counts; scs::DevBuf<uint64_t> slot_base; bool have_counts = false;
+    uint64_t reads_requested = 0, n_slots = 0;
+
+    scs::ReplayDev replay;
+    scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
+    scs_stats stats{};
+
+    // FASTQ slabs
+    scs::DevBuf<char> slab_dev[2][2];   // [buffer][file]
+    char* slab_host[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    uint64_t slab_cap = 0;
+
+    int fail(int code, const std::string& msg) { err = msg; return code; }
+};
+
+#define SCS_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return (ctx)->fail(SCS_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+#define SCS_LAUNCHED(ctx) ((ctx)->stats.kernel_launches++)
+
+namespace scs {
+// stage entry points (one .cu each)
+int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens);
+int genome_from_fasta(scs_ctx* c, const char* path);
+int upload_profile(scs_ctx* c);
+int create_frags(scs_ctx* c);
+int amplify(scs_ctx* c);
+int set_read_counts(scs_ctx* c);
+int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user);
+int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
+                 uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len);
+int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written);
+
+// draw source for a domain (Philox or replay tapes)
+DrawSrc draw_src(const scs_ctx* c, int domain);
+// host-side draw for the few serial decisions kept on the host (fragment lengths, leftover chunk draws)
+uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, uint64_t mark_index, uint64_t i);
+
+// device exclusive scan: out[i] = sum_{j<i} in[j] (u64), returns total through *total_dev (device pointer, may be null)
+int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
+}  // namespace scs

@@ -1,0 +1,146 @@
+// Device-side building blocks shared by every kernel of the genreads path:
+//  * Philox4x32-10 counter-based draws keyed by (seed, domain, engine, entity) — or, in replay
+//    mode, the same (entity, index) addressing into the recorded tapes of the reference;
+//  * the reference's uniform mappings reduced to exact integer arithmetic
+//    (/root/reference/lib/threadpool/ThreadPool.cpp:203-212);
+//  * det_log: a logarithm made only of IEEE +,-,*,/ so host and device agree bit for bit;
+//  * 2-bit packed genome access.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scs {
+
+enum Domain : int { D_FRAG = 0, D_POIS = 1, D_AMPF = 2, D_AMPS = 3, D_GCF = 4, D_MULTM = 5, D_MULTC = 6, D_READ = 7 };
+enum Engine : int { E_REAL = 0, E_INT = 1 };
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                       uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Where an entity's draws come from. tape == nullptr -> Philox.
+struct DrawSrc {
+    uint64_t seed;
+    const uint32_t* tape[2];   // replay: flat u32 tapes for E_REAL / E_INT of this domain
+    const uint64_t* marks;     // replay: triples (entity, off_real, off_int) in entity order of the domain
+};
+
+// Per-entity stream handle: (engine, i) -> u32
+struct Stream {
+    uint32_t k0, k1, e0, e1, dom2;       // Philox
+    const uint32_t* t[2];                // replay (already offset to the entity's first draw), or nullptr
+    __device__ __forceinline__ void init(const DrawSrc& s, int domain, uint64_t entity, uint64_t mark_index) {
+        k0 = (uint32_t)s.seed; k1 = (uint32_t)(s.seed >> 32);
+        e0 = (uint32_t)entity; e1 = (uint32_t)(entity >> 32); dom2 = (uint32_t)(domain * 2);
+        if (s.tape[0] != nullptr) {
+            t[0] = s.tape[0] + s.marks[3 * mark_index + 1];
+            t[1] = s.tape[1] + s.marks[3 * mark_index + 2];
+        } else { t[0] = nullptr; t[1] = nullptr; }
+    }
+    __device__ __forceinline__ bool replay() const { return t[0] != nullptr; }
+    // 4 consecutive draws i = 4*b .. 4*b+3
+    __device__ __forceinline__ void block(int engine, uint32_t b, uint32_t out[4]) const {
+        if (t[0] != nullptr) {
+            const uint32_t* p = t[engine] + 4ull * b;
+            out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3];
+        } else {
+            philox4x32_10(e0, e1, b, dom2 + (uint32_t)engine, k0, k1, out);
+        }
+    }
+    __device__ __forceinline__ uint32_t at(int engine, uint32_t i) const {
+        if (t[0] != nullptr) return t[engine][i];
+        uint32_t o[4];
+        philox4x32_10(e0, e1, i >> 2, dom2 + (uint32_t)engine, k0, k1, o);
+        return o[i & 3];
+    }
+};
+
+// start + (end-start) * (x / 2^32) truncated, for integer start/end with (end-start) < 2^21: exact
+// in FP64 (no rounding ever happens), hence this integer form is identical to the reference's.
+__host__ __device__ __forceinline__ uint32_t uni_trunc(uint32_t x, uint32_t start, uint32_t span) {
+    return start + (uint32_t)(((uint64_t)span * x) >> 32);
+}
+
+// number of leading thresholds <= x in a non-decreasing row
+__device__ __forceinline__ int count_le(const uint32_t* __restrict__ row, int n, uint32_t x) {
+    int lo = 0, hi = n;   // invariant: row[k] <= x for k < lo ; row[k] > x for k >= hi
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (row[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__host__ __device__ inline double det_log(double x) {
+    if (x <= 0.0) return -INFINITY;
+    int e;
+    double m = frexp(x, &e);
+    if (m < 0.70710678118654752440) { m = m * 2.0; e -= 1; }
+#ifdef __CUDA_ARCH__
+    double t = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
+    double t2 = __dmul_rn(t, t);
+    double s = 1.0 / 27.0;
+#define SCS_H(c) s = __dadd_rn(__dmul_rn(s, t2), (c))
+#else
+    double t = (m - 1.0) / (m + 1.0);
+    double t2 = t * t;
+    double s = 1.0 / 27.0;
+#define SCS_H(c) s = s * t2 + (c)
+#endif
+    SCS_H(1.0 / 25.0); SCS_H(1.0 / 23.0); SCS_H(1.0 / 21.0); SCS_H(1.0 / 19.0); SCS_H(1.0 / 17.0);
+    SCS_H(1.0 / 15.0); SCS_H(1.0 / 13.0); SCS_H(1.0 / 11.0); SCS_H(1.0 / 9.0); SCS_H(1.0 / 7.0);
+    SCS_H(1.0 / 5.0); SCS_H(1.0 / 3.0); SCS_H(1.0);
+#undef SCS_H
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+#ifdef __CUDA_ARCH__
+    double lm = __dmul_rn(__dmul_rn(2.0, t), s);
+    return __dadd_rn(__dmul_rn((double)e, LN2_HI), __dadd_rn(lm, __dmul_rn((double)e, LN2_LO)));
+#else
+    double lm = 2.0 * t * s;
+    return (double)e * LN2_HI + (lm + (double)e * LN2_LO);
+#endif
+}
+
+// ---- packed genome: 2 bits per base, 32 bases per u64 word, A=0 C=1 G=2 T=3 ----
+struct Genome {
+    const uint64_t* __restrict__ words;
+    uint64_t n_bases;
+};
+__device__ __forceinline__ uint32_t genome_base(const Genome& g, uint64_t pos) {
+    return (uint32_t)(__ldg(g.words + (pos >> 5)) >> ((pos & 31) * 2)) & 3u;
+}
+// base i of an oriented window: rc ? complement(G[gstart - i]) : G[gstart + i]
+__device__ __forceinline__ uint32_t window_base(const Genome& g, uint64_t gstart, int rc, uint32_t i) {
+    return rc ? (3u - genome_base(g, gstart - i)) : genome_base(g, gstart + i);
+}
+
+// Template descriptor shared by fragments, semi and full amplicons: an oriented genome window plus
+// a sparse overlay of substitutions. d0 = gstart(40) | rc(1) | len(17) ; errors = u32 pos(17)|base(2)<<17
+struct Tmpl {
+    uint64_t gstart; uint32_t len; uint32_t rc;
+};
+__host__ __device__ __forceinline__ uint64_t pack_desc(uint64_t gstart, uint32_t rc, uint32_t len) {
+    return gstart | ((uint64_t)rc << 40) | ((uint64_t)len << 41);
+}
+__host__ __device__ __forceinline__ Tmpl unpack_desc(uint64_t d) {
+    Tmpl t; t.gstart = d & ((1ull << 40) - 1); t.rc = (uint32_t)(d >> 40) & 1u; t.len = (uint32_t)(d >> 41) & 0x1FFFFu; return t;
+}
+__host__ __device__ __forceinline__ uint32_t pack_err(uint32_t pos, uint32_t base) { return pos | (base << 17); }
+__host__ __device__ __forceinline__ uint32_t err_pos(uint32_t e) { return e & 0x1FFFFu; }
+__host__ __device__ __forceinline__ uint32_t err_base(uint32_t e) { return (e >> 17) & 3u; }
+
+}  // namespace scs

@@ -1,0 +1,293 @@
+// K0 pack_genome: ASCII -> 2-bit packed genome in HBM, plus the host-side FASTA reader, the fragment
+// cutter and the device exclusive scan used by the later stages.
+//
+// Replaces Genome::loadRefSeq + FastaReference::getSubSequence + Fragment::createSequence
+// (/root/reference/lib/genome/Genome.cpp:176-198,272-278, lib/fastahack/Fasta.cpp:304-334,
+// lib/fragment/Fragment.cpp:40-50): instead of one fseek+fread+toupper copy per fragment and
+// strand, the whole genome is packed once (0.25 B/base) and every fragment / amplicon is an
+// oriented window into it. Genome::splitToFrags (Genome.cpp:753-782) stays a host loop: it is a
+// serial chain of ~2 draws per 55 kb.
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace scs {
+
+// ---------------------------------------------------------------------------- exclusive scan
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total, uint64_t* warp_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = lane < (kScanThreads / 32) ? warp_sums[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        if (lane < (kScanThreads / 32)) warp_sums[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return warp_sums[warp] + inc - v;
+}
+
+template <class TIn>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const TIn* __restrict__ in, uint64_t n, uint64_t* __restrict__ tile_sums) {
+    __shared__ uint64_t ws[kScanThreads / 32]; __shared__ uint64_t tot;
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) if (base + k < n) s += (uint64_t)in[base + k];
+    block_exclusive_scan(s, &tot, ws);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+template <class TIn>
+__global__ void __launch_bounds__(kScanThreads) scan_tiles(const TIn* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_offs,
+                                                           uint64_t* __restrict__ out) {
+    __shared__ uint64_t ws[kScanThreads / 32]; __shared__ uint64_t tot;
+    uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+    uint64_t v[kScanItems]; uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { v[k] = (base + k < n) ? (uint64_t)in[base + k] : 0; s += v[k]; }
+    uint64_t off = block_exclusive_scan(s, &tot, ws) + (tile_offs ? tile_offs[blockIdx.x] : 0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+}
+
+// recursive reduce-then-scan; no inter-block waiting
+template <class TIn> static int scan_rec(scs_ctx* c, const TIn* in, uint64_t* out, uint64_t n, uint64_t* total_dev) {
+    if (n == 0) return SCS_OK;
+    uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    DevBuf<uint64_t> sums, offs;
+    SCS_CUDA(c, sums.reserve(tiles + 1));
+    scan_tile_sums<TIn><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, sums.p); SCS_LAUNCHED(c);
+    if (tiles > 1) {
+        SCS_CUDA(c, offs.reserve(tiles + 1));
+        int rc = scan_rec<uint64_t>(c, sums.p, offs.p, tiles, total_dev);
+        if (rc) return rc;
+        scan_tiles<TIn><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, offs.p, out); SCS_LAUNCHED(c);
+    } else {
+        scan_tiles<TIn><<<1, kScanThreads, 0, c->st>>>(in, n, nullptr, out); SCS_LAUNCHED(c);
+        if (total_dev) SCS_CUDA(c, cudaMemcpyAsync(total_dev, sums.p, 8, cudaMemcpyDeviceToDevice, c->st));
+    }
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));   // temporaries die here
+    return SCS_OK;
+}
+
+int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host) {
+    DevBuf<uint64_t> tot;
+    SCS_CUDA(c, tot.reserve(1));
+    SCS_CUDA(c, cudaMemsetAsync(tot.p, 0, 8, c->st));
+    int rc = scan_rec<uint32_t>(c, in, out, n, tot.p);
+    if (rc) return rc;
+    if (total_host) { SCS_CUDA(c, cudaMemcpyAsync(total_host, tot.p, 8, cudaMemcpyDeviceToHost, c->st)); SCS_CUDA(c, cudaStreamSynchronize(c->st)); }
+    return SCS_OK;
+}
+
+// ------------------------------------------------------------------------------- K0 pack_genome
+// One thread packs 32 bases (two 16-byte loads) into one u64 word. Bases other than ACGT (any case)
+// raise a flag: N / IUPAC handling is SURVEY.md §8f row N4.
+__global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t* __restrict__ ascii, uint64_t n_bases, uint64_t* __restrict__ words,
+                                                          unsigned int* __restrict__ bad) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n_words = (n_bases + 31) >> 5;
+    if (w >= n_words) return;
+    uint64_t base = w << 5;
+    uint8_t b[32];
+    if (base + 32 <= n_bases && ((reinterpret_cast<uintptr_t>(ascii + base) & 15) == 0)) {
+        const uint4* p = reinterpret_cast<const uint4*>(ascii + base);
+        uint4 a = __ldg(p), d = __ldg(p + 1);
+        memcpy(b, &a, 16); memcpy(b + 16, &d, 16);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; k++) b[k] = (base + k < n_bases) ? ascii[base + k] : (uint8_t)'A';
+    }
+    uint64_t out = 0; unsigned int anybad = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        uint32_t ch = b[k] & 0xDFu;   // upper-case (Genome::getSubSequence toupper, Genome.cpp:274)
+        // A=0x41 C=0x43 G=0x47 T=0x54 -> (ch>>1)&3 = 0,1,3,2 ; fix G/T order with a xor
+        uint32_t code = (ch >> 1) & 3u; code ^= (code >> 1);
+        anybad |= (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T');
+        out |= (uint64_t)code << (2 * k);
+    }
+    words[w] = out;
+    if (anybad) atomicOr(bad, 1u);
+}
+
+static std::string ref_seq_name(const std::string& header) {   // lib/fastahack/Fasta.cpp:57-68
+    std::string name = header.substr(0, header.find_first_of(" \t"));
+    size_t i = name.find("chrom");
+    if (i == std::string::npos) { i = name.find("chr"); if (i != std::string::npos) name = name.substr(i + 3); }
+    else name = name.substr(i + 5);
+    return name;
+}
+
+int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens) {
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
+    if (n <= 0) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
+    c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear();
+    uint64_t goff = 0, refLen = 0;
+    for (int i = 0; i < n; i++) {
+        if (lens[i] >= (1ull << 31)) return c->fail(SCS_E_ARG, "sequence longer than 2^31-1 bases (lib/fastahack/Fasta.h:36)");
+        c->seq_names.push_back(ref_seq_name(names[i]));
+        c->seq_len.push_back(lens[i]); c->seq_goff.push_back(goff);
+        goff += (lens[i] + 31) & ~31ull;
+        // Malbac::yieldReads: refLen = sum of atoi(last '_' field) / 2 (Malbac.cpp:413-419)
+        const std::string& nm = c->seq_names.back();
+        size_t us = nm.rfind('_');
+        refLen += (uint64_t)atoi(us == std::string::npos ? nm.c_str() : nm.c_str() + us + 1);
+    }
+    if (goff >= (1ull << 40)) return c->fail(SCS_E_ARG, "genome too large");
+    c->ref_len_half = refLen / 2;
+    c->genome_bases = goff;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    SCS_CUDA(c, c->genome_words.reserve(goff / 32 + 2));
+    DevBuf<unsigned int> bad; SCS_CUDA(c, bad.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(bad.p, 0, 4, c->st));
+    // stage ASCII through a bounded device buffer
+    const uint64_t chunk = 256ull << 20;
+    DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(chunk));
+    cudaEventRecord(e0, c->st);
+    for (int i = 0; i < n; i++) {
+        for (uint64_t off = 0; off < lens[i]; off += chunk) {
+            uint64_t m = std::min(chunk, lens[i] - off);
+            SCS_CUDA(c, cudaMemcpyAsync(stage.p, seqs[i] + off, m, cudaMemcpyHostToDevice, c->st));
+            uint64_t nw = (m + 31) >> 5;
+            pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, c->genome_words.p + ((c->seq_goff[i] + off) >> 5), bad.p);
+            SCS_LAUNCHED(c);
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        }
+    }
+    cudaEventRecord(e1, c->st);
+    unsigned int hbad = 0;
+    SCS_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, c->st));
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_pack = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (hbad) return c->fail(SCS_E_UNSUPPORTED, "genome contains bases other than A/C/G/T (N / IUPAC support is not implemented yet)");
+    c->stats.n_sequences = n; c->stats.genome_bases = 0; for (auto l : c->seq_len) c->stats.genome_bases += l;
+    c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
+    return SCS_OK;
+}
+
+int genome_from_fasta(scs_ctx* c, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return c->fail(SCS_E_IO, std::string("could not open ") + path);
+    fseek(f, 0, SEEK_END); long long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<char> raw((size_t)sz + 1);
+    size_t got = sz > 0 ? fread(raw.data(), 1, (size_t)sz, f) : 0;
+    fclose(f);
+    raw[got] = '\n';
+    std::vector<std::string> names; std::vector<std::vector<char>> seqs;
+    // .fai side effect of FastaReference::open (lib/fastahack/Fasta.cpp:243-249): name, length, offset, line_blen, line_len
+    struct Fai { std::string name; uint64_t len, off; int blen, llen; };
+    std::vector<Fai> fai;
+    size_t pos = 0;
+    while (pos < got) {
+        char* s = &raw[pos];
+        char* e = (char*)memchr(s, '\n', got + 1 - pos);
+        size_t len = (size_t)(e - s);
+        size_t llen = len + 1;
+        if (len > 0 && s[len - 1] == '\r') len--;
+        if (len > 0 && s[0] == '>') {
+            names.push_back(std::string(s + 1, len - 1)); seqs.emplace_back();
+            std::string full(s + 1, len - 1);
+            fai.push_back({full.substr(0, full.find_first_of(" \t")), 0, (uint64_t)(pos + llen), 0, 0});
+        } else if (len > 0 && !seqs.empty()) {
+            seqs.back().insert(seqs.back().end(), s, s + len);
+            if (fai.back().blen == 0) { fai.back().blen = (int)len; fai.back().llen = (int)llen; }
+        }
+        pos += llen;
+    }
+    if (seqs.empty()) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
+    std::string faiPath = std::string(path) + ".fai";
+    if (FILE* t = fopen(faiPath.c_str(), "rb")) fclose(t);
+    else if (FILE* o = fopen(faiPath.c_str(), "wb")) {
+        for (size_t i = 0; i < fai.size(); i++) fprintf(o, "%s\t%llu\t%llu\t%d\t%d\n", fai[i].name.c_str(), (unsigned long long)seqs[i].size(), (unsigned long long)fai[i].off, fai[i].blen, fai[i].llen);
+        fclose(o);
+    }
+    std::vector<const char*> np, sp; std::vector<uint64_t> lens;
+    for (size_t i = 0; i < seqs.size(); i++) { np.push_back(names[i].c_str()); sp.push_back(seqs[i].data()); lens.push_back(seqs[i].size()); }
+    return genome_from_host(c, (int)seqs.size(), np.data(), sp.data(), lens.data());
+}
+
+// ------------------------------------------------------------------------------ fragments (host)
+DrawSrc draw_src(const scs_ctx* c, int domain) {
+    DrawSrc s; s.seed = c->P.seed; s.tape[0] = s.tape[1] = nullptr; s.marks = nullptr;
+    if (c->replay.on) {
+        switch (domain) {
+            case D_FRAG: case D_POIS: s.tape[0] = c->replay.mrand.p; s.tape[1] = c->replay.mrand.p; break;
+            case D_MULTM: s.tape[0] = c->replay.mreal.p; s.tape[1] = c->replay.mreal.p; break;
+            default: s.tape[0] = c->replay.wreal.p; s.tape[1] = c->replay.wint.p; break;
+        }
+        s.marks = c->replay.marks[domain].p;
+    }
+    return s;
+}
+
+uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, uint64_t mark_index, uint64_t i) {
+    if (c->replay.on) {
+        const std::vector<uint32_t>& t = (domain == D_MULTM) ? c->replay.h_mreal : c->replay.h_mrand;
+        uint64_t off = c->replay.hmarks[domain][3 * mark_index + 1 + engine] + i;
+        return off < t.size() ? t[off] : 0u;
+    }
+    uint32_t o[4];
+    philox4x32_10((uint32_t)entity, (uint32_t)(entity >> 32), (uint32_t)(i >> 2), (uint32_t)(domain * 2 + engine), (uint32_t)c->P.seed,
+                  (uint32_t)(c->P.seed >> 32), o);
+    return o[i & 3];
+}
+
+int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782
+    if (!c->have_genome) return c->fail(SCS_E_STATE, "scs_create_frags: no genome loaded");
+    const uint32_t fragMin = 10000, fragMax = 100000;   // Fragment.cpp:15-16
+    std::vector<HostFrag> all;
+    for (size_t s = 0; s < c->seq_len.size(); s++) {
+        int64_t chrLen = (int64_t)c->seq_len[s], start = 1; uint64_t i = 0;
+        while (start <= chrLen) {
+            int32_t fl = (int32_t)uni_trunc(host_draw(c, D_FRAG, E_REAL, s, s, i++), fragMin, fragMax + 1 - fragMin);
+            if (start + fl - 1 > chrLen) break;
+            all.push_back({(int32_t)s, start - 1, fl, 1});
+            all.push_back({(int32_t)s, start - 1, fl, -1});
+            start += fl;
+        }
+        if (start <= chrLen) {   // tail emitted twice on strand +1 (quirk kept)
+            int32_t fl = (int32_t)(chrLen - start + 1);
+            all.push_back({(int32_t)s, start - 1, fl, 1});
+            all.push_back({(int32_t)s, start - 1, fl, 1});
+        }
+    }
+    c->stats.n_frags = all.size();
+    scs_shard_range(all.size(), c->P.rank, c->P.world, &c->frag_lo, &c->frag_hi);
+    c->frags = all;   // every rank keeps the (tiny) global table; it amplifies [frag_lo, frag_hi)
+    uint64_t nloc = c->frag_hi - c->frag_lo;
+    std::vector<uint64_t> desc(nloc);
+    for (uint64_t k = 0; k < nloc; k++) {
+        const HostFrag& f = all[c->frag_lo + k];
+        uint64_t g = c->seq_goff[f.seq] + (uint64_t)f.start0;
+        // amplification template = complement(stored): strand -1 -> genome forward, strand +1 -> reverse complement
+        desc[k] = f.strand == 1 ? pack_desc(g + f.len - 1, 1, (uint32_t)f.len) : pack_desc(g, 0, (uint32_t)f.len);
+    }
+    SCS_CUDA(c, c->frag_desc.reserve(nloc + 1)); SCS_CUDA(c, c->frag_primers.reserve(nloc + 1));
+    if (nloc) SCS_CUDA(c, cudaMemcpyAsync(c->frag_desc.p, desc.data(), nloc * 8, cudaMemcpyHostToDevice, c->st));
+    SCS_CUDA(c, cudaMemsetAsync(c->frag_primers.p, 0, (nloc + 1) * 4, c->st));
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    c->have_frags = true; c->amplified = false; c->have_counts = false;
+    return SCS_OK;
+}
+
+}  // namespace scs
+
+extern "C" void scs_shard_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi) {
+    if (world < 1) world = 1;
+    if (rank < 0) rank = 0;
+    if (rank >= world) rank = world - 1;
+    uint64_t q = n / (uint64_t)world, r = n % (uint64_t)world;
+    *lo = q * (uint64_t)rank + std::min<uint64_t>((uint64_t)rank, r);
+    *hi = *lo + q + ((uint64_t)rank < r ? 1 : 0);
+}

@@ -1,0 +1,69 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Free-running mode: oracle and CUDA path draw from the same Philox4x32-10 streams, so every
+intermediate array and the FASTQ must be identical byte for byte.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000):
+    from scssim_b200 import api
+    fa = os.path.join(tmp, f"{name}.fa")
+    genome = H.write_genome(fa, n_chrom, chrom_len, gseed)
+    prof = H.profile_path(profile)
+    args = H.genreads_args(prof, layout, gamma, coverage, isize, primers)
+    oprefix, dprefix = os.path.join(tmp, name + "_orc"), os.path.join(tmp, name + "_dump")
+    H.run_oracle(fa, oprefix, args, seed=seed, dump_prefix=dprefix)
+    od = H.oracle_dump(dprefix)
+    with api.GenReads(primers=primers, gamma=gamma, coverage=coverage, isize=isize, layout=layout, seed=seed) as g:
+        g.load_profile(prof).load_genome(fa).create_frags()
+        fr = g.dump(api.DUMP_FRAGS)
+        assert np.array_equal(fr[:, :4], od["frags"][:, :4]), "fragments differ"
+        g.amplify()
+        st = g.stats()
+        assert st["n_semis"] == len(od["semis"]) and st["n_fulls"] == len(od["fulls"]), (st, len(od["semis"]), len(od["fulls"]))
+        esemis, efulls = H.expected_windows(genome, od)
+        gs, gf = g.dump(api.DUMP_SEMIS).astype(np.int64), g.dump(api.DUMP_FULLS).astype(np.int64)
+        assert np.array_equal(gs[:, :4], esemis[:, :4]), "semi amplicons differ"
+        assert np.array_equal(gs[:, 4], esemis[:, 4]), "semi primer counts differ"
+        assert np.array_equal(gf[:, :4], efulls[:, :4]), "full amplicons differ"
+        assert np.array_equal(g.dump(api.DUMP_PRIMER_COUNTS), od["primer_counts"]), "primer pool differs"
+        g.set_read_counts()
+        assert np.allclose(g.dump(api.DUMP_WEIGHTS), od["weights"], rtol=1e-12, atol=0), "weights differ"
+        assert np.array_equal(g.dump(api.DUMP_COUNTS), od["counts"]), "read counts differ"
+        f1, f2 = g.yield_reads_bytes()
+        st = g.stats()
+    names = H.fastq_names(oprefix, layout)
+    assert f1 == H.read_bytes(names[0]), "FASTQ file 1 differs"
+    if layout == "PE":
+        assert f2 == H.read_bytes(names[1]), "FASTQ file 2 differs"
+    return st
+
+
+def test_pe_hiseq2500_small(tmp_path):
+    st = _run_case(str(tmp_path), "pe2500", 1, 400_000, 7, "Illumina_HiSeq2500", "PE", 2e-10, 5.0, 260, seed=0x5C55)
+    assert st["fastq_bytes"][0] > 0
+
+
+def test_se_hiseq2000_default_gamma(tmp_path):
+    _run_case(str(tmp_path), "se2000", 2, 150_000, 3, "Illumina_HiSeq2000", "SE", 1e-9, 3.0, 260, seed=12345)
+
+
+def test_pe_xten_insert_failures(tmp_path):
+    # -s 1200: insert sizes often exceed the amplicon -> fragCount gaps and the >1000-failures rule
+    _run_case(str(tmp_path), "xten", 1, 400_000, 7, "Illumina_HiSeqXTen", "PE", 2e-10, 4.0, 1200, seed=99)
+
+
+def test_pe_gaiix_short_insert(tmp_path):
+    _run_case(str(tmp_path), "gaiix", 1, 400_000, 9, "Illumina_GenomeAnalyzerIIx", "PE", 5e-10, 4.0, 100, seed=4242)
+
+
+def test_pe_mostly_failing_inserts(tmp_path):
+    _run_case(str(tmp_path), "fail", 1, 400_000, 7, "Illumina_HiSeq2500", "PE", 3e-10, 6.0, 1900, seed=5)
