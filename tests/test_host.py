@@ -1,0 +1,120 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every declared symbol, the
+.profile parser + integer threshold tables agree exactly with the oracle's FP64 CDF sampling, shard
+arithmetic, flag validation. No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as H
+from scssim_b200 import api
+
+EPS = 2.2204e-16
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(H.ROOT, "include", "scssim_b200.h")).read()
+    declared = set(re.findall(r"\b(scs_[a-z0-9_]+)\s*\(", hdr)) - {"scs_sink_fn", "scs_allreduce_u64_fn", "scs_allreduce_f64_fn"}
+    L = api.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(api.EXPORTS) == declared
+    assert b"sm_100a" in L.scs_version()
+
+
+def test_no_device_means_failure_not_fallback():
+    with pytest.raises(api.ScsError) as e:
+        g = api.GenReads(device=-1)
+        g.load_profile(H.profile_path("Illumina_HiSeq2500"))
+        g.set_genome([("chrS1_1_100", np.frombuffer(b"ACGT" * 25, dtype=np.uint8))])
+    assert e.value.code == api.SCS_E_CUDA and "no CPU fallback" in e.value.msg
+
+
+def test_flag_validation_messages_match_reference():
+    for kw, msg in [(dict(primers=10), 'Error: the value of parameter "primers" should be at least 1000!'),
+                    (dict(gamma=1e-7), 'Error: the value of parameter "gamma" should be in 0~1e-8!'),
+                    (dict(coverage=0.0), "Error: sequencing coverage not properly specified!"),
+                    (dict(layout="XX"), "Error: sequence layout incorrectly specified!")]:
+        with pytest.raises(api.ScsError) as e:
+            api.GenReads(device=-1, **kw)
+        assert msg in e.value.msg
+
+
+def _r(x):  # ThreadPool::randomDouble(ZERO_FINAL, 1) on a 32-bit engine output
+    return EPS + (1.0 - EPS) * (np.asarray(x, dtype=np.float64) / 4294967296.0)
+
+
+def _ref_index(cdf, x):  # randIndx, MyDefine.cpp:274-282
+    r = _r(x)
+    k = np.searchsorted(cdf, r, side="left")  # first k with r <= cdf[k]
+    return np.minimum(k, len(cdf) - 1)
+
+
+def _thr_index(thr, eff, x):
+    k = np.searchsorted(thr[:eff], x, side="right")  # number of thresholds <= x
+    return np.minimum(k, eff)
+
+
+@pytest.mark.parametrize("profile", H.PROFILES)
+def test_threshold_tables_equal_fp64_sampling(profile):
+    """For every CDF row, sampling by integer thresholds == the reference's FP64 comparison, checked at the
+    draws around every cut point and at random draws."""
+    L = H.oracle_lib()
+    path = H.profile_path(profile)
+    err = C.create_string_buffer(256)
+    op = L.orc_profile_load(path.encode(), 1, 260, err, 256)
+    assert op, err.value
+    info = (C.c_int * 9)()
+    L.orc_profile_info(op, info)
+    RL, kmers = info[0], info[2]
+    g = api.GenReads(device=-1, layout="PE", isize=260).load_profile(path)
+    assert g.read_length == RL
+    rng = np.random.default_rng(7)
+    buf = np.zeros(RL * 94 + 4096, dtype=np.float64)
+
+    def check(which, idx, rows, cols):
+        n = L.orc_profile_cdf(op, which, idx, buf.ctypes.data)
+        assert n == rows * cols
+        cdfs = buf[:n].reshape(rows, cols).copy()
+        for row in (range(rows) if rows <= 8 else rng.choice(rows, 8, replace=False)):
+            thr, eff = g.thresholds(which, idx, int(row))
+            if which in (3, 4):
+                thr = thr[:3]
+            cuts = thr[:eff].astype(np.int64)
+            xs = np.unique(np.clip(np.concatenate([cuts - 1, cuts, cuts + 1, rng.integers(0, 2 ** 32, 4000), [0, 2 ** 32 - 1]]), 0, 2 ** 32 - 1)).astype(np.uint32)
+            want = _ref_index(cdfs[row], xs)
+            got = _thr_index(thr.astype(np.uint32), eff, xs)
+            assert np.array_equal(got, want), (profile, which, idx, row)
+
+    check(0, 0, 1, info[6]); check(1, 0, 1, info[7]); check(2, 0, 1, info[5])
+    for ki in rng.choice(kmers, 6, replace=False):
+        check(3, int(ki), RL, 4); check(4, int(ki), RL, 4)
+    for bp in range(16):
+        check(5, bp, RL, 94)
+    L.orc_profile_free(op)
+
+
+def test_shard_ranges_partition_everything():
+    for n in (0, 1, 7, 8, 1000, 123457):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = api.shard_range(n, r, world)
+                assert lo == prev and hi >= lo and hi - lo in (n // world, n // world + 1)
+                prev = hi
+            assert prev == n
+
+
+def test_cli_rejects_bad_flags_like_the_reference():
+    exe = os.path.join(H.ROOT, "scssim_b200", "bin", "scssim")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    r = subprocess.run([exe, "genreads", "-i", "x.fa", "-m", "m.profile", "-o", "out", "-r", "1"], capture_output=True)
+    assert r.returncode == 1 and b'"gamma" should be in 0~1e-8' in r.stderr
+    r = subprocess.run([exe, "genreads", "-m", "m.profile", "-o", "out"], capture_output=True)
+    assert r.returncode == 1 and b"reference file (.fasta) not specified" in r.stderr
+    r = subprocess.run([exe, "genreads", "-i", "x.fa", "-m", "m.profile", "-o", "out", "-l", "XX"], capture_output=True)
+    assert r.returncode == 1 and b"sequence layout incorrectly specified" in r.stderr
