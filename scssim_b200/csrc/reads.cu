@@ -264,7 +264,8 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
 
 // plan: output lengths of both mates -> record sizes for the scan
 __global__ void __launch_bounds__(kReadWarps * 32) plan_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, uint32_t* __restrict__ plan,
-                                                               uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, int* flags) {
+                                                               uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, int* flags,
+                                                               unsigned long long* __restrict__ records) {
     __shared__ WarpScratch scratch[kReadWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t ls = (uint64_t)blockIdx.x * kReadWarps + warp;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(kReadWarps * 32) plan_kernel(Genome g, DrawSrc
             const int hl = header_len((uint32_t)(A.amp_global0 + lo), fragNo, T.paired);
             s1 = hl + 2 * (p & 0xFFFF) + 4;
             if (T.paired) s2 = hl + 2 * (p >> 16) + 4;
+            atomicAdd(records, T.paired ? 2ull : 1ull);
         }
         size1[ls] = s1; size2[ls] = s2;
     }
@@ -391,6 +393,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     SlabArgs A; A.slot_global0 = 0; A.amp_global0 = 0; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
     A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr;
     DevBuf<int> flags; SCS_CUDA(c, flags.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st));
+    DevBuf<unsigned long long> drec; SCS_CUDA(c, drec.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(drec.p, 0, 8, c->st));
     cudaEvent_t e0, e1, ek0, ek1, ee0, ee1, ecopy[2], ekern[2];
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&ek0); cudaEventCreate(&ek1); cudaEventCreate(&ee0); cudaEventCreate(&ee1);
     for (int b = 0; b < 2; b++) { cudaEventCreateWithFlags(&ecopy[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ekern[b], cudaEventDisableTiming); }
@@ -423,7 +426,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         A.slot0 = s0; A.nslots = m;
         const unsigned nb = (unsigned)((m + kReadWarps - 1) / kReadWarps);
         cudaEventRecord(ek0, c->st);
-        plan_kernel<<<nb, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, plan.p, size1.p, size2.p, flags.p); SCS_LAUNCHED(c);
+        plan_kernel<<<nb, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, plan.p, size1.p, size2.p, flags.p, drec.p); SCS_LAUNCHED(c);
         uint64_t tot[2] = {0, 0};
         if (int rc = exclusive_scan_u32(c, size1.p, off1.p, m, &tot[0])) return rc;
         if (nfiles == 2) if (int rc = exclusive_scan_u32(c, size2.p, off2.p, m, &tot[1])) return rc;
@@ -450,6 +453,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     c->stats.ms_reads = ms; c->stats.ms_reads_kernels = msk; c->stats.ms_emit_kernel = mse;
     int hflags = 0; SCS_CUDA(c, cudaMemcpy(&hflags, flags.p, 4, cudaMemcpyDeviceToHost));
+    unsigned long long hrec = 0; SCS_CUDA(c, cudaMemcpy(&hrec, drec.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ek0); cudaEventDestroy(ek1); cudaEventDestroy(ee0); cudaEventDestroy(ee1);
     for (int b = 0; b < 2; b++) { cudaEventDestroy(ecopy[b]); cudaEventDestroy(ekern[b]); }
     if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
@@ -474,7 +478,9 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     }
     __syncwarp();
     uint32_t cr = 0, ci = 0; int nev = 0;
-    const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
+    const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags + r);
+    __syncwarp();
+    if (flags[r] != 0) { if (lane == 0) out_len[r] = -2; return; }   // more than kMaxEvents indel events
     if (np > kSrcCap || np > out_stride) { if (lane == 0) out_len[r] = -1; return; }
     __syncwarp();
     const uint8_t* src = build_source(S, RL, nev, lane, ws);
@@ -491,8 +497,8 @@ int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const u
     DevBuf<char> dsrc, dseq, dqual; DevBuf<uint32_t> dreal, dint; DevBuf<int> dlen, flags;
     SCS_CUDA(c, dsrc.reserve((size_t)n_reads * RL + 16)); SCS_CUDA(c, dseq.reserve((size_t)n_reads * out_stride + 16)); SCS_CUDA(c, dqual.reserve((size_t)n_reads * out_stride + 16));
     SCS_CUDA(c, dreal.reserve((size_t)n_reads * stride_real + 4096)); SCS_CUDA(c, dint.reserve((size_t)n_reads * stride_int + 4096));
-    SCS_CUDA(c, dlen.reserve(n_reads + 1)); SCS_CUDA(c, flags.reserve(1));
-    SCS_CUDA(c, cudaMemset(dreal.p, 0, dreal.cap * 4)); SCS_CUDA(c, cudaMemset(dint.p, 0, dint.cap * 4)); SCS_CUDA(c, cudaMemset(flags.p, 0, 4));
+    SCS_CUDA(c, dlen.reserve(n_reads + 1)); SCS_CUDA(c, flags.reserve(n_reads + 1));
+    SCS_CUDA(c, cudaMemset(dreal.p, 0, dreal.cap * 4)); SCS_CUDA(c, cudaMemset(dint.p, 0, dint.cap * 4)); SCS_CUDA(c, cudaMemset(flags.p, 0, flags.cap * 4));
     SCS_CUDA(c, cudaMemset(dseq.p, 0, dseq.cap)); SCS_CUDA(c, cudaMemset(dqual.p, 0, dqual.cap));
     SCS_CUDA(c, cudaMemcpy(dsrc.p, src, (size_t)n_reads * RL, cudaMemcpyHostToDevice));
     SCS_CUDA(c, cudaMemcpy(dreal.p, real, (size_t)n_reads * stride_real * 4, cudaMemcpyHostToDevice));
