@@ -40,6 +40,8 @@ int scs_create(const scs_params* p, scs_ctx** out) {
             cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
             g_create_error = std::string("CUDA error: ") + cudaGetErrorString(cudaGetLastError()); delete c; return SCS_E_CUDA;
         }
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, p->device) == cudaSuccess) { uint64_t keep = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
         c->have_device = true;
     }
     *out = c;
@@ -48,14 +50,20 @@ int scs_create(const scs_params* p, scs_ctx** out) {
 
 void scs_destroy(scs_ctx* c) {
     if (!c) return;
-    if (c->have_device) {
-        cudaSetDevice(c->P.device);
+    const bool dev = c->have_device;
+    cudaStream_t st = c->st, st_copy = c->st_copy;
+    if (dev) {
+        cudaSetDevice(c->P.device); alloc_stream() = c->st;
         cudaDeviceSynchronize();
         for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) if (c->slab_host[b][f]) cudaFreeHost(c->slab_host[b][f]);
-        if (c->st) cudaStreamDestroy(c->st);
-        if (c->st_copy) cudaStreamDestroy(c->st_copy);
+        if (c->rscratch.htotals) cudaFreeHost(c->rscratch.htotals);
     }
-    delete c;
+    delete c;   // device buffers are returned to the pool in stream order
+    if (dev) {
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st); cudaStreamDestroy(st_copy);
+        alloc_stream() = nullptr;
+    }
 }
 
 const char* scs_last_error(const scs_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -71,13 +79,13 @@ int scs_read_length(const scs_ctx* c) { return (c && c->have_profile) ? c->prof.
 int scs_load_genome(scs_ctx* c, const char* path) {
     if (!c || !path) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     return genome_from_fasta(c, path);
 }
 int scs_set_genome(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens) {
     if (!c || !names || !seqs || !lens) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     return genome_from_host(c, n, names, seqs, lens);
 }
 
@@ -87,13 +95,13 @@ int scs_set_collectives(scs_ctx* c, scs_allreduce_u64_fn fu, scs_allreduce_f64_f
     return SCS_OK;
 }
 
-int scs_create_frags(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return create_frags(c); }
-int scs_amplify(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return amplify(c); }
-int scs_set_read_counts(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); return set_read_counts(c); }
+int scs_create_frags(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return create_frags(c); }
+int scs_amplify(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return amplify(c); }
+int scs_set_read_counts(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return set_read_counts(c); }
 int scs_yield_reads_sink(scs_ctx* c, scs_sink_fn sink, void* user) {
     if (!c) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     return yield_reads(c, sink, user);
 }
 
@@ -127,19 +135,19 @@ int scs_get_stats(const scs_ctx* c, scs_stats* out) {
 int scs_set_replay(scs_ctx* c, const scs_replay* r) {
     if (!c || !r) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     ReplayDev& R = c->replay;
     const size_t pad = 8192;   // lanes may read a few draws past an entity's last one
     auto up = [&](DevBuf<uint32_t>& b, const uint32_t* p, uint64_t n) -> cudaError_t {
         cudaError_t e = b.reserve(n + pad); if (e != cudaSuccess) return e;
-        e = cudaMemset(b.p, 0, (n + pad) * 4); if (e != cudaSuccess) return e;
-        return n ? cudaMemcpy(b.p, p, n * 4, cudaMemcpyHostToDevice) : cudaSuccess;
+        e = memset_sync(c, b.p, 0, (n + pad) * 4); if (e != cudaSuccess) return e;
+        return n ? memcpy_sync(c, b.p, p, n * 4, cudaMemcpyHostToDevice) : cudaSuccess;
     };
     SCS_CUDA(c, up(R.wreal, r->wreal, r->n_wreal)); SCS_CUDA(c, up(R.wint, r->wint, r->n_wint));
     SCS_CUDA(c, up(R.mrand, r->mrand, r->n_mrand)); SCS_CUDA(c, up(R.mreal, r->mreal, r->n_mreal));
     R.h_mrand.assign(r->mrand, r->mrand + r->n_mrand); R.h_mreal.assign(r->mreal, r->mreal + r->n_mreal);
     SCS_CUDA(c, R.gcf.reserve(r->n_gcf + 16));
-    if (r->n_gcf) SCS_CUDA(c, cudaMemcpy(R.gcf.p, r->gcf, r->n_gcf * 8, cudaMemcpyHostToDevice));
+    if (r->n_gcf) SCS_CUDA(c, memcpy_sync(c, R.gcf.p, r->gcf, r->n_gcf * 8, cudaMemcpyHostToDevice));
     for (int d = 0; d < 8; d++) {
         std::vector<uint64_t>& h = R.hmarks[d];
         h.assign(r->marks[d], r->marks[d] + 3 * r->n_marks[d]);
@@ -151,7 +159,7 @@ int scs_set_replay(scs_ctx* c, const scs_replay* r) {
         }
         R.n_marks[d] = h.size() / 3;
         SCS_CUDA(c, R.marks[d].reserve(h.size() + 16));
-        if (!h.empty()) SCS_CUDA(c, cudaMemcpy(R.marks[d].p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+        if (!h.empty()) SCS_CUDA(c, memcpy_sync(c, R.marks[d].p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
     }
     R.on = true;
     return SCS_OK;
@@ -164,7 +172,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
         if (!buf) return (int64_t)need;
         if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
         std::vector<uint32_t> pr(c->frag_hi - c->frag_lo);
-        if (!pr.empty() && c->have_device) cudaMemcpy(pr.data(), c->frag_primers.p, pr.size() * 4, cudaMemcpyDeviceToHost);
+        if (!pr.empty() && c->have_device) memcpy_sync(c, pr.data(), c->frag_primers.p, pr.size() * 4, cudaMemcpyDeviceToHost);
         int64_t* o = (int64_t*)buf;
         for (size_t i = 0; i < c->frags.size(); i++) {
             const HostFrag& f = c->frags[i];
@@ -174,7 +182,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
         return (int64_t)need;
     }
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     if (what == SCS_DUMP_SEMIS || what == SCS_DUMP_FULLS) {
         AmpList& L = what == SCS_DUMP_SEMIS ? c->semis : c->fulls;
         uint64_t need = L.n * 6 * 8;
@@ -182,9 +190,9 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
         if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
         std::vector<uint64_t> d(L.n), e(L.n); std::vector<uint32_t> g(L.n), p(L.n, 0);
         if (L.n) {
-            cudaMemcpy(d.data(), L.desc.p, L.n * 8, cudaMemcpyDeviceToHost); cudaMemcpy(e.data(), L.errref.p, L.n * 8, cudaMemcpyDeviceToHost);
-            cudaMemcpy(g.data(), L.gc.p, L.n * 4, cudaMemcpyDeviceToHost);
-            if (what == SCS_DUMP_SEMIS) cudaMemcpy(p.data(), L.primers.p, L.n * 4, cudaMemcpyDeviceToHost);
+            memcpy_sync(c, d.data(), L.desc.p, L.n * 8, cudaMemcpyDeviceToHost); memcpy_sync(c, e.data(), L.errref.p, L.n * 8, cudaMemcpyDeviceToHost);
+            memcpy_sync(c, g.data(), L.gc.p, L.n * 4, cudaMemcpyDeviceToHost);
+            if (what == SCS_DUMP_SEMIS) memcpy_sync(c, p.data(), L.primers.p, L.n * 4, cudaMemcpyDeviceToHost);
         }
         uint64_t* o = (uint64_t*)buf;
         for (uint64_t i = 0; i < L.n; i++) { Tmpl t = unpack_desc(d[i]); o[6 * i] = t.gstart; o[6 * i + 1] = t.rc; o[6 * i + 2] = t.len; o[6 * i + 3] = g[i]; o[6 * i + 4] = p[i]; o[6 * i + 5] = e[i] & 0xFFFF; }
@@ -195,7 +203,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
         uint64_t es = what == SCS_DUMP_COUNTS ? 4 : 8, need = c->fulls.n * es;
         if (!buf) return (int64_t)need;
         if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
-        if (need) cudaMemcpy(buf, what == SCS_DUMP_COUNTS ? (void*)c->counts.p : (void*)c->weights.p, need, cudaMemcpyDeviceToHost);
+        if (need) memcpy_sync(c, buf, what == SCS_DUMP_COUNTS ? (void*)c->counts.p : (void*)c->weights.p, need, cudaMemcpyDeviceToHost);
         return (int64_t)need;
     }
     if (what == SCS_DUMP_PRIMER_COUNTS) {
@@ -203,7 +211,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
         if (!buf) return (int64_t)need;
         if (cap < need) return c->fail(SCS_E_ARG, "scs_dump: buffer too small");
         if (!c->amplified) return c->fail(SCS_E_STATE, "scs_dump: not amplified");
-        cudaMemcpy(buf, c->primer_counts.p, need, cudaMemcpyDeviceToHost);
+        memcpy_sync(c, buf, c->primer_counts.p, need, cudaMemcpyDeviceToHost);
         return (int64_t)need;
     }
     if (what == SCS_DUMP_FULL_SEQ) {
@@ -217,7 +225,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
 int scs_test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
                      uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len) {
     if (!c) return SCS_E_ARG;
-    if (c->have_device) cudaSetDevice(c->P.device);
+    if (c->have_device) cudaSetDevice(c->P.device); alloc_stream() = c->st;
     return test_predict(c, src, n_reads, is_read1, real, stride_real, ints, stride_int, out_seq, out_qual, out_stride, out_len);
 }
 
@@ -227,24 +235,24 @@ static __global__ void det_log_test_kernel(const double* x, int n, double* out) 
 int scs_test_philox(scs_ctx* c, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     if (!c) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     DevBuf<uint32_t> d; SCS_CUDA(c, d.reserve(16));
     uint32_t h[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
-    SCS_CUDA(c, cudaMemcpy(d.p, h, 24, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, d.p, h, 24, cudaMemcpyHostToDevice));
     philox_test_kernel<<<1, 1, 0, c->st>>>(d.p, d.p + 8); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    SCS_CUDA(c, cudaMemcpy(out, d.p + 8, 16, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, out, d.p + 8, 16, cudaMemcpyDeviceToHost));
     return SCS_OK;
 }
 int scs_test_det_log(scs_ctx* c, const double* x, int n, double* out) {
     if (!c) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
-    cudaSetDevice(c->P.device);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
     DevBuf<double> a, b; SCS_CUDA(c, a.reserve(n + 1)); SCS_CUDA(c, b.reserve(n + 1));
-    SCS_CUDA(c, cudaMemcpy(a.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, a.p, x, (size_t)n * 8, cudaMemcpyHostToDevice));
     det_log_test_kernel<<<(n + 255) / 256, 256, 0, c->st>>>(a.p, n, b.p); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    SCS_CUDA(c, cudaMemcpy(out, b.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, out, b.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return SCS_OK;
 }
 

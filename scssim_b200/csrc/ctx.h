@@ -13,6 +13,11 @@
 
 namespace scs {
 
+// Stream all device allocations are ordered on (set at every C-ABI entry to the context's compute stream).
+// cudaMallocAsync / cudaFreeAsync from the device's default pool (release threshold = never) make the many
+// short-lived scratch buffers of the stages free of device-wide synchronisation.
+inline cudaStream_t& alloc_stream() { static cudaStream_t s = nullptr; return s; }
+
 // growable device array (host-managed capacity)
 template <class T> struct DevBuf {
     T* p = nullptr; size_t cap = 0;
@@ -20,16 +25,16 @@ template <class T> struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; cap = 0; }
     // ensure capacity >= n, keeping the first `keep` elements
-    cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t st = 0) {
+    cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t = 0) {
         if (n <= cap) return cudaSuccess;
         size_t ncap = n + n / 8 + 1024;
         T* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)&q, ncap * sizeof(T), alloc_stream());
         if (e != cudaSuccess) return e;
-        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st); if (e != cudaSuccess) { cudaFree(q); return e; } cudaStreamSynchronize(st); }
-        if (p) cudaFree(p);
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, alloc_stream()); if (e != cudaSuccess) { cudaFreeAsync(q, alloc_stream()); return e; } }
+        if (p) cudaFreeAsync(p, alloc_stream());
         p = q; cap = ncap;
         return cudaSuccess;
     }
@@ -63,8 +68,17 @@ struct DevProfile {
     DevBuf<uint32_t> subs1, subs2, qual, ins, del, isize;
     DevBuf<uint8_t> qualEff;
     DevBuf<uint32_t> qualDiag;   // [4][bins][kDiagW] compact diagonal rows for shared memory
-    DevBuf<uint32_t> qualDiagMeta;   // [4][bins]: lo | (n << 8)
-    int diagW = 0; bool diagOK = false;
+    DevBuf<uint32_t> qualDiagPiv;    // [4][bins][4] pivots (entries 7, 15, 23, 31 of each compact row)
+    DevBuf<uint32_t> qualDiagMeta;   // [4][bins]: lo | (n << 8) | (global-only << 16)
+};
+
+// persistent scratch of the read stage (no allocation inside the slab loop)
+struct ReadScratch {
+    DevBuf<uint32_t> plan, size1, size2, nfail, hdrno;
+    DevBuf<uint64_t> off1, off2, scan, totals;
+    DevBuf<int> flags; DevBuf<unsigned long long> records;
+    uint64_t* htotals = nullptr;   // pinned + mapped
+    uint64_t* dtotals_mapped = nullptr;   // device view of htotals
 };
 
 }  // namespace scs
@@ -98,6 +112,7 @@ struct scs_ctx {
     scs::DevBuf<double> weights; scs::DevBuf<uint32_t> counts; scs::DevBuf<uint64_t> slot_base; bool have_counts = false;
     uint64_t reads_requested = 0, n_slots = 0;
 
+    scs::ReadScratch rscratch;
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
     scs_stats stats{};
@@ -120,6 +135,20 @@ struct scs_ctx {
 #define SCS_LAUNCHED(ctx) ((ctx)->stats.kernel_launches++)
 
 namespace scs {
+// blocking copy ordered on the context's compute stream (device buffers are stream-ordered allocations)
+inline cudaError_t memcpy_sync(scs_ctx* c, void* dst, const void* src, size_t n, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(c->st);
+}
+inline cudaError_t memset_sync(scs_ctx* c, void* dst, int v, size_t n) {
+    cudaError_t e = cudaMemsetAsync(dst, v, n, c->st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(c->st);
+}
+}  // namespace scs
+
+namespace scs {
 // stage entry points (one .cu each)
 int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens);
 int genome_from_fasta(scs_ctx* c, const char* path);
@@ -139,4 +168,6 @@ uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, ui
 
 // device exclusive scan: out[i] = sum_{j<i} in[j] (u64), returns total through *total_dev (device pointer, may be null)
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
+// same for n <= 2048*2048 without allocation or synchronisation: scratch holds 2048+8 u64, the total is left in *total_dev
+int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev);
 }  // namespace scs

@@ -77,7 +77,6 @@ template <class TIn> static int scan_rec(scs_ctx* c, const TIn* in, uint64_t* ou
         scan_tiles<TIn><<<1, kScanThreads, 0, c->st>>>(in, n, nullptr, out); SCS_LAUNCHED(c);
         if (total_dev) SCS_CUDA(c, cudaMemcpyAsync(total_dev, sums.p, 8, cudaMemcpyDeviceToDevice, c->st));
     }
-    SCS_CUDA(c, cudaStreamSynchronize(c->st));   // temporaries die here
     return SCS_OK;
 }
 
@@ -88,6 +87,28 @@ int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n
     int rc = scan_rec<uint32_t>(c, in, out, n, tot.p);
     if (rc) return rc;
     if (total_host) { SCS_CUDA(c, cudaMemcpyAsync(total_host, tot.p, 8, cudaMemcpyDeviceToHost, c->st)); SCS_CUDA(c, cudaStreamSynchronize(c->st)); }
+    return SCS_OK;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_single_tile(const uint64_t* in, uint64_t n, uint64_t* out, uint64_t* total) {
+    __shared__ uint64_t ws[kScanThreads / 32]; __shared__ uint64_t tot;
+    uint64_t base = (uint64_t)threadIdx.x * kScanItems;
+    uint64_t v[kScanItems]; uint64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+    uint64_t off = block_exclusive_scan(s, &tot, ws);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+    if (threadIdx.x == 0) { *total = tot; __threadfence_system(); }   // total may live in mapped host memory
+}
+
+int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev) {
+    if (n == 0) { SCS_CUDA(c, cudaMemsetAsync(total_dev, 0, 8, c->st)); return SCS_OK; }
+    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles > (uint64_t)kScanTile) return c->fail(SCS_E_ARG, "scan_u32_noalloc: too many items");
+    scan_tile_sums<uint32_t><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch); SCS_LAUNCHED(c);
+    scan_single_tile<<<1, kScanThreads, 0, c->st>>>(scratch, tiles, scratch, total_dev); SCS_LAUNCHED(c);
+    scan_tiles<uint32_t><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch, out); SCS_LAUNCHED(c);
     return SCS_OK;
 }
 

@@ -13,13 +13,18 @@
 // All sampling is integer compares against the threshold tables built on the host. Records are
 // assembled in shared memory at the destination's 16-byte phase and stored with 128-bit stores.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
 
 namespace scs {
 
-constexpr int kReadWarps = 8;         // warps per CTA
+constexpr int kReadWarps = 8;         // warps per CTA (plan / test kernels)
+constexpr int kEmitWarps = 24;        // warps per persistent CTA of the emit kernel (one CTA per SM)
+constexpr int kDiagW = 32;            // entries per compact quality row kept in shared memory
+constexpr int kDiagStride = 36;       // words per row: 32 + 4 pad keeps 128-bit loads of 8 neighbouring rows conflict-free
 constexpr int kRLCap = 256;           // max profile read length handled by the kernels
 constexpr int kSrcCap = 384;          // max read length after insertions (overflow -> error flag)
 constexpr int kMaxEvents = 32;        // indel events per read kept in shared memory
@@ -32,7 +37,11 @@ struct ReadTables {
     int insEff, delEff, isizeEff, minInsert, maxInsert;
     uint64_t thrIns, thrDel;                         // insertion iff x < thrIns ; else deletion iff x2 < thrDel
     int RL, paired;
+    // compact copies of the 4 diagonal (no substitution) quality tables for shared memory
+    const uint32_t* diagRows; const uint4* diagPiv; const uint32_t* diagMeta;   // [4][bins][36], [4][bins], [4][bins] lo | cnt<<8 | global<<16
 };
+
+struct QualSmem { const uint32_t* rows; const uint4* piv; const uint32_t* meta; };
 
 struct WarpScratch {
     uint8_t ref[kRLCap];
@@ -108,29 +117,57 @@ __device__ __forceinline__ int indel_pass(const Stream& S, const ReadTables& T, 
     return n + delta;
 }
 
-// source sequence after indels (Profile.cpp:1632-1654); lane 0 walks the (rare) events
-__device__ __forceinline__ const uint8_t* build_source(const Stream& S, int n, int nev, int lane, WarpScratch* ws) {
+// source sequence after indels (Profile.cpp:1632-1654): every lane maps its output positions back through the
+// (few) recorded events, so there is no serial walk
+__device__ __forceinline__ const uint8_t* build_source(const Stream& S, int np, int nev, int lane, WarpScratch* ws) {
     if (nev == 0) return ws->ref;
-    if (lane == 0) {
-        int m = 0, e = 0;
-        for (int j = 0; j < n;) {
-            if (e < nev && ws->ev_pos[e] == j) {
-                int len = ws->ev_len[e];
-                if (len < 0) { j += -len; e++; continue; }
-                if (m < kSrcCap) ws->src[m] = ws->ref[j]; m++;
-                uint32_t c0 = ws->ev_ci[e];
-                for (int i = 0; i < len; i++) { uint32_t b = uni_trunc(S.at(E_INT, c0 + i), 0, 3); if (m < kSrcCap) ws->src[m] = (uint8_t)b; m++; }   // A/C/G only, Profile.cpp:1560
-                j++; e++;
-            } else { if (m < kSrcCap) ws->src[m] = ws->ref[j]; m++; j++; }
+    for (int m = lane; m < np; m += 32) {
+        int shift = 0; uint32_t b = 0; bool done = false;
+        for (int e = 0; e < nev; e++) {
+            const int p = ws->ev_pos[e], L = ws->ev_len[e];
+            const int mp = p + shift;                 // output index of source position p
+            if (L > 0) {                              // L bases inserted after p (A/C/G only, Profile.cpp:1560)
+                if (m <= mp) break;
+                if (m <= mp + L) { b = uni_trunc(S.at(E_INT, ws->ev_ci[e] + (uint32_t)(m - mp - 1)), 0, 3); done = true; break; }
+                shift += L;
+            } else {                                  // -L bases deleted starting at p
+                if (m < mp) break;
+                shift += L;
+            }
         }
+        ws->src[m] = done ? (uint8_t)b : ws->ref[m - shift];
     }
     __syncwarp();
     return ws->src;
 }
 
+// quality index for (reference base b0, emitted base k, bin): diagonal rows from shared memory with a
+// 4-pivot + 8-entry search (two dependent 128-bit loads), everything else by binary search in global memory
+__device__ __forceinline__ int sample_quality(const ReadTables& T, const QualSmem* Q, uint32_t b0, uint32_t k, int bin, uint32_t xq) {
+    if (Q != nullptr && k == b0) {
+        const int r = (int)b0 * T.RL + bin;
+        const uint32_t meta = Q->meta[r];
+        if ((meta >> 16) == 0) {
+            const int lo = (int)(meta & 0xFFu), cnt = (int)((meta >> 8) & 0xFFu);
+            const uint4 pv = Q->piv[r];
+            const int oct = (int)(pv.x <= xq) + (int)(pv.y <= xq) + (int)(pv.z <= xq) + (int)(pv.w <= xq);
+            int c = kDiagW;
+            if (oct < 4) {
+                const uint4* row = reinterpret_cast<const uint4*>(Q->rows + (size_t)r * kDiagStride + oct * 8);
+                const uint4 a = row[0], d = row[1];
+                c = oct * 8 + (int)(a.x <= xq) + (int)(a.y <= xq) + (int)(a.z <= xq) + (int)(a.w <= xq) + (int)(d.x <= xq) + (int)(d.y <= xq) +
+                    (int)(d.z <= xq) + (int)(d.w <= xq);
+            }
+            return lo + min(c, cnt);
+        }
+    }
+    const size_t row = (size_t)(b0 * 4u + k) * T.RL + bin;
+    return count_le(T.qual + row * kQualN, (int)T.qualEff[row], xq);
+}
+
 // substitution + quality loop (Profile.cpp:1656-1694): two output positions per lane per step
-__device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTables& T, const uint8_t* __restrict__ src, int np, int isRead1, uint32_t& cr,
-                                                   int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
+__device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTables& T, const QualSmem* Q, const uint8_t* __restrict__ src, int np,
+                                                   int isRead1, uint32_t& cr, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
     const uint32_t* __restrict__ subs = (!isRead1 && T.subs2) ? T.subs2 : T.subs1;
     const int bins = T.RL;
     for (int m0 = 0; m0 < np; m0 += 64) {
@@ -145,13 +182,11 @@ __device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTa
                 if (m == 0) ki = b0;
                 else if (m == 1) ki = 4u + 4u * src[0] + b0;
                 else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0;
-                const int bin = m * bins / np;
+                const int bin = (np == bins) ? m : m * bins / np;
                 const uint4 th = __ldg(reinterpret_cast<const uint4*>(subs) + ((size_t)ki * bins + bin));
                 const uint32_t xs = x[2 * h], xq = x[2 * h + 1];
-                uint32_t k = (uint32_t)(th.w > 0 && th.x <= xs) + (uint32_t)(th.w > 1 && th.y <= xs) + (uint32_t)(th.w > 2 && th.z <= xs);
-                const size_t row = (size_t)(b0 * 4u + k) * bins + bin;
-                const int eff = T.qualEff[row];
-                const int q = count_le(T.qual + row * kQualN, eff, xq);
+                const uint32_t k = (uint32_t)(th.w > 0 && th.x <= xs) + (uint32_t)(th.w > 1 && th.y <= xs) + (uint32_t)(th.w > 2 && th.z <= xs);
+                const int q = sample_quality(T, Q, b0, k, bin, xq);
                 oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);   // "ACGT"[k]
                 oqual[m] = (char)(33 + q);
             }
@@ -196,108 +231,131 @@ struct SlabArgs {
     const uint64_t* desc; const uint64_t* errref; const uint32_t* err_pool;
     const uint32_t* hdr_no;            // slow path: fragCount per slot (0 = dropped); nullptr -> slot index + 1
     const uint32_t* nfail;             // slow path: failed insert-size attempts before the slot's success
+    uint64_t slab_cap;                 // bytes available in each output slab (emit bounds check)
 };
+
+// amplicon of a slot: last a with slot_base[a] <= slot, by a warp-cooperative 32-ary search (4 probes for 1e6 amplicons)
+__device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ slot_base, uint64_t n_amp, uint64_t slot, int lane) {
+    uint64_t lo = 0, hi = n_amp;   // invariant: slot_base[lo] <= slot < slot_base[hi]
+    while (hi - lo > 1) {
+        const uint64_t width = hi - lo, step = (width + 31) >> 5;
+        const uint64_t idx = lo + (uint64_t)lane * step;
+        const bool le = idx < hi && __ldg(slot_base + idx) <= slot;
+        const uint32_t m = __ballot_sync(0xffffffffu, le);   // prefix of lanes (slot_base is non-decreasing), lane 0 always set
+        const int j = __popc(m) - 1;
+        lo = lo + (uint64_t)j * step;
+        hi = min(hi, lo + step);
+    }
+    return lo;
+}
 
 // Shared body of the plan and emit kernels for one slot.
 template <bool EMIT>
-__device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const SlabArgs& A, uint64_t ls, int lane, WarpScratch* ws,
-                                        uint32_t* __restrict__ plan, const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
-                                        char* __restrict__ out1, char* __restrict__ out2, int* flags) {
+__device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
+                                        WarpScratch* ws, uint32_t* __restrict__ plan, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
+                                        const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, char* __restrict__ out1,
+                                        char* __restrict__ out2, int* flags, unsigned long long* records) {
     const uint64_t slot = A.slot0 + ls;
-    // amplicon of this slot: last a with slot_base[a] <= slot
-    uint64_t lo = 0, hi = A.n_amp;
-    while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (__ldg(A.slot_base + mid) <= slot) lo = mid; else hi = mid; }
-    const uint64_t a = lo;
+    const uint64_t a = find_amplicon(A.slot_base, A.n_amp, slot, lane);
     const Tmpl F = unpack_desc(__ldg(A.desc + a));
-    const uint64_t er = __ldg(A.errref + a);
-    const uint32_t nerr = (uint32_t)(er & 0xFFFF); const uint32_t* __restrict__ errs = A.err_pool + (er >> 16);
     const int RL = T.RL; const int ampLen = (int)F.len;
-    uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - __ldg(A.slot_base + a)) + 1u;
-    if (fragNo == 0 || ampLen < RL) { if (!EMIT && lane == 0) plan[ls] = 0; return; }   // dropped slot / Amplicon.cpp:442
+    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - __ldg(A.slot_base + a)) + 1u;
+    const uint32_t ampIdx = (uint32_t)(A.amp_global0 + a);
+    if (fragNo == 0 || ampLen < RL) {   // dropped slot / Amplicon.cpp:442
+        if (!EMIT && lane == 0) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; }
+        return;
+    }
     Stream S; S.init(dsrc, D_READ, A.slot_global0 + slot, A.slot_global0 + slot);
     uint32_t cr = 0, ci = 0;
-    int pos, isz = RL;
+    int pos = 0, isz = RL;
     if (T.paired) {
         if (A.nfail) cr = A.nfail[slot];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
-        isz = T.minInsert + min(count_le(T.isize, T.isizeEff, S.at(E_REAL, cr)), T.isizeEff);
+        isz = T.minInsert + count_le(T.isize, T.isizeEff, S.at(E_REAL, cr));
         cr += 1;
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
     } else {
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
     }
-    const uint32_t ampIdx = (uint32_t)(A.amp_global0 + a);
+    uint32_t nerr = 0; const uint32_t* __restrict__ errs = nullptr;
+    if (EMIT) { const uint64_t er = __ldg(A.errref + a); nerr = (uint32_t)(er & 0xFFFF); errs = A.err_pool + (er >> 16); }
     uint32_t lens = 0;
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
-        // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
-        __syncwarp();
-        for (int i = lane; i < RL; i += 32) {
-            uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
-            uint32_t b = window_base(g, F.gstart, F.rc, fi);
-            for (uint32_t e = 0; e < nerr; e++) { uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
-            ws->ref[i] = (uint8_t)(mate == 1 ? b : 3u - b);
+        if (EMIT) {
+            // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
+            __syncwarp();
+            for (int i = lane; i < RL; i += 32) {
+                const uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
+                uint32_t b = window_base(g, F.gstart, F.rc, fi);
+                for (uint32_t e = 0; e < nerr; e++) { const uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
+                ws->ref[i] = (uint8_t)(mate == 1 ? b : 3u - b);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         int nev = 0;
         const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
-        if (np > kSrcCap) { if (lane == 0) { atomicOr(flags, 8); if (!EMIT) plan[ls] = 0; } return; }
+        if (np > kSrcCap) { if (lane == 0) { atomicOr(flags, 8); if (!EMIT) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; } } return; }
         __syncwarp();
         if (!EMIT) {
             cr += 2u * (uint32_t)np;   // the substitution/quality pass draws twice per output base
             lens |= (uint32_t)np << (mate == 1 ? 0 : 16);
         } else {
-            const uint8_t* src = build_source(S, RL, nev, lane, ws);
+            const uint8_t* src = build_source(S, np, nev, lane, ws);
             const uint64_t o = (mate == 1) ? off1[ls] : off2[ls];
+            const int hl = header_len(ampIdx, fragNo, T.paired);
+            const int total = hl + 2 * np + 4;
+            if (o + (uint64_t)total > A.slab_cap) { if (lane == 0) atomicOr(flags, 16); return; }
             char* dst = ((mate == 1) ? out1 : out2) + o;
             char* rec = ws->rec + (reinterpret_cast<uintptr_t>(dst) & 15);
-            const int hl = header_len(ampIdx, fragNo, T.paired);
             if (lane == 0) {
                 write_header(rec, ampIdx, fragNo, T.paired ? mate : 0);
                 rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; rec[hl + 2 * np + 3] = '\n';
             }
-            subst_quality_pass(S, T, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
+            subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
             __syncwarp();
-            copy_out(dst, rec, hl + 2 * np + 4, lane);
+            copy_out(dst, rec, total, lane);
         }
     }
-    if (!EMIT && lane == 0) plan[ls] = lens;
+    if (!EMIT && lane == 0) {
+        const int hl = header_len(ampIdx, fragNo, T.paired);
+        plan[ls] = lens;
+        size1[ls] = (uint32_t)(hl + 2 * (int)(lens & 0xFFFF) + 4);
+        size2[ls] = T.paired ? (uint32_t)(hl + 2 * (int)(lens >> 16) + 4) : 0u;
+        atomicAdd(records, T.paired ? 2ull : 1ull);
+    }
 }
 
-// plan: output lengths of both mates -> record sizes for the scan
+// plan: output lengths of both mates -> record sizes for the scan (no sequence access: the indel pass only needs draws)
 __global__ void __launch_bounds__(kReadWarps * 32) plan_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, uint32_t* __restrict__ plan,
                                                                uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, int* flags,
                                                                unsigned long long* __restrict__ records) {
     __shared__ WarpScratch scratch[kReadWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t ls = (uint64_t)blockIdx.x * kReadWarps + warp;
-    if (ls >= A.nslots) return;
-    do_slot<false>(g, dsrc, T, A, ls, lane, &scratch[warp], plan, nullptr, nullptr, nullptr, nullptr, flags);
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t p = plan[ls];
-        uint32_t s1 = 0, s2 = 0;
-        if (p) {
-            const uint64_t slot = A.slot0 + ls;
-            uint64_t lo = 0, hi = A.n_amp;
-            while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (A.slot_base[mid] <= slot) lo = mid; else hi = mid; }
-            const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - A.slot_base[lo]) + 1u;
-            const int hl = header_len((uint32_t)(A.amp_global0 + lo), fragNo, T.paired);
-            s1 = hl + 2 * (p & 0xFFFF) + 4;
-            if (T.paired) s2 = hl + 2 * (p >> 16) + 4;
-            atomicAdd(records, T.paired ? 2ull : 1ull);
-        }
-        size1[ls] = s1; size2[ls] = s2;
-    }
+    for (uint64_t ls = (uint64_t)blockIdx.x * kReadWarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * kReadWarps)
+        do_slot<false>(g, dsrc, T, nullptr, A, ls, lane, &scratch[warp], plan, size1, size2, nullptr, nullptr, nullptr, nullptr, flags, records);
 }
 
-__global__ void __launch_bounds__(kReadWarps * 32) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, const uint32_t* __restrict__ plan,
-                                                               const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
-                                                               char* __restrict__ out1, char* __restrict__ out2, int* flags) {
-    __shared__ __align__(16) WarpScratch scratch[kReadWarps];
+// emit: persistent CTAs (one per SM); the diagonal quality tables are staged in shared memory once per CTA
+__global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, const uint32_t* __restrict__ plan,
+                                                                  const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
+                                                                  char* __restrict__ out1, char* __restrict__ out2, int* flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t ls = (uint64_t)blockIdx.x * kReadWarps + warp;
-    if (ls >= A.nslots) return;
-    if (plan[ls] == 0) return;
-    do_slot<true>(g, dsrc, T, A, ls, lane, &scratch[warp], nullptr, off1, off2, out1, out2, flags);
+    const int nrows = 4 * T.RL;
+    uint32_t* srows = reinterpret_cast<uint32_t*>(smem_raw);
+    uint4* spiv = reinterpret_cast<uint4*>(srows + (size_t)nrows * kDiagStride);
+    uint32_t* smeta = reinterpret_cast<uint32_t*>(spiv + nrows);
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smeta + ((nrows + 3) & ~3));
+    {
+        const uint4* grows = reinterpret_cast<const uint4*>(T.diagRows); uint4* s4 = reinterpret_cast<uint4*>(srows);
+        for (int i = threadIdx.x; i < nrows * (kDiagStride / 4); i += blockDim.x) s4[i] = __ldg(grows + i);
+        for (int i = threadIdx.x; i < nrows; i += blockDim.x) { spiv[i] = __ldg(T.diagPiv + i); smeta[i] = __ldg(T.diagMeta + i); }
+    }
+    __syncthreads();
+    QualSmem Q; Q.rows = srows; Q.piv = spiv; Q.meta = smeta;
+    for (uint64_t ls = (uint64_t)blockIdx.x * kEmitWarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * kEmitWarps) {
+        if (plan[ls] == 0) continue;
+        do_slot<true>(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], nullptr, nullptr, nullptr, off1, off2, out1, out2, flags, nullptr);
+    }
 }
 
 // ---- slow path (insert sizes that can exceed an amplicon, -s large): failed attempts per slot -----
@@ -310,7 +368,7 @@ __global__ void __launch_bounds__(256) fail_count_kernel(DrawSrc dsrc, ReadTable
     Stream S; S.init(dsrc, D_READ, A.slot_global0 + slot, A.slot_global0 + slot);
     uint32_t f = 0;
     for (; f <= 1001u; f++) {
-        int isz = T.minInsert + min(count_le(T.isize, T.isizeEff, S.at(E_REAL, f)), T.isizeEff);
+        int isz = T.minInsert + count_le(T.isize, T.isizeEff, S.at(E_REAL, f));
         if (!(isz < T.RL || isz > ampLen)) break;
     }
     nfail[slot] = f;
@@ -333,15 +391,28 @@ int upload_profile(scs_ctx* c) {
     const HostProfile& P = c->prof; DevProfile& D = c->dprof;
     auto up32 = [&](DevBuf<uint32_t>& b, const std::vector<uint32_t>& v) -> cudaError_t {
         cudaError_t e = b.reserve(v.size() + 4); if (e != cudaSuccess) return e;
-        return v.empty() ? cudaSuccess : cudaMemcpy(b.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
+        return v.empty() ? cudaSuccess : memcpy_sync(c, b.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice);
     };
     SCS_CUDA(c, up32(D.subs1, P.subsThr1));
     if (P.hasSubs2) SCS_CUDA(c, up32(D.subs2, P.subsThr2));
     SCS_CUDA(c, up32(D.qual, P.qualThr));
     SCS_CUDA(c, D.qualEff.reserve(P.qualEff.size() + 4));
-    SCS_CUDA(c, cudaMemcpy(D.qualEff.p, P.qualEff.data(), P.qualEff.size(), cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, D.qualEff.p, P.qualEff.data(), P.qualEff.size(), cudaMemcpyHostToDevice));
     SCS_CUDA(c, up32(D.ins, P.insThr.thr)); SCS_CUDA(c, up32(D.del, P.delThr.thr));
     if (P.hasISize) SCS_CUDA(c, up32(D.isize, P.iSizeThr.thr));
+    // compact diagonal quality rows: entries [lo, eff) of pair (b,b), padded to 32 with 0xFFFFFFFF; rows that do not fit stay global
+    const int bins = P.bins, nrows = 4 * bins;
+    std::vector<uint32_t> rows((size_t)nrows * kDiagStride, 0xFFFFFFFFu), piv((size_t)nrows * 4, 0xFFFFFFFFu), meta(nrows, 0);
+    for (int b = 0; b < 4; b++) for (int j = 0; j < bins; j++) {
+        const size_t r = (size_t)(b * 5) * bins + j;   // pair index b*4+b
+        const int lo = P.qualLo[r], eff = P.qualEff[r], cnt = eff - lo;
+        const int o = b * bins + j;
+        if (cnt > kDiagW || lo > 255) { meta[o] = 1u << 16; continue; }
+        for (int k = 0; k < cnt; k++) rows[(size_t)o * kDiagStride + k] = P.qualThr[r * kQualN + lo + k];
+        for (int q = 0; q < 4; q++) piv[(size_t)o * 4 + q] = rows[(size_t)o * kDiagStride + 8 * q + 7];
+        meta[o] = (uint32_t)lo | ((uint32_t)cnt << 8);
+    }
+    SCS_CUDA(c, up32(D.qualDiag, rows)); SCS_CUDA(c, up32(D.qualDiagPiv, piv)); SCS_CUDA(c, up32(D.qualDiagMeta, meta));
     return SCS_OK;
 }
 
@@ -354,10 +425,16 @@ static ReadTables make_tables(const scs_ctx* c) {
     T.minInsert = P.minInsert; T.maxInsert = P.maxInsert;
     T.thrIns = P.thrInsertAll ? (1ull << 32) : P.thrInsert; T.thrDel = P.thrDeleteAll ? (1ull << 32) : P.thrDelete;
     T.RL = P.readLength; T.paired = c->P.paired;
+    T.diagRows = D.qualDiag.p; T.diagPiv = reinterpret_cast<const uint4*>(D.qualDiagPiv.p); T.diagMeta = D.qualDiagMeta.p;
     return T;
 }
 
 // ---------------------------------------------------------------------------------- slab pipeline
+// allocation-free exclusive scan of up to 2048*2048 u32 sizes (one slab batch); total left in *total_dev
+static int scan_sizes(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev) {
+    return scan_u32_noalloc(c, in, out, n, scratch, total_dev);
+}
+
 int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
     if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
@@ -369,21 +446,19 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     const uint64_t nslots = c->n_slots;
     if (nslots == 0) return SCS_OK;
     const int nfiles = c->P.paired ? 2 : 1;
-    const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (128ull << 20);
-    const uint64_t worst = 40 + 2ull * (P.readLength + 128) + 8;   // bytes per record bound used for batching (checked below)
-    uint64_t batch = std::max<uint64_t>(1024, slab / worst);
+    const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (256ull << 20);
+    // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4; the emit kernel bounds-checks every store
+    const uint64_t typical = 30 + 2ull * (P.readLength + 8) + 4;
+    const uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(1024, slab / typical), 2048ull * 2048ull);
     // device + pinned slabs, double buffered
-    if (c->slab_cap < slab) {
+    if (c->slab_cap != slab) {
         for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) {
             c->slab_dev[b][f].release();
             if (c->slab_host[b][f]) { cudaFreeHost(c->slab_host[b][f]); c->slab_host[b][f] = nullptr; }
         }
-        for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) {
-            SCS_CUDA(c, c->slab_dev[b][f].reserve(slab + 64));
-            SCS_CUDA(c, cudaMallocHost((void**)&c->slab_host[b][f], slab + 64));
-        }
         c->slab_cap = slab;
-    } else for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) if (!c->slab_host[b][f]) {
+    }
+    for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) if (!c->slab_host[b][f]) {
         SCS_CUDA(c, c->slab_dev[b][f].reserve(slab + 64));
         SCS_CUDA(c, cudaMallocHost((void**)&c->slab_host[b][f], slab + 64));
     }
@@ -391,25 +466,34 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     Genome g; g.words = c->genome_words.p; g.n_bases = c->genome_bases;
     DrawSrc dsrc = draw_src(c, D_READ);
     SlabArgs A; A.slot_global0 = 0; A.amp_global0 = 0; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
-    A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr;
-    DevBuf<int> flags; SCS_CUDA(c, flags.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st));
-    DevBuf<unsigned long long> drec; SCS_CUDA(c, drec.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(drec.p, 0, 8, c->st));
-    cudaEvent_t e0, e1, ek0, ek1, ee0, ee1, ecopy[2], ekern[2];
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&ek0); cudaEventCreate(&ek1); cudaEventCreate(&ee0); cudaEventCreate(&ee1);
+    A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
+    ReadScratch& W = c->rscratch;
+    SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));
+    SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
+    SCS_CUDA(c, W.plan.reserve(batch + 1)); SCS_CUDA(c, W.size1.reserve(batch + 1)); SCS_CUDA(c, W.size2.reserve(batch + 1));
+    SCS_CUDA(c, W.off1.reserve(batch + 1)); SCS_CUDA(c, W.off2.reserve(batch + 1)); SCS_CUDA(c, W.scan.reserve(2 * 2048 + 16));
+    // slab byte totals are written by the scan kernel straight into mapped pinned memory: a D2H memcpy on the compute
+    // stream would queue behind the previous slab's 0.5 GB copy on the same copy engine and stall the emit kernel
+    if (!W.htotals) {
+        SCS_CUDA(c, cudaHostAlloc((void**)&W.htotals, 64, cudaHostAllocMapped));
+        SCS_CUDA(c, cudaHostGetDevicePointer((void**)&W.dtotals_mapped, W.htotals, 0));
+    }
+    int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t emit_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4 + sizeof(WarpScratch) * kEmitWarps;
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+    cudaEvent_t e0, e1, etot, ecopy[2], ekern[2];
+    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreateWithFlags(&etot, cudaEventDisableTiming);
     for (int b = 0; b < 2; b++) { cudaEventCreateWithFlags(&ecopy[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ekern[b], cudaEventDisableTiming); }
+    std::vector<cudaEvent_t> tev;   // per batch: plan start, emit start, emit end
     cudaEventRecord(e0, c->st);
     // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
-    DevBuf<uint32_t> nfail, hdrno;
     if (c->P.paired && P.maxInsert > 1000) {
-        SCS_CUDA(c, nfail.reserve(nslots + 1)); SCS_CUDA(c, hdrno.reserve(nslots + 1));
+        SCS_CUDA(c, W.nfail.reserve(nslots + 1)); SCS_CUDA(c, W.hdrno.reserve(nslots + 1));
         SlabArgs F = A; F.slot0 = 0; F.nslots = nslots;
-        fail_count_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, c->st>>>(dsrc, T, F, nfail.p); SCS_LAUNCHED(c);
-        fail_scan_kernel<<<(unsigned)((A.n_amp + 255) / 256), 256, 0, c->st>>>(F, nfail.p, hdrno.p); SCS_LAUNCHED(c);
-        A.hdr_no = hdrno.p; A.nfail = nfail.p;
+        fail_count_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, c->st>>>(dsrc, T, F, W.nfail.p); SCS_LAUNCHED(c);
+        fail_scan_kernel<<<(unsigned)((A.n_amp + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
+        A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p;
     }
-    DevBuf<uint32_t> plan, size1, size2; DevBuf<uint64_t> off1, off2;
-    SCS_CUDA(c, plan.reserve(batch + 1)); SCS_CUDA(c, size1.reserve(batch + 1)); SCS_CUDA(c, size2.reserve(batch + 1));
-    SCS_CUDA(c, off1.reserve(batch + 1)); SCS_CUDA(c, off2.reserve(batch + 1));
     struct Pending { bool live = false; uint64_t bytes[2] = {0, 0}; } pend[2];
     auto drain = [&](int b) -> int {
         if (!pend[b].live) return SCS_OK;
@@ -419,45 +503,63 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         if (sink) for (int f = 0; f < nfiles; f++) if (pend[b].bytes[f]) if (sink(user, f, c->slab_host[b][f], pend[b].bytes[f])) return c->fail(SCS_E_IO, "FASTQ sink failed");
         return SCS_OK;
     };
-    int bi = 0; double msk = 0, mse = 0;
+    int bi = 0;
+    const bool trace = getenv("SCS_TRACE") != nullptr, no_d2h = getenv("SCS_NO_D2H") != nullptr;
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tr0 = now_ms();
     for (uint64_t s0 = 0; s0 < nslots; s0 += batch, bi ^= 1) {
         const uint64_t m = std::min(batch, nslots - s0);
+        const double ta = now_ms();
         if (int rc = drain(bi)) return rc;   // buffer bi is free again once its previous copy has been consumed
+        const double tb = now_ms();
         A.slot0 = s0; A.nslots = m;
-        const unsigned nb = (unsigned)((m + kReadWarps - 1) / kReadWarps);
-        cudaEventRecord(ek0, c->st);
-        plan_kernel<<<nb, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, plan.p, size1.p, size2.p, flags.p, drec.p); SCS_LAUNCHED(c);
-        uint64_t tot[2] = {0, 0};
-        if (int rc = exclusive_scan_u32(c, size1.p, off1.p, m, &tot[0])) return rc;
-        if (nfiles == 2) if (int rc = exclusive_scan_u32(c, size2.p, off2.p, m, &tot[1])) return rc;
-        if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
-        cudaEventRecord(ee0, c->st);
-        emit_kernel<<<nb, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, plan.p, off1.p, off2.p, c->slab_dev[bi][0].p, nfiles == 2 ? c->slab_dev[bi][1].p : nullptr, flags.p);
+        cudaEvent_t t0, t1, t2; cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2); tev.push_back(t0); tev.push_back(t1); tev.push_back(t2);
+        cudaEventRecord(t0, c->st);
+        const unsigned nbp = (unsigned)std::min<uint64_t>((m + kReadWarps - 1) / kReadWarps, (uint64_t)sms * 32);
+        plan_kernel<<<nbp, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, W.plan.p, W.size1.p, W.size2.p, W.flags.p, W.records.p); SCS_LAUNCHED(c);
+        W.htotals[0] = W.htotals[1] = 0;
+        if (int rc = scan_sizes(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped)) return rc;
+        if (nfiles == 2) { if (int rc = scan_sizes(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 1)) return rc; }
+        cudaEventRecord(etot, c->st);
+        cudaEventRecord(t1, c->st);
+        emit_kernel<<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.plan.p, W.off1.p, W.off2.p, c->slab_dev[bi][0].p,
+                                                               nfiles == 2 ? c->slab_dev[bi][1].p : nullptr, W.flags.p);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
-        cudaEventRecord(ee1, c->st); cudaEventRecord(ek1, c->st);
+        cudaEventRecord(t2, c->st);
         cudaEventRecord(ekern[bi], c->st);
+        SCS_CUDA(c, cudaEventSynchronize(etot));   // byte totals of this slab (the emit kernel is already running)
+        uint64_t tot[2] = {W.htotals[0], W.htotals[1]};
+        if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
         SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[bi], 0));
-        for (int f = 0; f < nfiles; f++) if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(c->slab_host[bi][f], c->slab_dev[bi][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
+        const double tc = now_ms();
+        if (!no_d2h) for (int f = 0; f < nfiles; f++) if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(c->slab_host[bi][f], c->slab_dev[bi][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
         cudaEventRecord(ecopy[bi], c->st_copy);
         pend[bi].live = true; pend[bi].bytes[0] = tot[0]; pend[bi].bytes[1] = tot[1];
         c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
-        SCS_CUDA(c, cudaEventSynchronize(ek1));
-        float a = 0, b2 = 0; cudaEventElapsedTime(&a, ek0, ek1); cudaEventElapsedTime(&b2, ee0, ee1); msk += a; mse += b2;
-        // while this slab's copy runs, hand the previous slab to the sink
+        // while this slab is produced and copied, hand the previous one to the sink
+        const double td = now_ms();
         if (int rc = drain(bi ^ 1)) return rc;
+        if (trace) fprintf(stderr, "[scs trace] batch@%llu: start %.2f drain_own %.2f launch+wait_totals %.2f enqueue_copy %.2f drain_prev %.2f ms\n",
+                           (unsigned long long)s0, ta - tr0, tb - ta, tc - tb, td - tc, now_ms() - td);
     }
     if (int rc = drain(0)) return rc;
     if (int rc = drain(1)) return rc;
     SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[0], 0)); SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[1], 0));
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    double msk = 0, mse = 0;
+    for (size_t i = 0; i + 2 < tev.size(); i += 3) {
+        float a = 0, b2 = 0; cudaEventElapsedTime(&a, tev[i], tev[i + 2]); cudaEventElapsedTime(&b2, tev[i + 1], tev[i + 2]); msk += a; mse += b2;
+    }
+    for (auto ev : tev) cudaEventDestroy(ev);
     c->stats.ms_reads = ms; c->stats.ms_reads_kernels = msk; c->stats.ms_emit_kernel = mse;
-    int hflags = 0; SCS_CUDA(c, cudaMemcpy(&hflags, flags.p, 4, cudaMemcpyDeviceToHost));
-    unsigned long long hrec = 0; SCS_CUDA(c, cudaMemcpy(&hrec, drec.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(ek0); cudaEventDestroy(ek1); cudaEventDestroy(ee0); cudaEventDestroy(ee1);
+    int hflags = 0; SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
+    unsigned long long hrec = 0; SCS_CUDA(c, memcpy_sync(c, &hrec, W.records.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(etot);
     for (int b = 0; b < 2; b++) { cudaEventDestroy(ecopy[b]); cudaEventDestroy(ekern[b]); }
     if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
     if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
+    if (hflags & 16) return c->fail(SCS_E_NOMEM, "FASTQ slab overflow (raise slab_bytes)");
     return SCS_OK;
 }
 
@@ -483,8 +585,8 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     if (flags[r] != 0) { if (lane == 0) out_len[r] = -2; return; }   // more than kMaxEvents indel events
     if (np > kSrcCap || np > out_stride) { if (lane == 0) out_len[r] = -1; return; }
     __syncwarp();
-    const uint8_t* src = build_source(S, RL, nev, lane, ws);
-    subst_quality_pass(S, T, src, np, isRead1, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
+    const uint8_t* src = build_source(S, np, nev, lane, ws);
+    subst_quality_pass(S, T, nullptr, src, np, isRead1, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
     if (lane == 0) out_len[r] = np;
 }
 
@@ -498,19 +600,19 @@ int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const u
     SCS_CUDA(c, dsrc.reserve((size_t)n_reads * RL + 16)); SCS_CUDA(c, dseq.reserve((size_t)n_reads * out_stride + 16)); SCS_CUDA(c, dqual.reserve((size_t)n_reads * out_stride + 16));
     SCS_CUDA(c, dreal.reserve((size_t)n_reads * stride_real + 4096)); SCS_CUDA(c, dint.reserve((size_t)n_reads * stride_int + 4096));
     SCS_CUDA(c, dlen.reserve(n_reads + 1)); SCS_CUDA(c, flags.reserve(n_reads + 1));
-    SCS_CUDA(c, cudaMemset(dreal.p, 0, dreal.cap * 4)); SCS_CUDA(c, cudaMemset(dint.p, 0, dint.cap * 4)); SCS_CUDA(c, cudaMemset(flags.p, 0, flags.cap * 4));
-    SCS_CUDA(c, cudaMemset(dseq.p, 0, dseq.cap)); SCS_CUDA(c, cudaMemset(dqual.p, 0, dqual.cap));
-    SCS_CUDA(c, cudaMemcpy(dsrc.p, src, (size_t)n_reads * RL, cudaMemcpyHostToDevice));
-    SCS_CUDA(c, cudaMemcpy(dreal.p, real, (size_t)n_reads * stride_real * 4, cudaMemcpyHostToDevice));
-    SCS_CUDA(c, cudaMemcpy(dint.p, ints, (size_t)n_reads * stride_int * 4, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memset_sync(c, dreal.p, 0, dreal.cap * 4)); SCS_CUDA(c, memset_sync(c, dint.p, 0, dint.cap * 4)); SCS_CUDA(c, memset_sync(c, flags.p, 0, flags.cap * 4));
+    SCS_CUDA(c, memset_sync(c, dseq.p, 0, dseq.cap)); SCS_CUDA(c, memset_sync(c, dqual.p, 0, dqual.cap));
+    SCS_CUDA(c, memcpy_sync(c, dsrc.p, src, (size_t)n_reads * RL, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, dreal.p, real, (size_t)n_reads * stride_real * 4, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, dint.p, ints, (size_t)n_reads * stride_int * 4, cudaMemcpyHostToDevice));
     ReadTables T = make_tables(c);
     test_predict_kernel<<<(n_reads + kReadWarps - 1) / kReadWarps, kReadWarps * 32, 0, c->st>>>(T, dsrc.p, n_reads, is_read1, dreal.p, stride_real, dint.p, stride_int,
                                                                                               dseq.p, dqual.p, out_stride, dlen.p, flags.p);
     SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    SCS_CUDA(c, cudaMemcpy(out_seq, dseq.p, (size_t)n_reads * out_stride, cudaMemcpyDeviceToHost));
-    SCS_CUDA(c, cudaMemcpy(out_qual, dqual.p, (size_t)n_reads * out_stride, cudaMemcpyDeviceToHost));
-    SCS_CUDA(c, cudaMemcpy(out_len, dlen.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, out_seq, dseq.p, (size_t)n_reads * out_stride, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, out_qual, dqual.p, (size_t)n_reads * out_stride, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, out_len, dlen.p, (size_t)n_reads * 4, cudaMemcpyDeviceToHost));
     return SCS_OK;
 }
 
@@ -532,7 +634,7 @@ __global__ void full_seq_kernel(Genome g, const uint64_t* __restrict__ desc, con
 int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written) {
     const uint64_t n = c->fulls.n;
     std::vector<uint64_t> d(n);
-    if (n) SCS_CUDA(c, cudaMemcpy(d.data(), c->fulls.desc.p, n * 8, cudaMemcpyDeviceToHost));
+    if (n) SCS_CUDA(c, memcpy_sync(c, d.data(), c->fulls.desc.p, n * 8, cudaMemcpyDeviceToHost));
     std::vector<uint64_t> offs(n + 1, 0);
     for (uint64_t i = 0; i < n; i++) offs[i + 1] = offs[i] + unpack_desc(d[i]).len + 1;
     *written = (int64_t)offs[n];
@@ -541,11 +643,11 @@ int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written) {
     if (n == 0) return SCS_OK;
     DevBuf<uint64_t> doffs; DevBuf<char> dout;
     SCS_CUDA(c, doffs.reserve(n + 1)); SCS_CUDA(c, dout.reserve(offs[n] + 16));
-    SCS_CUDA(c, cudaMemcpy(doffs.p, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    SCS_CUDA(c, memcpy_sync(c, doffs.p, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
     Genome g; g.words = c->genome_words.p; g.n_bases = c->genome_bases;
     full_seq_kernel<<<(unsigned)n, 128, 0, c->st>>>(g, c->fulls.desc.p, c->fulls.errref.p, c->err_pool.p, doffs.p, n, dout.p); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    SCS_CUDA(c, cudaMemcpy(buf, dout.p, offs[n], cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, buf, dout.p, offs[n], cudaMemcpyDeviceToHost));
     return SCS_OK;
 }
 
