@@ -12,8 +12,9 @@ synthesis -> FASTQ packing, FASTQ landing in the library's pinned host ring.
   value : M reads/s with the packed genome already resident in HBM when the timed region starts (CUDA events).
   e2e   : the same through the C-ABI calls a user makes with HOST buffers: scs_set_genome (H2D of the ASCII genome
           from pinned memory + pack) ... scs_yield_reads_sink (D2H of every FASTQ byte) inside the timed region.
-For N > 1 (torchrun) every rank runs the same per-GPU workload on its own chromosome of the cell (weak scaling);
-NCCL is used for the step barrier and the max-over-ranks reduction only.
+For N > 1 (torchrun) the cell has N such chromosomes, one per rank (weak scaling: per-GPU work fixed). The ranks form ONE
+run: NCCL all-reduces carry the primer budget per amplification round, the per-batch amplicon counts and the cell-wide
+weight vector of the read allocation; every rank then writes its own FASTQ shard.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/bin/scssim, built from /root/reference by
 oracle/build_ref.sh) with all host threads on a bounded sample of the same workload.
@@ -141,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN, help="(debug) override the workload size; invalidates the number")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="(debug) skip the CPU leg")
+    ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(a.warmup, 0)
@@ -181,7 +183,11 @@ def main():
         pinned = torch.empty(glen, dtype=torch.uint8, pin_memory=True)
         pinned.numpy()[:] = seq
         named = [(f"chrS{rank + 1}_1_{glen}", pinned.numpy())]
-        g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55 + rank, device=local, slab_bytes=256 << 20)
+        # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream
+        g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world, slab_bytes=a.slab_mb << 20)
+        if world > 1:
+            from scssim_b200.dist import make_collectives
+            g.set_collectives(*make_collectives(dist, device=f"cuda:{local}"))
         g.load_profile(profile)
         g.set_genome(named).create_frags()
 
@@ -255,7 +261,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name() if glen == GENOME_LEN else f"DEBUG {glen} bp", "per_gpu": "one 250 Mb chromosome per rank", "layout": "PE", "read_length": READ_LEN,
+            "config": {"workload": workload_name() if glen == GENOME_LEN else f"DEBUG {glen} bp", "per_gpu": "one 250 Mb chromosome per rank; ranks form one cell (global read allocation over NCCL)", "layout": "PE", "read_length": READ_LEN,
                        "reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": bytes_all * a.steps / dev_s / 1e9,
                        "full_amplicons": n_fulls, "semi_amplicons": n_semis,
                        "l2": "every step streams ~5 GB of FASTQ through L2 (>> 126 MB), evicting the 62 MB packed genome between steps",

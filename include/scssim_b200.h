@@ -51,7 +51,7 @@ typedef struct scs_params {
     int32_t rank;         /* shard index in [0, world) */
     int32_t world;        /* number of shards (GPUs) */
     int32_t reserved;
-    uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (128 MiB) */
+    uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (64 MiB) */
 } scs_params;
 
 void scs_default_params(scs_params* p);

@@ -22,7 +22,25 @@ __device__ __forceinline__ double draw_r(uint32_t x) {   // randomDouble(ZERO_FI
     return __dadd_rn(2.2204e-16, __dmul_rn(__dadd_rn(1.0, -2.2204e-16), (double)x / 4294967296.0));
 }
 
-__global__ void __launch_bounds__(256) weights_kernel(DrawSrc src, const double* __restrict__ gcf_tape, uint64_t global0, uint64_t n,
+__global__ void __launch_bounds__(256) full_gidx_kernel(ListGeom G, uint64_t n, uint64_t* __restrict__ gidx) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) gidx[i] = global_index(G, i);
+}
+__global__ void __launch_bounds__(256) scatter_f64_kernel(const double* __restrict__ src, const uint64_t* __restrict__ gidx, uint64_t n, double* __restrict__ dst) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[gidx[i]] = src[i];
+}
+__global__ void __launch_bounds__(256) gather_counts_kernel(const double* __restrict__ wg, const uint32_t* __restrict__ cg, const uint64_t* __restrict__ sbase_g,
+                                                            const uint64_t* __restrict__ gidx, uint64_t n, int paired, double* __restrict__ w,
+                                                            uint32_t* __restrict__ counts, uint64_t* __restrict__ slot_gbase, uint32_t* __restrict__ slots) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t g = gidx[i];
+    const uint32_t v = cg[g];
+    w[i] = wg[g]; counts[i] = v; slot_gbase[i] = sbase_g[g]; slots[i] = paired ? (v >> 1) : v;
+}
+
+__global__ void __launch_bounds__(256) weights_kernel(DrawSrc src, const double* __restrict__ gcf_tape, const uint64_t* __restrict__ gidx, uint64_t n,
                                                       const uint64_t* __restrict__ desc, const uint32_t* __restrict__ gc,
                                                       const double* __restrict__ gcMeans, double gcStd, double* __restrict__ w) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -31,10 +49,10 @@ __global__ void __launch_bounds__(256) weights_kernel(DrawSrc src, const double*
     uint32_t pct = 100u * gc[i] / len;   // Amplicon.cpp:398
     double f = 0.0;
     if (pct <= 100u) {
-        if (gcf_tape) f = gcf_tape[global0 + i];
+        if (gcf_tape) f = gcf_tape[gidx[i]];
         else {
             // Marsaglia polar normal on Philox draws, redrawn until >= 0 (Profile.cpp:1508-1511)
-            Stream s; s.init(src, D_GCF, global0 + i, 0);
+            Stream s; s.init(src, D_GCF, gidx[i], 0);
             double mean = gcMeans[pct]; uint32_t k = 0;
             for (;;) {
                 double u1 = __dadd_rn((double)s.at(E_REAL, k), 0.5) / 4294967296.0;
@@ -126,30 +144,50 @@ __global__ void __launch_bounds__(256) parity_slots_kernel(uint32_t* __restrict_
 int set_read_counts(scs_ctx* c) {
     if (!c->amplified) return c->fail(SCS_E_STATE, "scs_set_read_counts: call scs_amplify first");
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_set_read_counts: no profile loaded");
-    if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "scs_set_read_counts: multi-rank allocation is not wired yet");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
-    const uint64_t n = c->fulls.n;
-    // Malbac::yieldReads: reads = refLen * coverage / readLength (Malbac.cpp:420), individual reads
+    const uint64_t n = c->fulls.n;   // local
+    const ListGeom G = list_geom(c->full_batch_total, c->full_batch_before, c->full_batch_local);
+    uint64_t N = 0; for (auto v : c->full_batch_total) N += v;   // all ranks
+    const bool multi = c->P.world > 1;
+    // Malbac::yieldReads: reads = refLen * coverage / readLength (Malbac.cpp:420), individual reads, whole cell
     c->reads_requested = (uint64_t)((double)c->ref_len_half * c->P.coverage / (double)c->prof.readLength);
     c->stats.reads_requested = c->reads_requested;
     SCS_CUDA(c, c->weights.reserve(n + 1)); SCS_CUDA(c, c->counts.reserve(n + 1)); SCS_CUDA(c, c->slot_base.reserve(n + 2));
+    SCS_CUDA(c, c->full_gidx.reserve(n + 1)); SCS_CUDA(c, c->slot_gbase.reserve(n + 1));
     c->n_slots = 0;
-    if (n == 0) { c->have_counts = true; return SCS_OK; }   // the reference crashes on an empty amplicon list; we emit nothing
+    if (N == 0) { c->have_counts = true; return SCS_OK; }   // the reference crashes on an empty amplicon list; we emit nothing
     DevBuf<double> gcm; SCS_CUDA(c, gcm.reserve(101));
     SCS_CUDA(c, cudaMemcpyAsync(gcm.p, c->prof.gcMeans, 101 * 8, cudaMemcpyHostToDevice, c->st));
-    const unsigned nb = (unsigned)((n + 255) / 256);
-    weights_kernel<<<nb, 256, 0, c->st>>>(draw_src(c, D_GCF), c->replay.on ? c->replay.gcf.p : nullptr, 0, n, c->fulls.desc.p, c->fulls.gc.p, gcm.p,
-                                          c->prof.gcStd, c->weights.p); SCS_LAUNCHED(c);
-    const uint64_t nch = (n + kChunk - 1) / kChunk;
+    const unsigned nbl = (unsigned)((n + 255) / 256), nb = (unsigned)((N + 255) / 256);
+    if (n) {
+        full_gidx_kernel<<<nbl, 256, 0, c->st>>>(G, n, c->full_gidx.p); SCS_LAUNCHED(c);
+        weights_kernel<<<nbl, 256, 0, c->st>>>(draw_src(c, D_GCF), c->replay.on ? c->replay.gcf.p : nullptr, c->full_gidx.p, n, c->fulls.desc.p, c->fulls.gc.p,
+                                               gcm.p, c->prof.gcStd, c->weights.p); SCS_LAUNCHED(c);
+    }
+    // The allocation itself is defined on the whole cell's list. With several ranks every rank gets the full weight vector
+    // (one all-reduce of a scattered copy) and runs the identical allocation, so the result does not depend on the rank count.
+    DevBuf<double> wg_buf; DevBuf<uint32_t> cg_buf;
+    double* wg = c->weights.p; uint32_t* cg = c->counts.p;
+    if (multi) {
+        SCS_CUDA(c, wg_buf.reserve(N + 1)); SCS_CUDA(c, cg_buf.reserve(N + 1));
+        wg = wg_buf.p; cg = cg_buf.p;
+        SCS_CUDA(c, cudaMemsetAsync(wg, 0, N * 8, c->st));
+        if (n) { scatter_f64_kernel<<<nbl, 256, 0, c->st>>>(c->weights.p, c->full_gidx.p, n, wg); SCS_LAUNCHED(c); }
+        std::vector<double> hw(N);
+        SCS_CUDA(c, memcpy_sync(c, hw.data(), wg, N * 8, cudaMemcpyDeviceToHost));
+        if (int rc = allreduce_f64(c, hw.data(), N)) return rc;
+        SCS_CUDA(c, memcpy_sync(c, wg, hw.data(), N * 8, cudaMemcpyHostToDevice));
+    }
+    const uint64_t nch = (N + kChunk - 1) / kChunk;
     DevBuf<double> dsums; SCS_CUDA(c, dsums.reserve(nch + 1));
     std::vector<double> hs(nch);
-    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p); SCS_LAUNCHED(c);
+    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaMemcpyAsync(hs.data(), dsums.p, nch * 8, cudaMemcpyDeviceToHost, c->st));
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
     double S = 0; for (uint64_t k = 0; k < nch; k++) S += hs[k];
     DevBuf<unsigned long long> dtot; SCS_CUDA(c, dtot.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(dtot.p, 0, 8, c->st));
-    normalize_floor_kernel<<<nb, 256, 0, c->st>>>(c->weights.p, n, kEpsH + S, (double)(long)c->reads_requested, c->counts.p, dtot.p); SCS_LAUNCHED(c);
-    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p); SCS_LAUNCHED(c);
+    normalize_floor_kernel<<<nb, 256, 0, c->st>>>(wg, N, kEpsH + S, (double)(long)c->reads_requested, cg, dtot.p); SCS_LAUNCHED(c);
+    chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p); SCS_LAUNCHED(c);
     unsigned long long floorSum = 0;
     SCS_CUDA(c, cudaMemcpyAsync(&floorSum, dtot.p, 8, cudaMemcpyDeviceToHost, c->st));
     SCS_CUDA(c, cudaMemcpyAsync(hs.data(), dsums.p, nch * 8, cudaMemcpyDeviceToHost, c->st));
@@ -176,21 +214,33 @@ int set_read_counts(scs_ctx* c) {
     for (uint64_t k = 0; k < nch; k++) { pref[k] = nsamp; nsamp += ns[k]; }
     pref[nch] = nsamp;
     if (nsamp) {
-        DevBuf<double> cdf; SCS_CUDA(c, cdf.reserve(n + 1));
+        DevBuf<double> cdf; SCS_CUDA(c, cdf.reserve(N + 1));
         DevBuf<uint64_t> dpref; SCS_CUDA(c, dpref.reserve(nch + 1));
         SCS_CUDA(c, cudaMemcpyAsync(dpref.p, pref.data(), (nch + 1) * 8, cudaMemcpyHostToDevice, c->st));
-        chunk_cdf_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(c->weights.p, n, dsums.p, cdf.p); SCS_LAUNCHED(c);
-        chunk_sample_kernel<<<(unsigned)((nsamp + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_MULTC), 0, n, nch, dpref.p, nsamp, cdf.p, c->counts.p); SCS_LAUNCHED(c);
-        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        chunk_cdf_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p, cdf.p); SCS_LAUNCHED(c);
+        chunk_sample_kernel<<<(unsigned)((nsamp + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_MULTC), 0, N, nch, dpref.p, nsamp, cdf.p, cg); SCS_LAUNCHED(c);
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));   // pref (host) is read by the copy above
     }
-    DevBuf<uint32_t> tmp; SCS_CUDA(c, tmp.reserve(n + 1));
-    DevBuf<uint64_t> oddp; SCS_CUDA(c, oddp.reserve(n + 1));
+    DevBuf<uint32_t> tmp; SCS_CUDA(c, tmp.reserve(N + 1));
+    DevBuf<uint64_t> oddp, sbase_g; SCS_CUDA(c, oddp.reserve(N + 1));
     if (c->P.paired) {
-        odd_flags_kernel<<<nb, 256, 0, c->st>>>(c->counts.p, n, tmp.p); SCS_LAUNCHED(c);
-        if (int rc = exclusive_scan_u32(c, tmp.p, oddp.p, n, nullptr)) return rc;
+        odd_flags_kernel<<<nb, 256, 0, c->st>>>(cg, N, tmp.p); SCS_LAUNCHED(c);
+        if (int rc = exclusive_scan_u32(c, tmp.p, oddp.p, N, nullptr)) return rc;
     }
-    parity_slots_kernel<<<nb, 256, 0, c->st>>>(c->counts.p, n, oddp.p, 0, c->P.paired, tmp.p); SCS_LAUNCHED(c);
-    if (int rc = exclusive_scan_u32(c, tmp.p, c->slot_base.p, n, &c->n_slots)) return rc;
+    parity_slots_kernel<<<nb, 256, 0, c->st>>>(cg, N, oddp.p, 0, c->P.paired, tmp.p); SCS_LAUNCHED(c);
+    if (!multi) {
+        if (int rc = exclusive_scan_u32(c, tmp.p, c->slot_base.p, N, &c->n_slots)) return rc;
+        SCS_CUDA(c, cudaMemcpyAsync(c->slot_gbase.p, c->slot_base.p, N * 8, cudaMemcpyDeviceToDevice, c->st));
+    } else {
+        SCS_CUDA(c, sbase_g.reserve(N + 1));
+        if (int rc = exclusive_scan_u32(c, tmp.p, sbase_g.p, N, nullptr)) return rc;
+        DevBuf<uint32_t> lslots; SCS_CUDA(c, lslots.reserve(n + 1));
+        if (n) {
+            gather_counts_kernel<<<nbl, 256, 0, c->st>>>(wg, cg, sbase_g.p, c->full_gidx.p, n, c->P.paired, c->weights.p, c->counts.p, c->slot_gbase.p, lslots.p);
+            SCS_LAUNCHED(c);
+            if (int rc = exclusive_scan_u32(c, lslots.p, c->slot_base.p, n, &c->n_slots)) return rc;
+        }
+    }
     SCS_CUDA(c, cudaMemcpyAsync(c->slot_base.p + n, &c->n_slots, 8, cudaMemcpyHostToDevice, c->st));
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_alloc = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);

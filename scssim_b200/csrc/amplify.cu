@@ -25,13 +25,27 @@ constexpr int kMaxErrPerAmp = 96;                // per-amplicon staging (own + 
 
 struct AmpParams {
     uint32_t thr_ber;        // error iff x < thr_ber   (p < ber, ber = 3.4e-4, Config.cpp:46)
-    uint64_t entity_base;    // (round << 40) | global index of this rank's template 0
+    uint64_t round_tag;      // round << 40
+    uint64_t base0;          // global index of this rank's template 0 (fragments: contiguous per rank)
     uint64_t mark_base;      // replay: index of template 0's mark inside the domain's mark array
+    int use_geom;            // semi amplicons: global index through the list geometry
+    ListGeom geom;
 };
+__device__ __forceinline__ uint64_t tmpl_entity(const AmpParams& ap, uint64_t t) {
+    return ap.round_tag | (ap.base0 + (ap.use_geom ? global_index(ap.geom, t) : t));
+}
+
+__global__ void __launch_bounds__(256) sum_len_kernel(const uint64_t* __restrict__ desc, uint64_t n, unsigned long long* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = i < n ? unpack_desc(desc[i]).len : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
+}
 
 // ---------------------------------------------------------------------------------- K1
 // k ~ Poisson(lambda) by Knuth's product method in log space, exactly the reference's loop.
-__global__ void __launch_bounds__(256) assign_primers_kernel(DrawSrc src, uint64_t entity_base, uint64_t mark_base, const uint64_t* __restrict__ desc,
+__global__ void __launch_bounds__(256) assign_primers_kernel(DrawSrc src, AmpParams ap, const uint64_t* __restrict__ desc,
                                                              uint64_t n, double expected, double totalLen, uint32_t mask, uint32_t* __restrict__ primers,
                                                              unsigned long long* __restrict__ count) {
     uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -39,7 +53,7 @@ __global__ void __launch_bounds__(256) assign_primers_kernel(DrawSrc src, uint64
     if (t < n) {
         Tmpl T = unpack_desc(desc[t]);
         double lambda = __dmul_rn(expected, __ddiv_rn(__dmul_rn(1.0, (double)T.len), totalLen));
-        Stream s; s.init(src, D_POIS, entity_base + t, mark_base + t);
+        Stream s; s.init(src, D_POIS, tmpl_entity(ap, t), ap.mark_base + t);
         double log1 = 0.0, log2 = -lambda; long long x = -1; uint32_t i = 0;
         do {
             uint32_t d = s.at(E_REAL, i++);
@@ -118,7 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
             const uint32_t* terr = nullptr; uint32_t tnerr = 0;
             if (!FROM_FRAG) { uint64_t er = errref[t]; tnerr = (uint32_t)(er & 0xFFFF); terr = err_pool + (er >> 16); }
             const uint64_t slot0 = slot_off[t];
-            Stream S; S.init(src, FROM_FRAG ? D_AMPF : D_AMPS, ap.entity_base + t, ap.mark_base + t);
+            Stream S; S.init(src, FROM_FRAG ? D_AMPF : D_AMPS, tmpl_entity(ap, t), ap.mark_base + t);
             const uint32_t bw = (T.len + 31) >> 5;
             for (uint32_t w = lane; w < bw; w += 32) bitmap[w] = 0;
             __syncwarp();
@@ -266,43 +280,43 @@ struct Round {
     DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
     DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created;
 
-    int allreduce_u64(uint64_t* v, size_t n) {
-        if (c->P.world <= 1) return SCS_OK;
-        if (!c->ar_u64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
-        return c->ar_u64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
+    int allreduce_u64(uint64_t* v, size_t n) { return scs::allreduce_u64(c, v, n); }
+
+    AmpParams params(int round, bool semis, int domain) {
+        AmpParams ap{}; ap.thr_ber = thr_ber; ap.round_tag = (uint64_t)round << 40;
+        if (semis) { ap.use_geom = 1; ap.base0 = 0; ap.geom = list_geom(c->semi_batch_total, c->semi_batch_before, c->semi_batch_local); ap.mark_base = mark_base(domain, round); }
+        else { ap.use_geom = 0; ap.base0 = c->frag_global0; ap.mark_base = mark_base(domain, round) + c->frag_global0; }
+        return ap;
     }
 
     // Malbac::setPrimers (Malbac.cpp:236-283)
     int set_primers(bool onlyFrags, int round) {
-        uint64_t nF = c->frag_hi - c->frag_lo, nS = onlyFrags ? 0 : c->semis.n;
-        // global template count and total length (lengths are integers: the FP64 sum is exact in any order)
-        uint64_t g3[3] = {0, 0, 0};
-        g3[0] = c->frags.size();
-        for (auto& f : c->frags) g3[1] += (uint64_t)f.len;
+        uint64_t nF = c->frags.size(), nS = onlyFrags ? 0 : c->semis.n;
+        // template count and total length over all ranks (lengths are integers: the FP64 sum is exact in any order)
         uint64_t loc[2] = {nS, 0};
         if (nS) {
-            // sum of semi lengths: small host reduction over the descriptors would cost a copy; use a device pass
-            std::vector<uint64_t> h(nS);
-            SCS_CUDA(c, cudaMemcpyAsync(h.data(), c->semis.desc.p, nS * 8, cudaMemcpyDeviceToHost, c->st));
+            SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
+            sum_len_kernel<<<(unsigned)((nS + 255) / 256), 256, 0, c->st>>>(c->semis.desc.p, nS, dcount.p); SCS_LAUNCHED(c);
+            SCS_CUDA(c, cudaMemcpyAsync(&loc[1], dcount.p, 8, cudaMemcpyDeviceToHost, c->st));
             SCS_CUDA(c, cudaStreamSynchronize(c->st));
-            for (uint64_t i = 0; i < nS; i++) loc[1] += unpack_desc(h[i]).len;
         }
         if (int rc = allreduce_u64(loc, 2)) return rc;
-        uint64_t templateNum = g3[0] + loc[0];
-        double totalLen = (double)(g3[1] + loc[1]);
+        uint64_t templateNum = c->n_frags_global + loc[0];
+        double totalLen = (double)(c->frag_len_sum_global + loc[1]);
         uint64_t expected = (uint64_t)((double)c->total_primers * c->P.gamma * (double)templateNum);
         SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
-        // global template index: fragments first, then semis in list order (this rank's semis sit at their global list index)
-        uint64_t ebase = (uint64_t)round << 40;
+        // global template index: fragments first, then semis in (global) list order
         if (nF) {
-            assign_primers_kernel<<<(unsigned)((nF + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ebase + c->frag_lo, mark_base(D_POIS, round) + c->frag_lo,
-                                                                                  c->frag_desc.p, nF, (double)expected, totalLen, 0xFFFFFFFFu, c->frag_primers.p, dcount.p);
+            AmpParams ap = params(round, false, D_POIS);
+            assign_primers_kernel<<<(unsigned)((nF + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ap, c->frag_desc.p, nF, (double)expected, totalLen,
+                                                                                  0xFFFFFFFFu, c->frag_primers.p, dcount.p);
             SCS_LAUNCHED(c);
         }
         if (nS) {
-            if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "multi-rank semi indexing requires single-batch layout");   // replaced below by per-batch launches
-            assign_primers_kernel<<<(unsigned)((nS + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ebase + c->frags.size(), mark_base(D_POIS, round) + c->frags.size(),
-                                                                                  c->semis.desc.p, nS, (double)expected, totalLen, 0xFFFu, c->semis.primers.p, dcount.p);
+            AmpParams ap = params(round, true, D_POIS);
+            ap.base0 = c->n_frags_global; ap.mark_base += c->n_frags_global;
+            assign_primers_kernel<<<(unsigned)((nS + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_POIS), ap, c->semis.desc.p, nS, (double)expected, totalLen, 0xFFFu,
+                                                                                  c->semis.primers.p, dcount.p);
             SCS_LAUNCHED(c);
         }
         uint64_t count = 0;
@@ -325,7 +339,7 @@ struct Round {
 
     // one amplification pass over `n` templates; products appended to `dst`
     template <bool FROM_FRAG>
-    int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, uint64_t tmpl_global0, AmpList& dst,
+    int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, AmpList& dst,
              std::vector<uint64_t>& batch_total, std::vector<uint64_t>& batch_before, std::vector<uint64_t>& batch_local) {
         uint64_t total_slots = 0;
         SCS_CUDA(c, slot_off.reserve(n + 1)); SCS_CUDA(c, cprefix.reserve(n + 1)); SCS_CUDA(c, created.reserve(n + 1));
@@ -340,8 +354,7 @@ struct Round {
             uint64_t need = etop + total_slots * 12 + 4096;
             SCS_CUDA(c, c->err_pool.reserve(need, etop, c->st));
             SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(ticket.p, 0, 8, c->st));
-            AmpParams ap; ap.thr_ber = thr_ber; ap.entity_base = ((uint64_t)round << 40) + tmpl_global0;
-            ap.mark_base = mark_base(FROM_FRAG ? D_AMPF : D_AMPS, round) + tmpl_global0;
+            AmpParams ap = params(round, !FROM_FRAG, FROM_FRAG ? D_AMPF : D_AMPS);
             int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (FROM_FRAG) {
                 constexpr int W = 4, BW = (100000 + 32) / 32 + 1;
@@ -391,7 +404,7 @@ struct Round {
 
 int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     if (!c->have_frags) return c->fail(SCS_E_STATE, "scs_amplify: call scs_create_frags first");
-    if (c->P.world > 1) return c->fail(SCS_E_UNSUPPORTED, "scs_amplify: multi-rank amplification is not wired yet");
+    if (c->P.world > 1 && c->replay.on) return c->fail(SCS_E_UNSUPPORTED, "replay runs on one rank only (the reference's logs are sequential)");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
     Round R; R.c = c; R.g.words = c->genome_words.p; R.g.n_bases = c->genome_bases;
     R.thr_ber = (uint32_t)std::min<uint64_t>(count_unit_lt(3.4e-4), 0xFFFFFFFFull);
@@ -406,15 +419,15 @@ int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     c->semis.clear(); c->fulls.clear();
     c->semi_batch_total.clear(); c->semi_batch_before.clear(); c->semi_batch_local.clear();
     c->full_batch_total.clear(); c->full_batch_before.clear(); c->full_batch_local.clear();
-    const uint64_t nF = c->frag_hi - c->frag_lo;
+    const uint64_t nF = c->frags.size();
     int rc;
     if ((rc = R.set_primers(true, 0))) return rc;
-    if ((rc = R.pass<true>(0, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->frag_lo, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+    if ((rc = R.pass<true>(0, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
     for (int i = 0; i < 5; i++) {
         if (c->total_primers == 0) break;
         if ((rc = R.set_primers(false, i + 1))) return rc;
-        if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, 0, c->fulls, c->full_batch_total, c->full_batch_before, c->full_batch_local))) return rc;
-        if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->frag_lo, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+        if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, c->fulls, c->full_batch_total, c->full_batch_before, c->full_batch_local))) return rc;
+        if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
     }
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_amplify = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -16,7 +16,7 @@ namespace scs {
 // Stream all device allocations are ordered on (set at every C-ABI entry to the context's compute stream).
 // cudaMallocAsync / cudaFreeAsync from the device's default pool (release threshold = never) make the many
 // short-lived scratch buffers of the stages free of device-wide synchronisation.
-inline cudaStream_t& alloc_stream() { static cudaStream_t s = nullptr; return s; }
+inline cudaStream_t& alloc_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
 // growable device array (host-managed capacity)
 template <class T> struct DevBuf {
@@ -41,6 +41,25 @@ template <class T> struct DevBuf {
 };
 
 struct HostFrag { int32_t seq; int64_t start0; int32_t len; int32_t strand; };
+
+// Where this rank's part of an amplicon list sits in the global (all ranks) list. A batch is the output of one
+// amplification pass; inside a batch the global order is reverse creation order over all ranks' templates, and a rank's
+// products are a contiguous run of the creation order (ranks own contiguous template ranges).
+struct ListGeom {
+    int nb;
+    uint64_t lend[6];    // local list size after batch b
+    uint64_t ltot[6];    // local products in batch b
+    uint64_t gbase[6];   // global list size before batch b
+    uint64_t gtot[6];    // global products in batch b
+    uint64_t before[6];  // products of lower ranks in batch b
+};
+__host__ __device__ inline uint64_t global_index(const ListGeom& G, uint64_t t) {
+    int b = 0;
+    while (b + 1 < G.nb && t >= G.lend[b]) b++;
+    const uint64_t q = t - (b ? G.lend[b - 1] : 0);                 // position inside the local batch (reverse creation order)
+    const uint64_t crank = G.before[b] + (G.ltot[b] - 1 - q);       // global creation rank
+    return G.gbase[b] + (G.gtot[b] - 1 - crank);
+}
 
 // amplicon list (semi or full), structure of arrays, list order = the reference's -t 1 order
 struct AmpList {
@@ -97,7 +116,11 @@ struct scs_ctx {
     uint64_t ref_len_half = 0;
 
     // fragments
-    std::vector<scs::HostFrag> frags; uint64_t frag_lo = 0, frag_hi = 0;   // this rank's global range
+    std::vector<scs::HostFrag> frags;   // this rank's fragments (cut from its own sequences)
+    uint64_t frag_lo = 0, frag_hi = 0;  // [0, frags.size())
+    // global geometry (world > 1: every rank holds its own sequences of the cell)
+    uint64_t seq_global0 = 0, frag_global0 = 0, n_frags_global = 0, frag_len_sum_global = 0, ref_len_sum = 0;
+    scs::DevBuf<uint64_t> full_gidx, slot_gbase;   // per local full amplicon: global list index, global id of its first slot
     scs::DevBuf<uint64_t> frag_desc; scs::DevBuf<uint32_t> frag_primers; bool have_frags = false;
 
     scs::AmpList semis, fulls;
@@ -167,6 +190,9 @@ DrawSrc draw_src(const scs_ctx* c, int domain);
 uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, uint64_t mark_index, uint64_t i);
 
 // device exclusive scan: out[i] = sum_{j<i} in[j] (u64), returns total through *total_dev (device pointer, may be null)
+ListGeom list_geom(const std::vector<uint64_t>& total, const std::vector<uint64_t>& before, const std::vector<uint64_t>& local);
+int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n);
+int allreduce_f64(scs_ctx* c, double* v, size_t n);
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
 // same for n <= 2048*2048 without allocation or synchronisation: scratch holds 2048+8 u64, the total is left in *total_dev
 int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev);

@@ -167,7 +167,7 @@ int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* co
         refLen += (uint64_t)atoi(us == std::string::npos ? nm.c_str() : nm.c_str() + us + 1);
     }
     if (goff >= (1ull << 40)) return c->fail(SCS_E_ARG, "genome too large");
-    c->ref_len_half = refLen / 2;
+    c->ref_len_sum = refLen; c->ref_len_half = refLen / 2;
     c->genome_bases = goff;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     SCS_CUDA(c, c->genome_words.reserve(goff / 32 + 2));
@@ -255,7 +255,9 @@ DrawSrc draw_src(const scs_ctx* c, int domain) {
 uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, uint64_t mark_index, uint64_t i) {
     if (c->replay.on) {
         const std::vector<uint32_t>& t = (domain == D_MULTM) ? c->replay.h_mreal : c->replay.h_mrand;
-        uint64_t off = c->replay.hmarks[domain][3 * mark_index + 1 + engine] + i;
+        const std::vector<uint64_t>& hm = c->replay.hmarks[domain];
+        if (3 * mark_index + 2 >= hm.size()) return 0u;
+        uint64_t off = hm[3 * mark_index + 1 + engine] + i;
         return off < t.size() ? t[off] : 0u;
     }
     uint32_t o[4];
@@ -264,14 +266,42 @@ uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, ui
     return o[i & 3];
 }
 
+int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n) {
+    if (c->P.world <= 1) return SCS_OK;
+    if (!c->ar_u64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
+    return c->ar_u64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
+}
+int allreduce_f64(scs_ctx* c, double* v, size_t n) {
+    if (c->P.world <= 1) return SCS_OK;
+    if (!c->ar_f64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
+    return c->ar_f64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
+}
+
+ListGeom list_geom(const std::vector<uint64_t>& total, const std::vector<uint64_t>& before, const std::vector<uint64_t>& local) {
+    ListGeom G{}; G.nb = (int)std::min<size_t>(total.size(), 6);
+    uint64_t le = 0, gb = 0;
+    for (int b = 0; b < G.nb; b++) {
+        le += local[b]; G.lend[b] = le; G.ltot[b] = local[b]; G.gbase[b] = gb; G.gtot[b] = total[b]; G.before[b] = before[b];
+        gb += total[b];
+    }
+    if (G.nb == 0) { G.nb = 1; G.lend[0] = 0; G.ltot[0] = 0; G.gbase[0] = 0; G.gtot[0] = 0; G.before[0] = 0; }
+    return G;
+}
+
 int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782
     if (!c->have_genome) return c->fail(SCS_E_STATE, "scs_create_frags: no genome loaded");
     const uint32_t fragMin = 10000, fragMax = 100000;   // Fragment.cpp:15-16
+    const int W = std::max(1, c->P.world), R = c->P.rank;
+    // global sequence numbering: rank r's sequences follow those of ranks < r
+    std::vector<uint64_t> v(2 * (size_t)W + 1, 0);
+    v[R] = c->seq_len.size();
+    if (int rc = allreduce_u64(c, v.data(), W)) return rc;
+    c->seq_global0 = 0; for (int r = 0; r < R; r++) c->seq_global0 += v[r];
     std::vector<HostFrag> all;
     for (size_t s = 0; s < c->seq_len.size(); s++) {
         int64_t chrLen = (int64_t)c->seq_len[s], start = 1; uint64_t i = 0;
         while (start <= chrLen) {
-            int32_t fl = (int32_t)uni_trunc(host_draw(c, D_FRAG, E_REAL, s, s, i++), fragMin, fragMax + 1 - fragMin);
+            int32_t fl = (int32_t)uni_trunc(host_draw(c, D_FRAG, E_REAL, c->seq_global0 + s, s, i++), fragMin, fragMax + 1 - fragMin);
             if (start + fl - 1 > chrLen) break;
             all.push_back({(int32_t)s, start - 1, fl, 1});
             all.push_back({(int32_t)s, start - 1, fl, -1});
@@ -283,13 +313,22 @@ int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782
             all.push_back({(int32_t)s, start - 1, fl, 1});
         }
     }
+    // fragment numbering, total template length and the cell's reference length over all ranks
+    std::fill(v.begin(), v.end(), 0);
+    v[R] = all.size();
+    for (auto& f : all) v[W + R] += (uint64_t)f.len;
+    v[2 * W] = c->ref_len_sum;
+    if (int rc = allreduce_u64(c, v.data(), v.size())) return rc;
+    c->frag_global0 = 0; c->n_frags_global = 0; c->frag_len_sum_global = 0;
+    for (int r = 0; r < W; r++) { if (r < R) c->frag_global0 += v[r]; c->n_frags_global += v[r]; c->frag_len_sum_global += v[W + r]; }
+    c->ref_len_half = v[2 * W] / 2;
     c->stats.n_frags = all.size();
-    scs_shard_range(all.size(), c->P.rank, c->P.world, &c->frag_lo, &c->frag_hi);
-    c->frags = all;   // every rank keeps the (tiny) global table; it amplifies [frag_lo, frag_hi)
-    uint64_t nloc = c->frag_hi - c->frag_lo;
+    c->frag_lo = 0; c->frag_hi = all.size();
+    c->frags = all;
+    uint64_t nloc = all.size();
     std::vector<uint64_t> desc(nloc);
     for (uint64_t k = 0; k < nloc; k++) {
-        const HostFrag& f = all[c->frag_lo + k];
+        const HostFrag& f = all[k];
         uint64_t g = c->seq_goff[f.seq] + (uint64_t)f.start0;
         // amplification template = complement(stored): strand -1 -> genome forward, strand +1 -> reverse complement
         desc[k] = f.strand == 1 ? pack_desc(g + f.len - 1, 1, (uint32_t)f.len) : pack_desc(g, 0, (uint32_t)f.len);

@@ -224,8 +224,8 @@ __device__ __forceinline__ void copy_out(char* __restrict__ dst, const char* __r
 
 struct SlabArgs {
     uint64_t slot0, nslots;            // this launch covers local slots [slot0, slot0 + nslots)
-    uint64_t slot_global0;             // global id of local slot 0 (Philox entity / replay mark index)
-    uint64_t amp_global0;              // global index of local amplicon 0 (FASTQ header)
+    const uint64_t* slot_gbase;        // per amplicon: global id of its first slot (Philox entity / replay mark index)
+    const uint64_t* amp_gidx;          // per amplicon: global list index (FASTQ header)
     uint64_t n_amp;
     const uint64_t* slot_base;         // [n_amp + 1] exclusive prefix of slots per amplicon
     const uint64_t* desc; const uint64_t* errref; const uint32_t* err_pool;
@@ -259,13 +259,15 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     const uint64_t a = find_amplicon(A.slot_base, A.n_amp, slot, lane);
     const Tmpl F = unpack_desc(__ldg(A.desc + a));
     const int RL = T.RL; const int ampLen = (int)F.len;
-    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - __ldg(A.slot_base + a)) + 1u;
-    const uint32_t ampIdx = (uint32_t)(A.amp_global0 + a);
+    const uint64_t sb = __ldg(A.slot_base + a);
+    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - sb) + 1u;
+    const uint32_t ampIdx = (uint32_t)__ldg(A.amp_gidx + a);
+    const uint64_t entity = __ldg(A.slot_gbase + a) + (slot - sb);
     if (fragNo == 0 || ampLen < RL) {   // dropped slot / Amplicon.cpp:442
         if (!EMIT && lane == 0) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; }
         return;
     }
-    Stream S; S.init(dsrc, D_READ, A.slot_global0 + slot, A.slot_global0 + slot);
+    Stream S; S.init(dsrc, D_READ, entity, entity);
     uint32_t cr = 0, ci = 0;
     int pos = 0, isz = RL;
     if (T.paired) {
@@ -365,7 +367,8 @@ __global__ void __launch_bounds__(256) fail_count_kernel(DrawSrc dsrc, ReadTable
     uint64_t lo = 0, hi = A.n_amp;
     while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (A.slot_base[mid] <= slot) lo = mid; else hi = mid; }
     const int ampLen = (int)unpack_desc(A.desc[lo]).len;
-    Stream S; S.init(dsrc, D_READ, A.slot_global0 + slot, A.slot_global0 + slot);
+    const uint64_t entity = A.slot_gbase[lo] + (slot - A.slot_base[lo]);
+    Stream S; S.init(dsrc, D_READ, entity, entity);
     uint32_t f = 0;
     for (; f <= 1001u; f++) {
         int isz = T.minInsert + count_le(T.isize, T.isizeEff, S.at(E_REAL, f));
@@ -446,7 +449,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     const uint64_t nslots = c->n_slots;
     if (nslots == 0) return SCS_OK;
     const int nfiles = c->P.paired ? 2 : 1;
-    const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (256ull << 20);
+    const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
     // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4; the emit kernel bounds-checks every store
     const uint64_t typical = 30 + 2ull * (P.readLength + 8) + 4;
     const uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(1024, slab / typical), 2048ull * 2048ull);
@@ -465,7 +468,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     ReadTables T = make_tables(c);
     Genome g; g.words = c->genome_words.p; g.n_bases = c->genome_bases;
     DrawSrc dsrc = draw_src(c, D_READ);
-    SlabArgs A; A.slot_global0 = 0; A.amp_global0 = 0; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
+    SlabArgs A; A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
     A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
     ReadScratch& W = c->rscratch;
     SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));

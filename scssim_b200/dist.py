@@ -1,0 +1,54 @@
+"""Collectives for world > 1: the two host-array all-reduces the C ABI asks for (scs_set_collectives), on top of
+torch.distributed. One process per GPU; backend NCCL on the GPU box (arrays staged through a device tensor, NVLink),
+gloo on CPU for the host-logic tests. The path has no bulk exchange: per amplification round a 2-word and a 1-word sum,
+per batch one word per rank, once the weight vector of the cell."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def make_collectives(dist, device="cuda"):
+    """Return (allreduce_u64, allreduce_f64): in-place sums over all ranks of a 1-D numpy array."""
+    import torch
+
+    def _sum(a: np.ndarray, torch_dtype):
+        t = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a)
+        if device != "cpu":
+            d = t.to(device)
+            dist.all_reduce(d, op=dist.ReduceOp.SUM)
+            t.copy_(d.cpu())
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def ar_u64(a: np.ndarray):   # two's-complement add == unsigned add
+        _sum(a, torch.int64)
+
+    def ar_f64(a: np.ndarray):
+        _sum(a, torch.float64)
+
+    return ar_u64, ar_f64
+
+
+class ThreadCollectives:
+    """In-process stand-in (ranks = threads sharing one GPU) used by the single-GPU multi-rank parity test."""
+
+    def __init__(self, world: int):
+        import threading
+        self.world, self.lock, self.bar = world, threading.Lock(), threading.Barrier(world)
+        self.acc = None
+
+    def _sum(self, a: np.ndarray):
+        self.bar.wait()
+        with self.lock:
+            if self.acc is None:
+                self.acc = a.copy()
+            else:
+                self.acc += a
+        self.bar.wait()
+        a[:] = self.acc
+        self.bar.wait()
+        with self.lock:
+            self.acc = None
+
+    def pair(self):
+        return self._sum, self._sum

@@ -1,0 +1,70 @@
+"""world_size-2 gloo test (CPU) of the multi-rank host logic: the all-reduce adapters handed to
+scs_set_collectives and the list-geometry arithmetic that turns per-rank product counts into global amplicon indices."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _global_index(lend, ltot, gbase, gtot, before, t):
+    """Python restatement of scs::global_index (scssim_b200/csrc/ctx.h)."""
+    b = 0
+    while b + 1 < len(lend) and t >= lend[b]:
+        b += 1
+    q = t - (lend[b - 1] if b else 0)
+    crank = before[b] + (ltot[b] - 1 - q)
+    return gbase[b] + (gtot[b] - 1 - crank)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scssim_b200.dist import make_collectives
+    ar_u64, ar_f64 = make_collectives(dist, device="cpu")
+    # 1. sums
+    a = np.array([rank + 1, 2 ** 63 + 5 * rank, 0], dtype=np.uint64)
+    ar_u64(a)
+    f = np.array([0.5 * (rank + 1), 1e-300], dtype=np.float64)
+    ar_f64(f)
+    # 2. the per-batch geometry exchange of amplify(): every rank contributes its product count per batch
+    local = [[3, 0, 5], [2, 4, 1]][rank]                  # products of this rank in batches 0..2
+    per_rank = np.zeros((3, world), dtype=np.uint64)
+    per_rank[:, rank] = local
+    flat = per_rank.reshape(-1).copy()
+    ar_u64(flat)
+    per_rank = flat.reshape(3, world)
+    gtot = per_rank.sum(axis=1).tolist()
+    before = per_rank[:, :rank].sum(axis=1).tolist()
+    lend = np.cumsum(local).tolist()
+    gbase = [0] + np.cumsum(gtot).tolist()[:-1]
+    gidx = [_global_index(lend, local, gbase, gtot, before, t) for t in range(sum(local))]
+    q.put((rank, a.tolist(), f.tolist(), gidx, int(sum(gtot))))
+    dist.destroy_process_group()
+
+
+def test_collectives_and_list_geometry_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    for rank, a, f, gidx, total in res:
+        assert a == [3, (2 ** 63 + 2 ** 63 + 5) % 2 ** 64, 0]
+        assert f[0] == 1.5
+    # the two ranks' global indices partition [0, total) and, inside a batch, higher ranks come first (reverse creation order)
+    all_idx = sorted(res[0][3] + res[1][3])
+    assert all_idx == list(range(res[0][4]))
+    assert res[0][3][:3] == [2 + 0, 2 + 1, 2 + 2] and res[1][3][:2] == [0, 1]   # batch 0: rank 1's 2 products precede rank 0's 3

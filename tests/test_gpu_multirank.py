@@ -1,0 +1,56 @@
+"""Multi-rank parity on one GPU: two ranks (threads, each with its own context and half of the cell's sequences,
+collectives = in-process sums) must together write exactly the records a single rank writes for the whole cell —
+same headers (global amplicon ids), same bases and qualities — because Philox streams and FASTQ headers are keyed by
+global ids. Only the record order differs (each rank emits its own amplicons)."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _records(fq: bytes):
+    lines = fq.split(b"\n")
+    assert lines[-1] == b""
+    return sorted(b"\n".join(lines[i:i + 4]) for i in range(0, len(lines) - 1, 4))
+
+
+@pytest.mark.parametrize("layout,gamma,isize", [("PE", 2e-10, 260), ("SE", 5e-10, 260), ("PE", 2e-10, 1200)])
+def test_two_ranks_equal_one_rank(tmp_path, layout, gamma, isize):
+    from scssim_b200 import api
+    from scssim_b200.dist import ThreadCollectives
+    from scssim_b200.synth import synth_genome
+    prof = H.profile_path("Illumina_HiSeq2500")
+    genome = synth_genome(2, 150_000, seed=17, diploid=True)   # 4 sequences
+    kw = dict(gamma=gamma, coverage=4.0, isize=isize, layout=layout, seed=777)
+    with api.GenReads(**kw) as g:
+        g.load_profile(prof).set_genome(genome).create_frags().amplify()
+        one = g.yield_reads_bytes()
+        st1 = g.stats()
+    world = 2
+    coll = ThreadCollectives(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            with api.GenReads(rank=rank, world=world, **kw) as g:
+                g.set_collectives(*coll.pair())
+                g.load_profile(prof).set_genome(genome[2 * rank:2 * rank + 2]).create_frags().amplify()
+                out[rank] = (g.yield_reads_bytes(), g.stats())
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            coll.bar.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert sum(o[1]["n_fulls"] for o in out) == st1["n_fulls"]
+    assert out[0][1]["n_fulls_global"] == st1["n_fulls"]
+    for f in range(2 if layout == "PE" else 1):
+        assert _records(out[0][0][f] + out[1][0][f]) == _records(one[f]), f"file {f}: shards differ from the single-rank output"
+    assert len(one[0]) > 0
