@@ -146,8 +146,8 @@ int set_read_counts(scs_ctx* c) {
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_set_read_counts: no profile loaded");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
     const uint64_t n = c->fulls.n;   // local
-    const ListGeom G = list_geom(c->full_batch_total, c->full_batch_before, c->full_batch_local);
-    uint64_t N = 0; for (auto v : c->full_batch_total) N += v;   // all ranks
+    const ListGeom G = c->full_geom;
+    uint64_t N = 0; for (int b = 0; b < G.nb; b++) N += G.gtot[b];   // all ranks
     const bool multi = c->P.world > 1;
     // Malbac::yieldReads: reads = refLen * coverage / readLength (Malbac.cpp:420), individual reads, whole cell
     c->reads_requested = (uint64_t)((double)c->ref_len_half * c->P.coverage / (double)c->prof.readLength);

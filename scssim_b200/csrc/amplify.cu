@@ -284,7 +284,7 @@ struct Round {
 
     AmpParams params(int round, bool semis, int domain) {
         AmpParams ap{}; ap.thr_ber = thr_ber; ap.round_tag = (uint64_t)round << 40;
-        if (semis) { ap.use_geom = 1; ap.base0 = 0; ap.geom = list_geom(c->semi_batch_total, c->semi_batch_before, c->semi_batch_local); ap.mark_base = mark_base(domain, round); }
+        if (semis) { ap.use_geom = 1; ap.base0 = 0; ap.geom = c->semi_geom; ap.mark_base = mark_base(domain, round); }
         else { ap.use_geom = 0; ap.base0 = c->frag_global0; ap.mark_base = mark_base(domain, round) + c->frag_global0; }
         return ap;
     }
@@ -339,8 +339,7 @@ struct Round {
 
     // one amplification pass over `n` templates; products appended to `dst`
     template <bool FROM_FRAG>
-    int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, AmpList& dst,
-             std::vector<uint64_t>& batch_total, std::vector<uint64_t>& batch_before, std::vector<uint64_t>& batch_local) {
+    int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, AmpList& dst, ListGeom& geom) {
         uint64_t total_slots = 0;
         SCS_CUDA(c, slot_off.reserve(n + 1)); SCS_CUDA(c, cprefix.reserve(n + 1)); SCS_CUDA(c, created.reserve(n + 1));
         uint64_t made_total = 0;
@@ -378,13 +377,34 @@ struct Round {
             if (hflags & 1) return c->fail(SCS_E_UNSUPPORTED, "amplify: more than 96 substitutions on one amplicon");
             if (int rc = exclusive_scan_u32(c, created.p, cprefix.p, n, &made_total)) return rc;
         }
-        // list geometry across ranks: this rank's creations are a contiguous run of the batch's creation order
-        std::vector<uint64_t> per_rank((size_t)std::max(1, c->P.world), 0);
-        per_rank[c->P.rank] = made_total;
-        if (int rc = allreduce_u64(per_rank.data(), per_rank.size())) return rc;
-        uint64_t gtot = 0, before = 0;
-        for (int r = 0; r < (int)per_rank.size(); r++) { if (r < c->P.rank) before += per_rank[r]; gtot += per_rank[r]; }
-        batch_total.push_back(gtot); batch_before.push_back(before); batch_local.push_back(made_total);
+        // list geometry across ranks (see ListGeom): count this rank's products per sub-batch, exchange, derive offsets
+        const int W = std::max(1, c->P.world), R = c->P.rank;
+        const int nsub = FROM_FRAG ? 1 : std::max(1, c->semi_geom.nb);
+        std::vector<uint64_t> M((size_t)W * nsub, 0);   // M[r][sb]
+        if (FROM_FRAG || made_total == 0 || nsub == 1) M[(size_t)R * nsub] = made_total;
+        else {
+            // products per batch of the semi list = differences of the creation prefix at the batch boundaries
+            uint64_t prev = 0;
+            for (int sb = 0; sb < nsub; sb++) {
+                uint64_t end = c->semi_geom.lend[sb], cp = made_total;
+                if (end < n) { SCS_CUDA(c, cudaMemcpyAsync(&cp, cprefix.p + end, 8, cudaMemcpyDeviceToHost, c->st)); SCS_CUDA(c, cudaStreamSynchronize(c->st)); }
+                M[(size_t)R * nsub + sb] = cp - prev; prev = cp;
+            }
+        }
+        if (int rc = allreduce_u64(M.data(), M.size())) return rc;
+        if (geom.nb >= 6) return c->fail(SCS_E_STATE, "amplify: too many batches");
+        const int b = geom.nb++;
+        uint64_t gtot = 0, l0 = 0, g0 = 0;
+        geom.nsub[b] = nsub;
+        for (int sb = 0; sb < nsub; sb++) {
+            uint64_t subtot = 0, ahead = 0;   // ahead = products created before this rank's inside the sub-batch
+            for (int r = 0; r < W; r++) { subtot += M[(size_t)r * nsub + sb]; if (FROM_FRAG ? (r < R) : (r > R)) ahead += M[(size_t)r * nsub + sb]; }
+            geom.sub_l0[b][sb] = l0; geom.sub_g0[b][sb] = g0 + ahead;
+            l0 += M[(size_t)R * nsub + sb]; g0 += subtot; gtot += subtot;
+        }
+        geom.ltot[b] = made_total; geom.gtot[b] = gtot;
+        geom.gbase[b] = b ? geom.gbase[b - 1] + geom.gtot[b - 1] : 0;
+        geom.lend[b] = (b ? geom.lend[b - 1] : 0) + made_total;
         uint64_t old = dst.n;
         SCS_CUDA(c, dst.desc.reserve(old + made_total + 1, old, c->st)); SCS_CUDA(c, dst.gc.reserve(old + made_total + 1, old, c->st));
         SCS_CUDA(c, dst.errref.reserve(old + made_total + 1, old, c->st));
@@ -417,23 +437,22 @@ int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     SCS_CUDA(c, c->err_top.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(c->err_top.p, 0, 8, c->st));
     SCS_CUDA(c, c->err_pool.reserve(4096));
     c->semis.clear(); c->fulls.clear();
-    c->semi_batch_total.clear(); c->semi_batch_before.clear(); c->semi_batch_local.clear();
-    c->full_batch_total.clear(); c->full_batch_before.clear(); c->full_batch_local.clear();
+    c->semi_geom = ListGeom{}; c->full_geom = ListGeom{};
     const uint64_t nF = c->frags.size();
     int rc;
     if ((rc = R.set_primers(true, 0))) return rc;
-    if ((rc = R.pass<true>(0, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+    if ((rc = R.pass<true>(0, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_geom))) return rc;
     for (int i = 0; i < 5; i++) {
         if (c->total_primers == 0) break;
         if ((rc = R.set_primers(false, i + 1))) return rc;
-        if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, c->fulls, c->full_batch_total, c->full_batch_before, c->full_batch_local))) return rc;
-        if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_batch_total, c->semi_batch_before, c->semi_batch_local))) return rc;
+        if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, c->fulls, c->full_geom))) return rc;
+        if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_geom))) return rc;
     }
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_amplify = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->stats.n_semis = c->semis.n; c->stats.n_fulls = c->fulls.n;
-    c->stats.n_semis_global = 0; for (auto v : c->semi_batch_total) c->stats.n_semis_global += v;
-    c->stats.n_fulls_global = 0; for (auto v : c->full_batch_total) c->stats.n_fulls_global += v;
+    c->stats.n_semis_global = 0; for (int b = 0; b < c->semi_geom.nb; b++) c->stats.n_semis_global += c->semi_geom.gtot[b];
+    c->stats.n_fulls_global = 0; for (int b = 0; b < c->full_geom.nb; b++) c->stats.n_fulls_global += c->full_geom.gtot[b];
     c->stats.total_primers_left = c->total_primers;
     c->amplified = true; c->have_counts = false;
     return SCS_OK;

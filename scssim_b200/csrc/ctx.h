@@ -43,22 +43,31 @@ template <class T> struct DevBuf {
 struct HostFrag { int32_t seq; int64_t start0; int32_t len; int32_t strand; };
 
 // Where this rank's part of an amplicon list sits in the global (all ranks) list. A batch is the output of one
-// amplification pass; inside a batch the global order is reverse creation order over all ranks' templates, and a rank's
-// products are a contiguous run of the creation order (ranks own contiguous template ranges).
+// amplification pass; inside a batch the global order is the REVERSE of the creation order (Amplicon.cpp:574-585),
+// and the creation order walks the templates in global list order. A batch is cut into sub-batches inside which this
+// rank's products are a contiguous run of the creation order:
+//   * products of fragments (semi amplicons): one sub-batch; ranks own contiguous fragment ranges, lower ranks first;
+//   * products of semi amplicons (full amplicons): one sub-batch per batch of the semi list; inside it the semi list
+//     holds higher ranks first (it is itself reversed), so higher ranks' products are created first.
 struct ListGeom {
     int nb;
-    uint64_t lend[6];    // local list size after batch b
-    uint64_t ltot[6];    // local products in batch b
-    uint64_t gbase[6];   // global list size before batch b
-    uint64_t gtot[6];    // global products in batch b
-    uint64_t before[6];  // products of lower ranks in batch b
+    uint64_t lend[6];        // local list size after batch b
+    uint64_t ltot[6];        // local products in batch b
+    uint64_t gbase[6];       // global list size before batch b
+    uint64_t gtot[6];        // global products in batch b
+    int nsub[6];
+    uint64_t sub_l0[6][6];   // local creation rank of this rank's first product of the sub-batch
+    uint64_t sub_g0[6][6];   // global creation rank (inside the batch) of that product
 };
 __host__ __device__ inline uint64_t global_index(const ListGeom& G, uint64_t t) {
     int b = 0;
     while (b + 1 < G.nb && t >= G.lend[b]) b++;
-    const uint64_t q = t - (b ? G.lend[b - 1] : 0);                 // position inside the local batch (reverse creation order)
-    const uint64_t crank = G.before[b] + (G.ltot[b] - 1 - q);       // global creation rank
-    return G.gbase[b] + (G.gtot[b] - 1 - crank);
+    const uint64_t q = t - (b ? G.lend[b - 1] : 0);        // position inside the local batch (reverse creation order)
+    const uint64_t lcr = G.ltot[b] - 1 - q;                 // local creation rank
+    int sb = 0;
+    while (sb + 1 < G.nsub[b] && lcr >= G.sub_l0[b][sb + 1]) sb++;
+    const uint64_t gcr = G.sub_g0[b][sb] + (lcr - G.sub_l0[b][sb]);
+    return G.gbase[b] + (G.gtot[b] - 1 - gcr);
 }
 
 // amplicon list (semi or full), structure of arrays, list order = the reference's -t 1 order
@@ -128,8 +137,7 @@ struct scs_ctx {
     scs::DevBuf<long long> primer_counts; uint64_t total_primers = 0;
     bool amplified = false;
     // global (all ranks) list geometry, per batch
-    std::vector<uint64_t> semi_batch_total, semi_batch_before, full_batch_total, full_batch_before;   // totals and this rank's creation prefix
-    std::vector<uint64_t> semi_batch_local, full_batch_local;
+    scs::ListGeom semi_geom{}, full_geom{};   // this rank's place in the global semi / full lists
 
     // read allocation
     scs::DevBuf<double> weights; scs::DevBuf<uint32_t> counts; scs::DevBuf<uint64_t> slot_base; bool have_counts = false;
@@ -190,7 +198,6 @@ DrawSrc draw_src(const scs_ctx* c, int domain);
 uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, uint64_t mark_index, uint64_t i);
 
 // device exclusive scan: out[i] = sum_{j<i} in[j] (u64), returns total through *total_dev (device pointer, may be null)
-ListGeom list_geom(const std::vector<uint64_t>& total, const std::vector<uint64_t>& before, const std::vector<uint64_t>& local);
 int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n);
 int allreduce_f64(scs_ctx* c, double* v, size_t n);
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);

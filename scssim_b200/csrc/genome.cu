@@ -277,17 +277,6 @@ int allreduce_f64(scs_ctx* c, double* v, size_t n) {
     return c->ar_f64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
 }
 
-ListGeom list_geom(const std::vector<uint64_t>& total, const std::vector<uint64_t>& before, const std::vector<uint64_t>& local) {
-    ListGeom G{}; G.nb = (int)std::min<size_t>(total.size(), 6);
-    uint64_t le = 0, gb = 0;
-    for (int b = 0; b < G.nb; b++) {
-        le += local[b]; G.lend[b] = le; G.ltot[b] = local[b]; G.gbase[b] = gb; G.gtot[b] = total[b]; G.before[b] = before[b];
-        gb += total[b];
-    }
-    if (G.nb == 0) { G.nb = 1; G.lend[0] = 0; G.ltot[0] = 0; G.gbase[0] = 0; G.gtot[0] = 0; G.before[0] = 0; }
-    return G;
-}
-
 int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782
     if (!c->have_genome) return c->fail(SCS_E_STATE, "scs_create_frags: no genome loaded");
     const uint32_t fragMin = 10000, fragMax = 100000;   // Fragment.cpp:15-16
