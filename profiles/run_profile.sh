@@ -8,6 +8,6 @@ $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/plain2.log 2> gpurun_out/plain2.err && \
-ncu --set full --clock-control none --import-source on -k regex:'emit_kernel|plan_kernel|amplify_kernel' -s 12 -c 9 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'emit_kernel|plan_kernel|amplify_kernel' -s 30 -c 8 -f -o gpurun_out/prof $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full rc=$?"
 tail -2 gpurun_out/plain.log

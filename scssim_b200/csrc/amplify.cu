@@ -22,6 +22,9 @@ namespace scs {
 
 constexpr int kAmpMin = 1000, kAmpMax = 2000;   // Config.cpp:39-40
 constexpr int kMaxErrPerAmp = 96;                // per-amplicon staging (own + inherited substitutions)
+constexpr int kSiteCap = 64;                     // attached primer sites of a fragment kept as a list in shared memory; beyond
+                                                 // that (large gamma) the warp switches to a bitmap in global scratch
+constexpr int kFragBitmapWords = (100000 + 32) / 32 + 1;   // fragments are <= 100 kb (Fragment.cpp:15)
 
 struct AmpParams {
     uint32_t thr_ber;        // error iff x < thr_ber   (p < ber, ber = 3.4e-4, Config.cpp:46)
@@ -107,22 +110,27 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                                                              uint32_t* __restrict__ out_gc, uint64_t* __restrict__ out_errref,
                                                              uint32_t* __restrict__ created, uint32_t* err_pool, unsigned long long* err_top,
                                                              uint64_t err_cap, int* __restrict__ flags, long long* primer_counts,
-                                                             unsigned long long* __restrict__ ticket) {
+                                                             unsigned long long* __restrict__ ticket, uint32_t* __restrict__ gbitmaps) {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // attached-site set (posAttached[], Fragment.cpp:70): semi templates (<= 2000 bp) use a bitmap in shared memory; fragments
+    // keep a short list of sites in shared memory and fall back to a per-warp bitmap in global memory for many primers
     uint32_t* bitmap = smem + (size_t)warp * BITMAP_WORDS;
+    uint32_t* gbitmap = FROM_FRAG ? gbitmaps + ((size_t)blockIdx.x * WARPS + warp) * kFragBitmapWords : nullptr;
     uint32_t* errbuf = smem + (size_t)WARPS * BITMAP_WORDS + (size_t)warp * kMaxErrPerAmp;
     for (;;) {
-        // dynamic work: chunks of 32 consecutive templates per warp
+        // dynamic work: fragments (every one has primers, each worth thousands of draws) are handed out one per warp;
+        // semi amplicons (mostly zero primers) in chunks of 32 consecutive templates filtered by a ballot
+        constexpr uint64_t kChunk = FROM_FRAG ? 1 : 32;
         unsigned long long chunk = 0;
         if (lane == 0) chunk = atomicAdd(ticket, 1ull);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        uint64_t t0 = chunk * 32ull;
+        uint64_t t0 = chunk * kChunk;
         if (t0 >= n_tmpl) break;
         uint64_t tl = t0 + lane;
         uint32_t myp = 0; uint64_t myd = 0;
-        if (tl < n_tmpl) { myp = primers[tl]; myd = desc[tl]; if (unpack_desc(myd).len < (uint32_t)(kAmpMin + 27)) myp = 0; }
-        if (tl < n_tmpl && myp == 0) created[tl] = 0;
+        if (lane < (int)kChunk && tl < n_tmpl) { myp = primers[tl]; myd = desc[tl]; if (unpack_desc(myd).len < (uint32_t)(kAmpMin + 27)) myp = 0; }
+        if (lane < (int)kChunk && tl < n_tmpl && myp == 0) created[tl] = 0;
         uint32_t work = __ballot_sync(0xffffffffu, myp != 0);
         while (work) {
             int src_lane = __ffs(work) - 1; work &= work - 1;
@@ -133,8 +141,12 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
             if (!FROM_FRAG) { uint64_t er = errref[t]; tnerr = (uint32_t)(er & 0xFFFF); terr = err_pool + (er >> 16); }
             const uint64_t slot0 = slot_off[t];
             Stream S; S.init(src, FROM_FRAG ? D_AMPF : D_AMPS, tmpl_entity(ap, t), ap.mark_base + t);
-            const uint32_t bw = (T.len + 31) >> 5;
-            for (uint32_t w = lane; w < bw; w += 32) bitmap[w] = 0;
+            const bool use_list = FROM_FRAG && primerNum <= (uint32_t)kSiteCap;
+            if (!use_list) {
+                uint32_t* bm = FROM_FRAG ? gbitmap : bitmap;
+                const uint32_t bw = (T.len + 31) >> 5;
+                for (uint32_t w = lane; w < bw; w += 32) bm[w] = 0;
+            }
             __syncwarp();
             uint32_t ci = 0, cr = 0, made = 0;
             for (uint32_t pi = 0; pi < primerNum; pi++) {
@@ -146,7 +158,11 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     if (k < 50) {
                         sp = uni_trunc(S.at(E_INT, ci + k), 27, T.len - 27);
                         al = uni_trunc(S.at(E_REAL, cr + k), kAmpMin, kAmpMax + 1 - kAmpMin);
-                        ok = (sp + al <= T.len) && !((bitmap[sp >> 5] >> (sp & 31)) & 1u);
+                        ok = (sp + al <= T.len);
+                        if (ok) {
+                            if (use_list) { for (uint32_t q = 0; q < made; q++) ok &= (bitmap[q] != sp); }
+                            else { const uint32_t* bm = FROM_FRAG ? gbitmap : bitmap; ok = !((bm[sp >> 5] >> (sp & 31)) & 1u); }
+                        }
                         if (ok) {
                             for (int q = 0; q < 8; q++) pidx = pidx * 4 + tmpl_base(g, T, terr, tnerr, sp + q);
                             ok = primer_counts[pidx] > 0;
@@ -165,7 +181,10 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     }
                 }
                 if (!acc) { ci += 51; cr += 51; break; }   // 51st try draws, then the template is abandoned
-                if (lane == 0) bitmap[spos >> 5] |= 1u << (spos & 31);
+                if (lane == 0) {
+                    if (use_list) bitmap[made] = spos;   // every accepted primer yields exactly one product: `made` indexes the list
+                    else { uint32_t* bm = FROM_FRAG ? gbitmap : bitmap; bm[spos >> 5] |= 1u << (spos & 31); }
+                }
                 // ---- GC content of the window (countGC, MyDefine.cpp:434-452)
                 int gc = (int)window_gc_raw(g, T, spos, alen, lane);
                 if (!FROM_FRAG) for (uint32_t e = 0; e < tnerr; e++) {
@@ -278,7 +297,7 @@ namespace {
 struct Round {
     scs_ctx* c; Genome g; uint32_t thr_ber;
     DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
-    DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created;
+    DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created, gbitmaps;
 
     int allreduce_u64(uint64_t* v, size_t n) { return scs::allreduce_u64(c, v, n); }
 
@@ -356,18 +375,18 @@ struct Round {
             AmpParams ap = params(round, !FROM_FRAG, FROM_FRAG ? D_AMPF : D_AMPS);
             int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (FROM_FRAG) {
-                constexpr int W = 4, BW = (100000 + 32) / 32 + 1;
+                constexpr int W = 8, BW = kSiteCap, CTAS = 5;
                 size_t sm = (size_t)W * (BW + kMaxErrPerAmp) * 4;
+                SCS_CUDA(c, gbitmaps.reserve((size_t)sms * CTAS * W * kFragBitmapWords));
                 auto kern = amplify_kernel<true, BW, W>;
-                SCS_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-                kern<<<sms * 4, W * 32, sm, c->st>>>(g, draw_src(c, D_AMPF), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
-                                                     c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p);
+                kern<<<sms * CTAS, W * 32, sm, c->st>>>(g, draw_src(c, D_AMPF), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
+                                                        c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p, gbitmaps.p);
             } else {
                 constexpr int W = 8, BW = (kAmpMax + 32) / 32 + 1;
                 size_t sm = (size_t)W * (BW + kMaxErrPerAmp) * 4;
                 auto kern = amplify_kernel<false, BW, W>;
                 kern<<<sms * 8, W * 32, sm, c->st>>>(g, draw_src(c, D_AMPS), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
-                                                     c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p);
+                                                     c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p, nullptr);
             }
             SCS_LAUNCHED(c);
             int hflags = 0;

@@ -23,8 +23,9 @@ namespace scs {
 
 constexpr int kReadWarps = 8;         // warps per CTA (plan / test kernels)
 constexpr int kEmitWarps = 24;        // warps per persistent CTA of the emit kernel (one CTA per SM)
-constexpr int kDiagW = 32;            // entries per compact quality row kept in shared memory
-constexpr int kDiagStride = 36;       // words per row: 32 + 4 pad keeps 128-bit loads of 8 neighbouring rows conflict-free
+constexpr int kDiagW = 40;            // entries per compact quality row kept in shared memory (shipped profiles need <= 39)
+constexpr int kDiagStride = 44;       // words per row: 40 + 4 pad; 44*r mod 32 is a distinct multiple of 4 for 8 neighbouring rows,
+                                      // so their 128-bit loads are bank-conflict free
 constexpr int kRLCap = 256;           // max profile read length handled by the kernels
 constexpr int kSrcCap = 384;          // max read length after insertions (overflow -> error flag)
 constexpr int kMaxEvents = 32;        // indel events per read kept in shared memory
@@ -150,14 +151,12 @@ __device__ __forceinline__ int sample_quality(const ReadTables& T, const QualSme
         if ((meta >> 16) == 0) {
             const int lo = (int)(meta & 0xFFu), cnt = (int)((meta >> 8) & 0xFFu);
             const uint4 pv = Q->piv[r];
+            // pivots = entries 7, 15, 23, 31: they select one of five octets, which is then counted
             const int oct = (int)(pv.x <= xq) + (int)(pv.y <= xq) + (int)(pv.z <= xq) + (int)(pv.w <= xq);
-            int c = kDiagW;
-            if (oct < 4) {
-                const uint4* row = reinterpret_cast<const uint4*>(Q->rows + (size_t)r * kDiagStride + oct * 8);
-                const uint4 a = row[0], d = row[1];
-                c = oct * 8 + (int)(a.x <= xq) + (int)(a.y <= xq) + (int)(a.z <= xq) + (int)(a.w <= xq) + (int)(d.x <= xq) + (int)(d.y <= xq) +
-                    (int)(d.z <= xq) + (int)(d.w <= xq);
-            }
+            const uint4* row = reinterpret_cast<const uint4*>(Q->rows + (size_t)r * kDiagStride + oct * 8);
+            const uint4 a = row[0], d = row[1];
+            const int c = oct * 8 + (int)(a.x <= xq) + (int)(a.y <= xq) + (int)(a.z <= xq) + (int)(a.w <= xq) + (int)(d.x <= xq) + (int)(d.y <= xq) +
+                          (int)(d.z <= xq) + (int)(d.w <= xq);
             return lo + min(c, cnt);
         }
     }
@@ -234,6 +233,22 @@ struct SlabArgs {
     uint64_t slab_cap;                 // bytes available in each output slab (emit bounds check)
 };
 
+// count_le on a long row, evaluated by the whole warp: 32 pivots, then the segment between two pivots (2 ballots)
+__device__ __forceinline__ int warp_count_le(const uint32_t* __restrict__ row, int n, uint32_t x, int lane) {
+    if (n <= 0) return 0;
+    if (n > 1024) return count_le(row, n, x);
+    const int step = (n + 31) >> 5;
+    const int pi = min((lane + 1) * step, n) - 1;                       // last entry of lane's segment
+    const uint32_t below = __ballot_sync(0xffffffffu, __ldg(row + pi) <= x);   // a prefix of lanes (row is non-decreasing)
+    const int seg = __popc(below);                                      // segments fully <= x
+    if (seg >= 32) return n;
+    const int base = seg * step;
+    if (base >= n) return n;
+    const int idx = base + lane;
+    const bool le = lane < step && idx < n && __ldg(row + idx) <= x;
+    return base + __popc(__ballot_sync(0xffffffffu, le));
+}
+
 // amplicon of a slot: last a with slot_base[a] <= slot, by a warp-cooperative 32-ary search (4 probes for 1e6 amplicons)
 __device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ slot_base, uint64_t n_amp, uint64_t slot, int lane) {
     uint64_t lo = 0, hi = n_amp;   // invariant: slot_base[lo] <= slot < slot_base[hi]
@@ -272,7 +287,7 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     int pos = 0, isz = RL;
     if (T.paired) {
         if (A.nfail) cr = A.nfail[slot];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
-        isz = T.minInsert + count_le(T.isize, T.isizeEff, S.at(E_REAL, cr));
+        isz = T.minInsert + warp_count_le(T.isize, T.isizeEff, S.at(E_REAL, cr), lane);
         cr += 1;
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
     } else {

@@ -13,10 +13,10 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000):
+def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000, diploid=True):
     from scssim_b200 import api
     fa = os.path.join(tmp, f"{name}.fa")
-    genome = H.write_genome(fa, n_chrom, chrom_len, gseed)
+    genome = H.write_genome(fa, n_chrom, chrom_len, gseed, diploid=diploid)
     prof = H.profile_path(profile)
     args = H.genreads_args(prof, layout, gamma, coverage, isize, primers)
     oprefix, dprefix = os.path.join(tmp, name + "_orc"), os.path.join(tmp, name + "_dump")
@@ -67,3 +67,10 @@ def test_pe_gaiix_short_insert(tmp_path):
 
 def test_pe_mostly_failing_inserts(tmp_path):
     _run_case(str(tmp_path), "fail", 1, 400_000, 7, "Illumina_HiSeq2500", "PE", 3e-10, 6.0, 1900, seed=5)
+
+
+def test_se_many_primers_per_fragment(tmp_path):
+    # gamma 2.5e-9 on two 40 kb fragments: hundreds of primers per fragment (attached-site bitmap path instead of the
+    # short list), ~70 k full amplicons from 3 k semi amplicons, nearly all reads allocated by the multinomial remainder
+    st = _run_case(str(tmp_path), "manyprimers", 1, 40_000, 41, "Illumina_HiSeq2000", "SE", 2.5e-9, 2.0, 260, seed=5, diploid=False)
+    assert st["n_fulls"] > 50_000
