@@ -84,22 +84,25 @@ __device__ __forceinline__ uint32_t tmpl_base(const Genome& g, const Tmpl& T, co
     return b;
 }
 
-// GC count of template window [s, s+l): popcount over packed words (+ overlay fix-up by the caller)
-__device__ __forceinline__ uint32_t window_gc_raw(const Genome& g, const Tmpl& T, uint32_t s, uint32_t l, int lane) {
+// GC count and N count of template window [s, s+l): popcounts over packed words (+ overlay fix-up by the caller).
+// Packed N bases are stored as code 0 (= A), so they never count as GC.
+__device__ __forceinline__ uint32_t window_gc_raw(const Genome& g, const Tmpl& T, uint32_t s, uint32_t l, int lane, uint32_t* n_count) {
     uint64_t lo = T.rc ? (T.gstart - (s + l - 1)) : (T.gstart + s);   // genome interval [lo, lo+l)
     uint64_t hi = lo + l;
     uint64_t w0 = lo >> 5, w1 = (hi - 1) >> 5;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0, nn = 0;
     for (uint64_t w = w0 + lane; w <= w1; w += 32) {
         uint64_t x = __ldg(g.words + w);
         uint64_t m = (x ^ (x >> 1)) & 0x5555555555555555ull;   // 1 where the base is C or G
+        uint32_t nm = g.has_n ? __ldg(g.nmask + w) : 0u;
         uint64_t b0 = w << 5;
-        if (b0 < lo) m &= ~0ull << (2 * (lo - b0));
-        if (b0 + 32 > hi) m &= ~0ull >> (2 * (b0 + 32 - hi));
-        cnt += __popcll(m);
+        if (b0 < lo) { m &= ~0ull << (2 * (lo - b0)); nm &= ~0u << (lo - b0); }
+        if (b0 + 32 > hi) { m &= ~0ull >> (2 * (b0 + 32 - hi)); nm &= ~0u >> (b0 + 32 - hi); }
+        cnt += __popcll(m); nn += __popc(nm);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    for (int o = 16; o > 0; o >>= 1) { cnt += __shfl_xor_sync(0xffffffffu, cnt, o); nn += __shfl_xor_sync(0xffffffffu, nn, o); }
+    *n_count = nn;
     return cnt;
 }
 
@@ -164,8 +167,9 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                             else { const uint32_t* bm = FROM_FRAG ? gbitmap : bitmap; ok = !((bm[sp >> 5] >> (sp & 31)) & 1u); }
                         }
                         if (ok) {
-                            for (int q = 0; q < 8; q++) pidx = pidx * 4 + tmpl_base(g, T, terr, tnerr, sp + q);
-                            ok = primer_counts[pidx] > 0;
+                            // 8-mers holding an N never bind (reference: a trie node created on the fly, Malbac.cpp:91-98)
+                            for (int q = 0; q < 8; q++) { uint32_t b8 = tmpl_base(g, T, terr, tnerr, sp + q); ok &= (b8 < 4u); pidx = pidx * 4 + (b8 & 3u); }
+                            if (ok) ok = primer_counts[pidx] > 0;
                         }
                     }
                     uint32_t cand = __ballot_sync(0xffffffffu, ok);
@@ -186,14 +190,17 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     else { uint32_t* bm = FROM_FRAG ? gbitmap : bitmap; bm[spos >> 5] |= 1u << (spos & 31); }
                 }
                 // ---- GC content of the window (countGC, MyDefine.cpp:434-452)
-                int gc = (int)window_gc_raw(g, T, spos, alen, lane);
+                uint32_t nN = 0;
+                int gc = (int)window_gc_raw(g, T, spos, alen, lane, &nN);
                 if (!FROM_FRAG) for (uint32_t e = 0; e < tnerr; e++) {
                     uint32_t v = terr[e], p = err_pos(v);
                     if (p >= spos && p < spos + alen) {
                         uint32_t raw = window_base(g, T.gstart, T.rc, p), nb = err_base(v);
                         gc += (int)((nb == 1u) | (nb == 2u)) - (int)((raw == 1u) | (raw == 2u));
+                        if (raw == 4u) nN--;   // the substitution replaced an N
                     }
                 }
+                if (nN) gc = 0;   // countGC() gives 0 as soon as the window holds an N (MyDefine.cpp:448-450)
                 // ---- per-base polymerase errors, j = 8 .. alen-1 (Fragment.cpp:105-123)
                 // draw d on the real stream belongs to position j = 8 + (d - dbase)
                 uint32_t nown = 0; uint32_t dbase = cr, dcur = cr; const uint32_t dend_pos = alen;   // position limit
@@ -365,11 +372,11 @@ struct Round {
         if (n) {
             if (int rc = exclusive_scan_u32(c, primers, slot_off.p, n, &total_slots)) return rc;
             SCS_CUDA(c, tdesc.reserve(total_slots + 1)); SCS_CUDA(c, terr.reserve(total_slots + 1)); SCS_CUDA(c, tgc.reserve(total_slots + 1));
-            // error pool: own errors ~ ber * 2000 per product, inherited about as many; 8x head-room, retried on overflow
+            // error pool: ~0.5 own + ~0.5 inherited substitutions per product expected; 5 slots per product reserved, overflow is reported
             uint64_t etop = 0;
             SCS_CUDA(c, cudaMemcpyAsync(&etop, c->err_top.p, 8, cudaMemcpyDeviceToHost, c->st));
             SCS_CUDA(c, cudaStreamSynchronize(c->st));
-            uint64_t need = etop + total_slots * 12 + 4096;
+            uint64_t need = etop + total_slots * 5 + 4096;
             SCS_CUDA(c, c->err_pool.reserve(need, etop, c->st));
             SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(ticket.p, 0, 8, c->st));
             AmpParams ap = params(round, !FROM_FRAG, FROM_FRAG ? D_AMPF : D_AMPS);
@@ -445,7 +452,7 @@ int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     if (!c->have_frags) return c->fail(SCS_E_STATE, "scs_amplify: call scs_create_frags first");
     if (c->P.world > 1 && c->replay.on) return c->fail(SCS_E_UNSUPPORTED, "replay runs on one rank only (the reference's logs are sequential)");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
-    Round R; R.c = c; R.g.words = c->genome_words.p; R.g.n_bases = c->genome_bases;
+    Round R; R.c = c; R.g = c->dev_genome();
     R.thr_ber = (uint32_t)std::min<uint64_t>(count_unit_lt(3.4e-4), 0xFFFFFFFFull);
     SCS_CUDA(c, R.dcount.reserve(1)); SCS_CUDA(c, R.ticket.reserve(1)); SCS_CUDA(c, R.flags.reserve(1));
     // createPrimers (Malbac.cpp:36-81): 4^8 primer types, -p copies each

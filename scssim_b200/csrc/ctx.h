@@ -121,7 +121,8 @@ struct scs_ctx {
 
     // genome
     std::vector<std::string> seq_names; std::vector<uint64_t> seq_len, seq_goff;   // goff in bases, 32-aligned
-    scs::DevBuf<uint64_t> genome_words; uint64_t genome_bases = 0; bool have_genome = false;
+    scs::DevBuf<uint64_t> genome_words; scs::DevBuf<uint32_t> genome_nmask; uint64_t genome_bases = 0; bool have_genome = false; int genome_has_n = 0;
+    scs::Genome dev_genome() const { scs::Genome g; g.words = genome_words.p; g.nmask = genome_nmask.p; g.n_bases = genome_bases; g.has_n = genome_has_n; return g; }
     uint64_t ref_len_half = 0;
 
     // fragments

@@ -116,16 +116,24 @@ __host__ __device__ inline double det_log(double x) {
 }
 
 // ---- packed genome: 2 bits per base, 32 bases per u64 word, A=0 C=1 G=2 T=3 ----
+// Bases other than A/C/G/T (N, IUPAC codes; the reference's complement maps them all to 'N',
+// lib/mydefine/MyDefine.cpp:352-367) are code 4: stored as 0 in the packed words plus one bit in `nmask`
+// (32 bases per u32 word). has_n == 0 (no such base in the genome) lets every kernel skip the mask.
 struct Genome {
     const uint64_t* __restrict__ words;
+    const uint32_t* __restrict__ nmask;
     uint64_t n_bases;
+    int has_n;
 };
 __device__ __forceinline__ uint32_t genome_base(const Genome& g, uint64_t pos) {
-    return (uint32_t)(__ldg(g.words + (pos >> 5)) >> ((pos & 31) * 2)) & 3u;
+    uint32_t b = (uint32_t)(__ldg(g.words + (pos >> 5)) >> ((pos & 31) * 2)) & 3u;
+    if (g.has_n && ((__ldg(g.nmask + (pos >> 5)) >> (pos & 31)) & 1u)) b = 4u;
+    return b;
 }
+__device__ __forceinline__ uint32_t comp_code(uint32_t b) { return b < 4u ? 3u - b : 4u; }
 // base i of an oriented window: rc ? complement(G[gstart - i]) : G[gstart + i]
 __device__ __forceinline__ uint32_t window_base(const Genome& g, uint64_t gstart, int rc, uint32_t i) {
-    return rc ? (3u - genome_base(g, gstart - i)) : genome_base(g, gstart + i);
+    return rc ? comp_code(genome_base(g, gstart - i)) : genome_base(g, gstart + i);
 }
 
 // Template descriptor shared by fragments, semi and full amplicons: an oriented genome window plus

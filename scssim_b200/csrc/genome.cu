@@ -113,10 +113,10 @@ int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, 
 }
 
 // ------------------------------------------------------------------------------- K0 pack_genome
-// One thread packs 32 bases (two 16-byte loads) into one u64 word. Bases other than ACGT (any case)
-// raise a flag: N / IUPAC handling is SURVEY.md §8f row N4.
+// One thread packs 32 bases (two 16-byte loads) into one u64 word and one u32 of N-mask. Bases other than ACGT (any
+// case) become code 4 ("N", as after the reference's complement) and raise the has_n flag.
 __global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t* __restrict__ ascii, uint64_t n_bases, uint64_t* __restrict__ words,
-                                                          unsigned int* __restrict__ bad) {
+                                                          uint32_t* __restrict__ nmask, unsigned int* __restrict__ bad) {
     uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t n_words = (n_bases + 31) >> 5;
     if (w >= n_words) return;
@@ -130,17 +130,18 @@ __global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t* __restr
 #pragma unroll
         for (int k = 0; k < 32; k++) b[k] = (base + k < n_bases) ? ascii[base + k] : (uint8_t)'A';
     }
-    uint64_t out = 0; unsigned int anybad = 0;
+    uint64_t out = 0; uint32_t mask = 0;
 #pragma unroll
     for (int k = 0; k < 32; k++) {
         uint32_t ch = b[k] & 0xDFu;   // upper-case (Genome::getSubSequence toupper, Genome.cpp:274)
         // A=0x41 C=0x43 G=0x47 T=0x54 -> (ch>>1)&3 = 0,1,3,2 ; fix G/T order with a xor
         uint32_t code = (ch >> 1) & 3u; code ^= (code >> 1);
-        anybad |= (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T');
-        out |= (uint64_t)code << (2 * k);
+        const bool bad1 = (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T');
+        mask |= (uint32_t)bad1 << k;
+        out |= (uint64_t)(bad1 ? 0u : code) << (2 * k);
     }
-    words[w] = out;
-    if (anybad) atomicOr(bad, 1u);
+    words[w] = out; nmask[w] = mask;
+    if (mask) atomicOr(bad, 1u);
 }
 
 static std::string ref_seq_name(const std::string& header) {   // lib/fastahack/Fasta.cpp:57-68
@@ -170,7 +171,7 @@ int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* co
     c->ref_len_sum = refLen; c->ref_len_half = refLen / 2;
     c->genome_bases = goff;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    SCS_CUDA(c, c->genome_words.reserve(goff / 32 + 2));
+    SCS_CUDA(c, c->genome_words.reserve(goff / 32 + 2)); SCS_CUDA(c, c->genome_nmask.reserve(goff / 32 + 2));
     DevBuf<unsigned int> bad; SCS_CUDA(c, bad.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(bad.p, 0, 4, c->st));
     // stage ASCII through a bounded device buffer
     const uint64_t chunk = 256ull << 20;
@@ -181,7 +182,8 @@ int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* co
             uint64_t m = std::min(chunk, lens[i] - off);
             SCS_CUDA(c, cudaMemcpyAsync(stage.p, seqs[i] + off, m, cudaMemcpyHostToDevice, c->st));
             uint64_t nw = (m + 31) >> 5;
-            pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, c->genome_words.p + ((c->seq_goff[i] + off) >> 5), bad.p);
+            pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, c->genome_words.p + ((c->seq_goff[i] + off) >> 5),
+                                                                                c->genome_nmask.p + ((c->seq_goff[i] + off) >> 5), bad.p);
             SCS_LAUNCHED(c);
             SCS_CUDA(c, cudaStreamSynchronize(c->st));
         }
@@ -191,7 +193,7 @@ int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* co
     SCS_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, c->st));
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_pack = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (hbad) return c->fail(SCS_E_UNSUPPORTED, "genome contains bases other than A/C/G/T (N / IUPAC support is not implemented yet)");
+    c->genome_has_n = hbad ? 1 : 0;
     c->stats.n_sequences = n; c->stats.genome_bases = 0; for (auto l : c->seq_len) c->stats.genome_bases += l;
     c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
     return SCS_OK;

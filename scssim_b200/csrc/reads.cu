@@ -194,6 +194,54 @@ __device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTa
     cr += 2u * (uint32_t)np;
 }
 
+// Same loop for windows that hold an N (code 4): the number of draws per output base then varies — 0 real + 1 int for an N
+// (emitted as 'N' with quality randomInteger(33,53), Profile.cpp:1578-1580,1686-1688), 1 real when only the k-mer context
+// holds an N (no substitution draw, Profile.cpp:1527-1529), 2 otherwise — so draw indices come from a warp prefix sum.
+// WRITE = false only advances the cursors (plan kernel).
+template <bool WRITE>
+__device__ __forceinline__ void subst_quality_pass_n(const Stream& S, const ReadTables& T, const QualSmem* Q, const uint8_t* __restrict__ src, int np,
+                                                     int isRead1, uint32_t& cr, uint32_t& ci, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
+    const uint32_t* __restrict__ subs = (!isRead1 && T.subs2) ? T.subs2 : T.subs1;
+    const int bins = T.RL;
+    for (int m0 = 0; m0 < np; m0 += 32) {
+        const int m = m0 + lane;
+        const bool valid = m < np;
+        const uint32_t b0 = valid ? src[m] : 0u;
+        const bool curN = valid && b0 == 4u;
+        const bool ctxN = valid && !curN && ((m >= 1 && src[m - 1] == 4u) || (m >= 2 && src[m - 2] == 4u));
+        uint32_t nr = !valid ? 0u : curN ? 0u : ctxN ? 1u : 2u, ni = curN ? 1u : 0u;
+        uint32_t pr = nr, pi = ni;   // inclusive scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t a = __shfl_up_sync(0xffffffffu, pr, o), b = __shfl_up_sync(0xffffffffu, pi, o);
+            if (lane >= o) { pr += a; pi += b; }
+        }
+        const uint32_t tot_r = __shfl_sync(0xffffffffu, pr, 31), tot_i = __shfl_sync(0xffffffffu, pi, 31);
+        if (WRITE && valid) {
+            const uint32_t ir = cr + pr - nr, ii = ci + pi - ni;
+            if (curN) {
+                oseq[m] = 'N';
+                oqual[m] = (char)uni_trunc(S.at(E_INT, ii), 33, 20);
+            } else {
+                const int bin = (np == bins) ? m : m * bins / np;
+                uint32_t k = b0, xq;
+                if (!ctxN) {
+                    uint32_t ki;
+                    if (m == 0) ki = b0; else if (m == 1) ki = 4u + 4u * src[0] + b0; else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0;
+                    const uint4 th = __ldg(reinterpret_cast<const uint4*>(subs) + ((size_t)ki * bins + bin));
+                    const uint32_t xs = S.at(E_REAL, ir);
+                    k = (uint32_t)(th.w > 0 && th.x <= xs) + (uint32_t)(th.w > 1 && th.y <= xs) + (uint32_t)(th.w > 2 && th.z <= xs);
+                    xq = S.at(E_REAL, ir + 1);
+                } else xq = S.at(E_REAL, ir);
+                const int q = sample_quality(T, Q, b0, k, bin, xq);
+                oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);
+                oqual[m] = (char)(33 + q);
+            }
+        }
+        cr += tot_r; ci += tot_i;
+    }
+}
+
 __device__ __forceinline__ int dec_digits(uint32_t v) {
     return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }
@@ -293,19 +341,26 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     } else {
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
     }
+    // the plan kernel needs the bases only when the genome holds N (draw consumption then depends on the sequence)
+    const bool fetch = EMIT || g.has_n;
     uint32_t nerr = 0; const uint32_t* __restrict__ errs = nullptr;
-    if (EMIT) { const uint64_t er = __ldg(A.errref + a); nerr = (uint32_t)(er & 0xFFFF); errs = A.err_pool + (er >> 16); }
+    if (fetch) { const uint64_t er = __ldg(A.errref + a); nerr = (uint32_t)(er & 0xFFFF); errs = A.err_pool + (er >> 16); }
     uint32_t lens = 0;
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
-        if (EMIT) {
+        bool hasN = false;
+        if (fetch) {
             // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
             __syncwarp();
+            bool myN = false;
             for (int i = lane; i < RL; i += 32) {
                 const uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
                 uint32_t b = window_base(g, F.gstart, F.rc, fi);
                 for (uint32_t e = 0; e < nerr; e++) { const uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
-                ws->ref[i] = (uint8_t)(mate == 1 ? b : 3u - b);
+                b = (mate == 1) ? b : comp_code(b);
+                myN |= (b == 4u);
+                ws->ref[i] = (uint8_t)b;
             }
+            hasN = g.has_n && __any_sync(0xffffffffu, myN);
             __syncwarp();
         }
         int nev = 0;
@@ -313,7 +368,10 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
         if (np > kSrcCap) { if (lane == 0) { atomicOr(flags, 8); if (!EMIT) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; } } return; }
         __syncwarp();
         if (!EMIT) {
-            cr += 2u * (uint32_t)np;   // the substitution/quality pass draws twice per output base
+            if (hasN) {
+                const uint8_t* src = build_source(S, np, nev, lane, ws);
+                subst_quality_pass_n<false>(S, T, nullptr, src, np, mate == 1, cr, ci, lane, nullptr, nullptr);
+            } else cr += 2u * (uint32_t)np;   // the substitution/quality pass draws twice per output base
             lens |= (uint32_t)np << (mate == 1 ? 0 : 16);
         } else {
             const uint8_t* src = build_source(S, np, nev, lane, ws);
@@ -327,7 +385,8 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
                 write_header(rec, ampIdx, fragNo, T.paired ? mate : 0);
                 rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; rec[hl + 2 * np + 3] = '\n';
             }
-            subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
+            if (hasN) subst_quality_pass_n<true>(S, T, Q, src, np, mate == 1, cr, ci, lane, rec + hl, rec + hl + np + 3);
+            else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
             __syncwarp();
             copy_out(dst, rec, total, lane);
         }
@@ -481,7 +540,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         SCS_CUDA(c, cudaMallocHost((void**)&c->slab_host[b][f], slab + 64));
     }
     ReadTables T = make_tables(c);
-    Genome g; g.words = c->genome_words.p; g.n_bases = c->genome_bases;
+    Genome g = c->dev_genome();
     DrawSrc dsrc = draw_src(c, D_READ);
     SlabArgs A; A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
     A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
@@ -594,9 +653,12 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     const int RL = T.RL;
     for (int i = lane; i < RL; i += 32) {
         char ch = srcAscii[(size_t)r * RL + i];
-        ws->ref[i] = (uint8_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3);
+        ws->ref[i] = (uint8_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4);
     }
     __syncwarp();
+    bool myN = false;
+    for (int i = lane; i < RL; i += 32) myN |= (ws->ref[i] == 4);
+    const bool hasN = __any_sync(0xffffffffu, myN);
     uint32_t cr = 0, ci = 0; int nev = 0;
     const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags + r);
     __syncwarp();
@@ -604,7 +666,8 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     if (np > kSrcCap || np > out_stride) { if (lane == 0) out_len[r] = -1; return; }
     __syncwarp();
     const uint8_t* src = build_source(S, np, nev, lane, ws);
-    subst_quality_pass(S, T, nullptr, src, np, isRead1, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
+    if (hasN) subst_quality_pass_n<true>(S, T, nullptr, src, np, isRead1, cr, ci, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
+    else subst_quality_pass(S, T, nullptr, src, np, isRead1, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
     if (lane == 0) out_len[r] = np;
 }
 
@@ -644,7 +707,7 @@ __global__ void full_seq_kernel(Genome g, const uint64_t* __restrict__ desc, con
     for (uint32_t i = threadIdx.x; i < F.len; i += blockDim.x) {
         uint32_t b = window_base(g, F.gstart, F.rc, i);
         for (uint32_t e = 0; e < nerr; e++) if (err_pos(errs[e]) == i) b = err_base(errs[e]);
-        o[i] = "ACGT"[b];
+        o[i] = "ACGTN"[b];
     }
     if (threadIdx.x == 0) o[F.len] = '\n';
 }
@@ -662,7 +725,7 @@ int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written) {
     DevBuf<uint64_t> doffs; DevBuf<char> dout;
     SCS_CUDA(c, doffs.reserve(n + 1)); SCS_CUDA(c, dout.reserve(offs[n] + 16));
     SCS_CUDA(c, memcpy_sync(c, doffs.p, offs.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-    Genome g; g.words = c->genome_words.p; g.n_bases = c->genome_bases;
+    Genome g = c->dev_genome();
     full_seq_kernel<<<(unsigned)n, 128, 0, c->st>>>(g, c->fulls.desc.p, c->fulls.errref.p, c->err_pool.p, doffs.p, n, dout.p); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
     SCS_CUDA(c, memcpy_sync(c, buf, dout.p, offs[n], cudaMemcpyDeviceToHost));

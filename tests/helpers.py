@@ -157,3 +157,21 @@ def expected_windows(genome, od):
     semis = np.stack([u_g, u_rc.astype(np.int64), l, se[:, 3], se[:, 4]], axis=1)
     fulls = np.stack([f_g, f_rc.astype(np.int64), l2, fu[:, 3]], axis=1)
     return semis, fulls
+
+
+def write_genome_with_n(path: str, glen: int = 300_000, seed: int = 77, width: int = 70):
+    """Synthetic diploid chromosome with an N run, scattered N, IUPAC codes and soft-masked (lower-case) stretches."""
+    from scssim_b200.synth import synth_genome, write_fasta
+    g = synth_genome(1, glen, seed, diploid=True)
+    rng = np.random.default_rng(seed)
+    out = []
+    for name, s in g:
+        s = s.copy()
+        s[glen * 2 // 5:glen * 2 // 5 + 5000] = ord("N")
+        s[rng.integers(0, glen, 120)] = ord("N")
+        s[rng.integers(0, glen, 10)] = ord("R")
+        for lo in rng.integers(0, glen - 2000, 5):
+            s[lo:lo + 1500] |= 0x20          # lower case
+        out.append((name, s))
+    write_fasta(path, out, width=width)
+    return out

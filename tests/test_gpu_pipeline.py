@@ -13,10 +13,10 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000, diploid=True):
+def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000, diploid=True, with_n=False):
     from scssim_b200 import api
     fa = os.path.join(tmp, f"{name}.fa")
-    genome = H.write_genome(fa, n_chrom, chrom_len, gseed, diploid=diploid)
+    genome = H.write_genome_with_n(fa, chrom_len, gseed) if with_n else H.write_genome(fa, n_chrom, chrom_len, gseed, diploid=diploid)
     prof = H.profile_path(profile)
     args = H.genreads_args(prof, layout, gamma, coverage, isize, primers)
     oprefix, dprefix = os.path.join(tmp, name + "_orc"), os.path.join(tmp, name + "_dump")
@@ -74,3 +74,11 @@ def test_se_many_primers_per_fragment(tmp_path):
     # short list), ~70 k full amplicons from 3 k semi amplicons, nearly all reads allocated by the multinomial remainder
     st = _run_case(str(tmp_path), "manyprimers", 1, 40_000, 41, "Illumina_HiSeq2000", "SE", 2.5e-9, 2.0, 260, seed=5, diploid=False)
     assert st["n_fulls"] > 50_000
+
+
+@pytest.mark.parametrize("layout", ["PE", "SE"])
+def test_genome_with_n_iupac_and_lowercase(tmp_path, layout):
+    # N runs / scattered N / IUPAC codes (all "N" after the reference's complement) / soft-masked bases: primer sites over N
+    # never bind, countGC() = 0 for windows with N, reads over N emit 'N' with Q in [33,53) and consume draws differently
+    st = _run_case(str(tmp_path), "withn" + layout, 1, 300_000, 77, "Illumina_HiSeq2500", layout, 3e-10, 6.0, 260, seed=9, with_n=True)
+    assert st["records"] > 0
