@@ -192,8 +192,9 @@ def main():
         # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream
         g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world, slab_bytes=a.slab_mb << 20)
         if world > 1:
-            from scssim_b200.dist import make_collectives
+            from scssim_b200.dist import make_collectives, make_device_allreduce
             g.set_collectives(*make_collectives(dist, device=f"cuda:{local}"))
+            g.set_device_collective(make_device_allreduce(dist, f"cuda:{local}"))
         g.load_profile(profile)
         g.set_genome(named).create_frags()
 

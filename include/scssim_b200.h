@@ -75,6 +75,11 @@ int scs_set_genome(scs_ctx* ctx, int n, const char* const* names, const char* co
 typedef int (*scs_allreduce_u64_fn)(void* user, uint64_t* buf, size_t n);
 typedef int (*scs_allreduce_f64_fn)(void* user, double* buf, size_t n);
 int scs_set_collectives(scs_ctx* ctx, scs_allreduce_u64_fn fu, scs_allreduce_f64_fn fd, void* user);
+/* Optional: in-place sum of `n` doubles that live in DEVICE memory (the cell-wide weight vector of the read allocation;
+ * ncclAllReduce over NVLink without a host round trip). The library's stream is idle when the hook is called and the
+ * hook must have completed the reduction when it returns. Without it the host hook above is used. */
+typedef int (*scs_allreduce_dev_f64_fn)(void* user, double* dev_buf, size_t n);
+int scs_set_device_collective(scs_ctx* ctx, scs_allreduce_dev_f64_fn fn, void* user);
 
 int scs_create_frags(scs_ctx* ctx);   /* Genome::splitToFrags, Genome.cpp:753-782 */
 int scs_amplify(scs_ctx* ctx);        /* Malbac::amplify, Malbac.cpp:173-201 */

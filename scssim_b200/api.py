@@ -63,10 +63,11 @@ class Replay(C.Structure):
 SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
 AR_U64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t)
 AR_F64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
+AR_DEV_F64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 # every symbol include/scssim_b200.h declares
 EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", "scs_load_profile", "scs_read_length",
-           "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_create_frags", "scs_amplify",
+           "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_create_frags", "scs_amplify",
            "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version"]
@@ -92,6 +93,7 @@ def lib():
         L.scs_load_genome.argtypes = [C.c_void_p, C.c_char_p]
         L.scs_set_genome.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.scs_set_collectives.argtypes = [C.c_void_p, AR_U64_FN, AR_F64_FN, C.c_void_p]
+        L.scs_set_device_collective.argtypes = [C.c_void_p, AR_DEV_F64_FN, C.c_void_p]
         for f in ("scs_create_frags", "scs_amplify", "scs_set_read_counts"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.scs_yield_reads_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
@@ -222,6 +224,15 @@ class GenReads:
             return 0
         self._cb = (AR_U64_FN(fu), AR_F64_FN(fd))
         self._ck(lib().scs_set_collectives(self._h, self._cb[0], self._cb[1], None))
+        return self
+
+    def set_device_collective(self, allreduce_dev_f64):
+        """allreduce_dev_f64(device_pointer: int, n: int) -> None, in place on device memory."""
+        def fd(_u, ptr, n):
+            allreduce_dev_f64(int(ptr), int(n))
+            return 0
+        self._cb_dev = AR_DEV_F64_FN(fd)
+        self._ck(lib().scs_set_device_collective(self._h, self._cb_dev, None))
         return self
 
     def create_frags(self):                     # malbac.createFrags()

@@ -173,10 +173,15 @@ int set_read_counts(scs_ctx* c) {
         wg = wg_buf.p; cg = cg_buf.p;
         SCS_CUDA(c, cudaMemsetAsync(wg, 0, N * 8, c->st));
         if (n) { scatter_f64_kernel<<<nbl, 256, 0, c->st>>>(c->weights.p, c->full_gidx.p, n, wg); SCS_LAUNCHED(c); }
-        std::vector<double> hw(N);
-        SCS_CUDA(c, memcpy_sync(c, hw.data(), wg, N * 8, cudaMemcpyDeviceToHost));
-        if (int rc = allreduce_f64(c, hw.data(), N)) return rc;
-        SCS_CUDA(c, memcpy_sync(c, wg, hw.data(), N * 8, cudaMemcpyHostToDevice));
+        if (c->ar_dev_f64) {   // NCCL on the device buffer
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            if (c->ar_dev_f64(c->ar_dev_user, wg, N)) return c->fail(SCS_E_STATE, "device allreduce callback failed");
+        } else {
+            std::vector<double> hw(N);
+            SCS_CUDA(c, memcpy_sync(c, hw.data(), wg, N * 8, cudaMemcpyDeviceToHost));
+            if (int rc = allreduce_f64(c, hw.data(), N)) return rc;
+            SCS_CUDA(c, memcpy_sync(c, wg, hw.data(), N * 8, cudaMemcpyHostToDevice));
+        }
     }
     const uint64_t nch = (N + kChunk - 1) / kChunk;
     DevBuf<double> dsums; SCS_CUDA(c, dsums.reserve(nch + 1));

@@ -38,9 +38,12 @@ __device__ __forceinline__ uint64_t tmpl_entity(const AmpParams& ap, uint64_t t)
     return ap.round_tag | (ap.base0 + (ap.use_geom ? global_index(ap.geom, t) : t));
 }
 
-__global__ void __launch_bounds__(256) sum_len_kernel(const uint64_t* __restrict__ desc, uint64_t n, unsigned long long* __restrict__ out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long v = i < n ? unpack_desc(desc[i]).len : 0;
+// sum of the lengths of the products sitting in the per-template slots
+__global__ void __launch_bounds__(256) sum_len_slots_kernel(uint64_t n_tmpl, const uint32_t* __restrict__ created, const uint64_t* __restrict__ slot_off,
+                                                            const uint64_t* __restrict__ tdesc, unsigned long long* __restrict__ out) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    if (t < n_tmpl) { const uint32_t m = created[t]; const uint64_t s0 = slot_off[t]; for (uint32_t i = 0; i < m; i++) v += unpack_desc(tdesc[s0 + i]).len; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, v);
@@ -304,6 +307,7 @@ namespace {
 struct Round {
     scs_ctx* c; Genome g; uint32_t thr_ber;
     DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
+    uint64_t pending_count = 0, semi_len_sum_global = 0;
     DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created, gbitmaps;
 
     int allreduce_u64(uint64_t* v, size_t n) { return scs::allreduce_u64(c, v, n); }
@@ -318,17 +322,11 @@ struct Round {
     // Malbac::setPrimers (Malbac.cpp:236-283)
     int set_primers(bool onlyFrags, int round) {
         uint64_t nF = c->frags.size(), nS = onlyFrags ? 0 : c->semis.n;
-        // template count and total length over all ranks (lengths are integers: the FP64 sum is exact in any order)
-        uint64_t loc[2] = {nS, 0};
-        if (nS) {
-            SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
-            sum_len_kernel<<<(unsigned)((nS + 255) / 256), 256, 0, c->st>>>(c->semis.desc.p, nS, dcount.p); SCS_LAUNCHED(c);
-            SCS_CUDA(c, cudaMemcpyAsync(&loc[1], dcount.p, 8, cudaMemcpyDeviceToHost, c->st));
-            SCS_CUDA(c, cudaStreamSynchronize(c->st));
-        }
-        if (int rc = allreduce_u64(loc, 2)) return rc;
-        uint64_t templateNum = c->n_frags_global + loc[0];
-        double totalLen = (double)(c->frag_len_sum_global + loc[1]);
+        // template count and total length over all ranks (lengths are integers: the FP64 sum is exact in any order); the
+        // cell-wide semi-amplicon count and length are kept up to date by pass() — no collective here
+        uint64_t nS_global = 0; for (int b = 0; b < c->semi_geom.nb; b++) nS_global += c->semi_geom.gtot[b];
+        uint64_t templateNum = c->n_frags_global + (onlyFrags ? 0 : nS_global);
+        double totalLen = (double)(c->frag_len_sum_global + (onlyFrags ? 0 : semi_len_sum_global));
         uint64_t expected = (uint64_t)((double)c->total_primers * c->P.gamma * (double)templateNum);
         SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
         // global template index: fragments first, then semis in (global) list order
@@ -348,8 +346,7 @@ struct Round {
         uint64_t count = 0;
         SCS_CUDA(c, cudaMemcpyAsync(&count, dcount.p, 8, cudaMemcpyDeviceToHost, c->st));
         SCS_CUDA(c, cudaStreamSynchronize(c->st));
-        if (int rc = allreduce_u64(&count, 1)) return rc;
-        c->total_primers -= count;   // unsigned wrap as in the reference (unsigned long, Malbac.h:29)
+        pending_count += count;   // summed over ranks and charged to the primer budget by the next pass()'s exchange
         return SCS_OK;
     }
 
@@ -406,7 +403,7 @@ struct Round {
         // list geometry across ranks (see ListGeom): count this rank's products per sub-batch, exchange, derive offsets
         const int W = std::max(1, c->P.world), R = c->P.rank;
         const int nsub = FROM_FRAG ? 1 : std::max(1, c->semi_geom.nb);
-        std::vector<uint64_t> M((size_t)W * nsub, 0);   // M[r][sb]
+        std::vector<uint64_t> M((size_t)W * nsub + 2, 0);   // M[r][sb], then: length of the new semi amplicons, primers used
         if (FROM_FRAG || made_total == 0 || nsub == 1) M[(size_t)R * nsub] = made_total;
         else {
             // products per batch of the semi list = differences of the creation prefix at the batch boundaries
@@ -417,7 +414,16 @@ struct Round {
                 M[(size_t)R * nsub + sb] = cp - prev; prev = cp;
             }
         }
+        if (FROM_FRAG && made_total) {   // total length of this rank's new semi amplicons (sits in the per-template slots)
+            SCS_CUDA(c, cudaMemsetAsync(dcount.p, 0, 8, c->st));
+            sum_len_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(n, created.p, slot_off.p, tdesc.p, dcount.p); SCS_LAUNCHED(c);
+            SCS_CUDA(c, cudaMemcpyAsync(&M[(size_t)W * nsub], dcount.p, 8, cudaMemcpyDeviceToHost, c->st));
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        }
+        M[(size_t)W * nsub + 1] = pending_count; pending_count = 0;
         if (int rc = allreduce_u64(M.data(), M.size())) return rc;
+        semi_len_sum_global += M[(size_t)W * nsub];
+        c->total_primers -= M[(size_t)W * nsub + 1];   // unsigned wrap as in the reference (unsigned long, Malbac.h:29)
         if (geom.nb >= 6) return c->fail(SCS_E_STATE, "amplify: too many batches");
         const int b = geom.nb++;
         uint64_t gtot = 0, l0 = 0, g0 = 0;

@@ -95,6 +95,12 @@ int scs_set_collectives(scs_ctx* c, scs_allreduce_u64_fn fu, scs_allreduce_f64_f
     return SCS_OK;
 }
 
+int scs_set_device_collective(scs_ctx* c, scs_allreduce_dev_f64_fn fn, void* user) {
+    if (!c) return SCS_E_ARG;
+    c->ar_dev_f64 = fn; c->ar_dev_user = user;
+    return SCS_OK;
+}
+
 int scs_create_frags(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return create_frags(c); }
 int scs_amplify(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return amplify(c); }
 int scs_set_read_counts(scs_ctx* c) { if (!c) return SCS_E_ARG; if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device"); cudaSetDevice(c->P.device); alloc_stream() = c->st; return set_read_counts(c); }

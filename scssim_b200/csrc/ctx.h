@@ -147,6 +147,7 @@ struct scs_ctx {
     scs::ReadScratch rscratch;
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
+    scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; void* ar_dev_user = nullptr;
     scs_stats stats{};
 
     // FASTQ slabs

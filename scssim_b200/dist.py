@@ -29,6 +29,23 @@ def make_collectives(dist, device="cuda"):
     return ar_u64, ar_f64
 
 
+def make_device_allreduce(dist, device):
+    """Return f(ptr, n): in-place NCCL sum of n float64 in device memory at `ptr` (zero-copy view through
+    __cuda_array_interface__), finished when it returns."""
+    import torch
+
+    class _View:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    def ar(ptr: int, n: int):
+        t = torch.as_tensor(_View(ptr, n), device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream(t.device).synchronize()
+
+    return ar
+
+
 class ThreadCollectives:
     """In-process stand-in (ranks = threads sharing one GPU) used by the single-GPU multi-rank parity test."""
 

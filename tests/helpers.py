@@ -32,9 +32,10 @@ def profile_path(name: str) -> str:
     """Decompress the committed copy of a shipped .profile (test fixture) and return its path."""
     out = os.path.join(scratch_dir(), name + ".profile")
     if not os.path.exists(out):
-        with lzma.open(os.path.join(GOLDEN, "profiles", name + ".profile.xz")) as f, open(out + ".tmp", "wb") as o:
+        tmp = f"{out}.{os.getpid()}.tmp"      # several ranks may decompress at once: unique name, atomic rename
+        with lzma.open(os.path.join(GOLDEN, "profiles", name + ".profile.xz")) as f, open(tmp, "wb") as o:
             o.write(f.read())
-        os.replace(out + ".tmp", out)
+        os.replace(tmp, out)
     return out
 
 
