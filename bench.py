@@ -250,19 +250,27 @@ def main():
         value = reads_all * a.steps / dev_s / 1e6
         e2e_value = reads_all * e2e_steps / e2e_s / 1e6
 
-        # pinned D2H copy ceiling of this box, measured live (the binding roof of the read stage)
-        d2h_peak = None
-        if rank == 0:
-            nb = 256 << 20
-            dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda"); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-            hbuf.copy_(dbuf, non_blocking=True); torch.cuda.synchronize()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for _ in range(4):
-                hbuf.copy_(dbuf, non_blocking=True)
-            c1.record(); torch.cuda.synchronize()
-            d2h_peak = 4 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9
-            del dbuf, hbuf
+        # pinned D2H copy ceiling of this box, measured live with ALL ranks copying at once (the binding roof of the read
+        # stage; on shared PCIe fabrics the per-GPU rate drops as N grows)
+        nb = 256 << 20
+        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda"); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        hbuf.copy_(dbuf, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(6):
+            hbuf.copy_(dbuf, non_blocking=True)
+        c1.record(); torch.cuda.synchronize()
+        mine = torch.tensor([6 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9], dtype=torch.float64, device="cuda")
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, mine)
+        else:
+            per_rank = [mine]
+        d2h_per_rank = [float(x) for x in per_rank]
+        d2h_peak = sum(d2h_per_rank)            # aggregate over the N GPUs
+        d2h_slowest = min(d2h_per_rank)
+        del dbuf, hbuf
         cpu = None
         if rank == 0 and not a.no_cpu_baseline:
             v, cores, sample, sec, kind, _ = run_reference_cpu(tmp, profile, 1, 0)
@@ -275,6 +283,12 @@ def main():
         # (ceil(L/4) B per read) + 16 B descriptor per amplicon touched + 20 B of plan/offsets per slot
         slots = reads_per_step / 2
         alg_step = fastq_bytes + reads_per_step * ((READ_LEN + 3) // 4) + 16 * n_fulls + 20 * slots
+        traffic = None
+        try:   # dram__bytes_read+write of one emit launch from the committed ncu --set full capture of this same command
+            with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            pass
         emit_launches_per_step = emit_n / a.steps if a.steps else 0
         emit_ms_avg = emit_ms / emit_n if emit_n else None
         achieved = (alg_step / emit_launches_per_step) / (emit_ms_avg / 1e3) / 1e9 if emit_ms_avg else None
@@ -290,12 +304,14 @@ def main():
                     "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "launches_per_step": emit_launches_per_step, "avg_launch_ms": emit_ms_avg,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": (alg_step / emit_launches_per_step) if emit_launches_per_step else None, "peak_source": peak_src, "launches_per_step": emit_launches_per_step, "avg_launch_ms": emit_ms_avg,
                          "kernel_share_of_step": (emit_ms / a.steps) / (dev_s / a.steps * 1e3) if dev_s else None,
-                         "d2h": {"bound": "pcie", "achieved": bytes_all / world * a.steps / dev_s / 1e9, "peak": d2h_peak, "unit": "GB/s",
-                                 "frac": (bytes_all / world * a.steps / dev_s / 1e9 / d2h_peak) if d2h_peak else None,
-                                 "frac_read_stage": (bytes_all / world / (reads_ms / a.steps / 1e3) / 1e9 / d2h_peak) if d2h_peak and reads_ms else None,
-                                 "note": "FASTQ bytes per GPU landing in pinned host memory over the whole step / over the read stage only, against the pinned D2H copy rate measured in this run; this, not HBM, is the binding roof of the path"}},
+                         "d2h": {"bound": "pcie", "achieved": bytes_all * a.steps / dev_s / 1e9, "peak": d2h_peak, "unit": "GB/s (all GPUs)",
+                                 "frac": (bytes_all * a.steps / dev_s / 1e9 / d2h_peak) if d2h_peak else None,
+                                 "frac_read_stage_rank0": (bytes_all / world / (reads_ms / a.steps / 1e3) / 1e9 / d2h_per_rank[0]) if reads_ms else None,
+                                 "per_gpu_peak": [round(x, 1) for x in d2h_per_rank],
+                                 "weak_scaling_ceiling": world * d2h_slowest,
+                                 "note": "FASTQ bytes landing in pinned host memory over the whole step, against the pinned D2H copy rate measured in this run with all ranks copying at once; this, not HBM, is the binding roof of the path. With equal shards the slowest GPU's link sets the pace: ceiling = N x slowest"}},
             "cpu_baseline": cpu, "clocks": clk,
         }
         emit(out)

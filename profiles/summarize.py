@@ -56,4 +56,15 @@ with open(f"profiles/{tag}_ncu_full.txt", "w") as out:
         for k in KEYS:
             if k in idx:
                 out.write(f"   {k:90s} {r[idx[k]]:>18s} {units[idx[k]]}\n")
+# DRAM traffic of one emit launch (bench.py reports it as roofline.traffic)
+import json
+for r in rows[2:]:
+    if r[idx["Kernel Name"]].startswith("emit_kernel") or "emit_kernel" in r[idx["Kernel Name"]]:
+        def val(k):
+            v = float(r[idx[k]].replace(",", "")); u = units[idx[k]]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        json.dump({"kernel": "emit_kernel", "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                   "source": f"profiles/{tag}_ncu_full.txt (ncu --set full, python bench.py --steps 2 --warmup 1 --no-cpu-baseline)"},
+                  open("profiles/emit_traffic.json", "w"))
+        break
 print(open(f"profiles/{tag}_launches.txt").read())
