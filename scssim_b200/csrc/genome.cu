@@ -235,9 +235,29 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
         for (size_t i = 0; i < fai.size(); i++) fprintf(o, "%s\t%llu\t%llu\t%d\t%d\n", fai[i].name.c_str(), (unsigned long long)seqs[i].size(), (unsigned long long)fai[i].off, fai[i].blen, fai[i].llen);
         fclose(o);
     }
+    // world > 1: this rank keeps a contiguous run of sequences, cut where the cumulative length crosses rank/world of the
+    // total (sequence midpoints decide), so every rank holds about the same number of bases
+    size_t lo = 0, hi = seqs.size();
+    if (c->P.world > 1) {
+        long double total = 0; for (auto& s : seqs) total += s.size();
+        long double acc = 0; lo = hi = seqs.size(); bool started = false;
+        for (size_t i = 0; i < seqs.size(); i++) {
+            long double mid = acc + seqs[i].size() / 2.0L;
+            int owner = std::min(c->P.world - 1, (int)(mid * c->P.world / (total > 0 ? total : 1)));
+            if (owner == c->P.rank) { if (!started) { lo = i; started = true; } hi = i + 1; }
+            acc += seqs[i].size();
+        }
+        if (!started) lo = hi = 0;
+    }
     std::vector<const char*> np, sp; std::vector<uint64_t> lens;
-    for (size_t i = 0; i < seqs.size(); i++) { np.push_back(names[i].c_str()); sp.push_back(seqs[i].data()); lens.push_back(seqs[i].size()); }
-    return genome_from_host(c, (int)seqs.size(), np.data(), sp.data(), lens.data());
+    for (size_t i = lo; i < hi; i++) { np.push_back(names[i].c_str()); sp.push_back(seqs[i].data()); lens.push_back(seqs[i].size()); }
+    if (np.empty()) {   // more ranks than sequences: this rank holds nothing but still takes part in the collectives
+        c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear(); c->ref_len_sum = 0; c->ref_len_half = 0; c->genome_bases = 0;
+        SCS_CUDA(c, c->genome_words.reserve(2)); SCS_CUDA(c, c->genome_nmask.reserve(2));
+        c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
+        return SCS_OK;
+    }
+    return genome_from_host(c, (int)np.size(), np.data(), sp.data(), lens.data());
 }
 
 // ------------------------------------------------------------------------------ fragments (host)

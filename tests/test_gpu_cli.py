@@ -32,3 +32,25 @@ def test_cli_missing_profile_exits_like_reference(tmp_path):
     H.write_genome(fa, 1, 50_000, seed=1)
     r = subprocess.run([EXE, "genreads", "-i", fa, "-m", "/nonexistent.profile", "-o", os.path.join(str(tmp_path), "x")], capture_output=True)
     assert r.returncode != 0 and b"can not open file /nonexistent.profile" in r.stderr
+
+
+def test_cli_two_gpu_workers_write_the_same_records(tmp_path):
+    """--gpus 2 (both workers on this GPU via the test hook): the concatenated shards hold exactly the records of --gpus 1."""
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome(fa, 2, 120_000, seed=33)          # 4 sequences -> 2 per worker
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, "PE", 2e-10, 4.0, 260)
+    outs = {}
+    for n in (1, 2):
+        r = subprocess.run([EXE, "genreads", "-i", fa, "-o", os.path.join(tmp, f"g{n}"), "--seed", "99", "--gpus", str(n)] + args,
+                           capture_output=True, env=dict(os.environ, SCS_CLI_SAME_DEVICE="1"))
+        assert r.returncode == 0, r.stderr.decode()
+        outs[n] = [H.read_bytes(os.path.join(tmp, f"g{n}_{k}.fq")) for k in (1, 2)]
+        assert not os.path.exists(os.path.join(tmp, f"g{n}.rank0_1.fq"))
+
+    def recs(b):
+        ls = b.split(b"\n")[:-1]
+        return sorted(b"\n".join(ls[i:i + 4]) for i in range(0, len(ls), 4))
+    for k in range(2):
+        assert len(outs[1][k]) > 0 and recs(outs[1][k]) == recs(outs[2][k])
