@@ -54,3 +54,19 @@ def test_cli_two_gpu_workers_write_the_same_records(tmp_path):
         return sorted(b"\n".join(ls[i:i + 4]) for i in range(0, len(ls), 4))
     for k in range(2):
         assert len(outs[1][k]) > 0 and recs(outs[1][k]) == recs(outs[2][k])
+
+
+def test_cli_more_workers_than_sequences(tmp_path):
+    """A worker that owns no sequence still takes part in every collective; output equals the single-worker run."""
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome(fa, 1, 150_000, seed=35, diploid=False)      # one sequence, two workers
+    prof = H.profile_path("Illumina_HiSeq2000")
+    args = H.genreads_args(prof, "SE", 3e-10, 3.0, 260)
+    outs = {}
+    for n in (1, 2):
+        r = subprocess.run([EXE, "genreads", "-i", fa, "-o", os.path.join(tmp, f"g{n}"), "--seed", "7", "--gpus", str(n)] + args,
+                           capture_output=True, env=dict(os.environ, SCS_CLI_SAME_DEVICE="1"), timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        outs[n] = H.read_bytes(os.path.join(tmp, f"g{n}.fq"))
+    assert len(outs[1]) > 0 and outs[1] == outs[2]
