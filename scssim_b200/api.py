@@ -18,7 +18,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscssim_b200.so")
+LIB_PATH = os.environ.get("SCS_LIB_PATH") or os.path.join(_HERE, "libscssim_b200.so")   # SCS_LIB_PATH: A/B builds while tuning
 
 SCS_OK, SCS_E_ARG, SCS_E_IO, SCS_E_CUDA, SCS_E_STATE, SCS_E_UNSUPPORTED, SCS_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 D_FRAG, D_POIS, D_AMPF, D_AMPS, D_GCF, D_MULTM, D_MULTC, D_READ = range(8)

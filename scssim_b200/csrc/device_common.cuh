@@ -32,6 +32,10 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Out-of-line copy for the scattered single-draw call sites: every inlined Philox is ~100 instructions (1.6 KB of SASS), and the
+// read kernels must stay inside the 32 KB instruction cache (ncu: 17 % no_instruction stalls with everything inlined).
+__device__ __noinline__ void philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out);
+
 // Where an entity's draws come from. tape == nullptr -> Philox.
 struct DrawSrc {
     uint64_t seed;
@@ -64,7 +68,11 @@ struct Stream {
     __device__ __forceinline__ uint32_t at(int engine, uint32_t i) const {
         if (t[0] != nullptr) return t[engine][i];
         uint32_t o[4];
+#ifdef SCS_PHILOX_OUTLINE
+        philox4x32_10_call(e0, e1, i >> 2, dom2 + (uint32_t)engine, k0, k1, o);
+#else
         philox4x32_10(e0, e1, i >> 2, dom2 + (uint32_t)engine, k0, k1, o);
+#endif
         return o[i & 3];
     }
 };

@@ -17,9 +17,14 @@
 #include <cstdlib>
 #include <cstring>
 
+#define SCS_PHILOX_OUTLINE 1
 #include "ctx.h"
 
 namespace scs {
+
+__device__ __noinline__ void philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+    philox4x32_10(c0, c1, c2, c3, k0, k1, out);
+}
 
 constexpr int kReadWarps = 8;         // warps per CTA (plan / test kernels)
 constexpr int kEmitWarps = 24;        // warps per persistent CTA of the emit kernel (one CTA per SM)
@@ -346,6 +351,7 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     uint32_t nerr = 0; const uint32_t* __restrict__ errs = nullptr;
     if (fetch) { const uint64_t er = __ldg(A.errref + a); nerr = (uint32_t)(er & 0xFFFF); errs = A.err_pool + (er >> 16); }
     uint32_t lens = 0;
+#pragma unroll 1
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
         bool hasN = false;
         if (fetch) {
