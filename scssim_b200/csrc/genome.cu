@@ -144,6 +144,29 @@ __global__ void __launch_bounds__(256) pack_genome_kernel(const uint8_t* __restr
     if (mask) atomicOr(bad, 1u);
 }
 
+// Same, reading straight from FASTA text with a fixed line geometry (blen bases per line, llen bytes per line incl. the
+// line terminator — the .fai model of lib/fastahack/Fasta.cpp:304-334): the newlines are never stripped on the host.
+__global__ void __launch_bounds__(256) pack_fasta_kernel(const uint8_t* __restrict__ text, uint64_t n_bases, uint32_t blen, uint32_t llen,
+                                                         uint64_t* __restrict__ words, uint32_t* __restrict__ nmask, unsigned int* __restrict__ bad) {
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t n_words = (n_bases + 31) >> 5;
+    if (w >= n_words) return;
+    uint64_t base = w << 5;
+    uint64_t line = base / blen; uint32_t col = (uint32_t)(base % blen);
+    const uint8_t* p = text + line * llen + col;
+    uint64_t out = 0; uint32_t mask = 0;
+    for (int k = 0; k < 32; k++) {
+        uint32_t ch = (base + k < n_bases) ? (*p & 0xDFu) : (uint32_t)'A';
+        uint32_t code = (ch >> 1) & 3u; code ^= (code >> 1);
+        const bool bad1 = (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T');
+        mask |= (uint32_t)bad1 << k;
+        out |= (uint64_t)(bad1 ? 0u : code) << (2 * k);
+        if (++col == blen) { col = 0; p += llen - blen + 1; } else p++;
+    }
+    words[w] = out; nmask[w] = mask;
+    if (mask) atomicOr(bad, 1u);
+}
+
 static std::string ref_seq_name(const std::string& header) {   // lib/fastahack/Fasta.cpp:57-68
     std::string name = header.substr(0, header.find_first_of(" \t"));
     size_t i = name.find("chrom");
@@ -152,7 +175,19 @@ static std::string ref_seq_name(const std::string& header) {   // lib/fastahack/
     return name;
 }
 
+// one sequence of the cell on the host: contiguous ASCII bases (blen == 0) or FASTA text with a fixed line geometry
+struct SeqSrc { const char* p; uint64_t len; uint32_t blen, llen; };
+static int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src);
+
 int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens) {
+    std::vector<SeqSrc> src((size_t)std::max(n, 0));
+    for (int i = 0; i < n; i++) src[i] = {seqs[i], lens[i], 0, 0};
+    return genome_from_sources(c, n, names, src.data());
+}
+
+static int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src) {
+    std::vector<uint64_t> lens_v((size_t)std::max(n, 0)); for (int i = 0; i < n; i++) lens_v[i] = src[i].len;
+    const uint64_t* lens = lens_v.data();
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
     if (n <= 0) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
     c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear();
@@ -175,17 +210,34 @@ int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* co
     DevBuf<unsigned int> bad; SCS_CUDA(c, bad.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(bad.p, 0, 4, c->st));
     // stage ASCII through a bounded device buffer
     const uint64_t chunk = 256ull << 20;
-    DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(chunk));
+    DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(chunk + (chunk >> 4) + 4096));
     cudaEventRecord(e0, c->st);
     for (int i = 0; i < n; i++) {
-        for (uint64_t off = 0; off < lens[i]; off += chunk) {
-            uint64_t m = std::min(chunk, lens[i] - off);
-            SCS_CUDA(c, cudaMemcpyAsync(stage.p, seqs[i] + off, m, cudaMemcpyHostToDevice, c->st));
-            uint64_t nw = (m + 31) >> 5;
-            pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, c->genome_words.p + ((c->seq_goff[i] + off) >> 5),
-                                                                                c->genome_nmask.p + ((c->seq_goff[i] + off) >> 5), bad.p);
-            SCS_LAUNCHED(c);
-            SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        if (src[i].blen == 0) {
+            for (uint64_t off = 0; off < lens[i]; off += chunk) {
+                uint64_t m = std::min(chunk, lens[i] - off);
+                SCS_CUDA(c, cudaMemcpyAsync(stage.p, src[i].p + off, m, cudaMemcpyHostToDevice, c->st));
+                uint64_t nw = (m + 31) >> 5;
+                pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, c->genome_words.p + ((c->seq_goff[i] + off) >> 5),
+                                                                                    c->genome_nmask.p + ((c->seq_goff[i] + off) >> 5), bad.p);
+                SCS_LAUNCHED(c);
+                SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            }
+        } else {
+            // FASTA text: chunks of whole lines whose base count is a multiple of 32 (so every chunk starts on a packed word)
+            const uint64_t blen = src[i].blen, llen = src[i].llen;
+            uint64_t lines_per_chunk = std::max<uint64_t>(32, (chunk / llen) / 32 * 32);
+            for (uint64_t l0 = 0; l0 * blen < lens[i]; l0 += lines_per_chunk) {
+                const uint64_t b0 = l0 * blen, m = std::min(lines_per_chunk * blen, lens[i] - b0);
+                const uint64_t nbytes = m + (m - 1) / blen * (llen - blen);   // text bytes spanned by m bases
+                SCS_CUDA(c, cudaMemcpyAsync(stage.p, src[i].p + l0 * llen, nbytes, cudaMemcpyHostToDevice, c->st));
+                uint64_t nw = (m + 31) >> 5;
+                pack_fasta_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>(stage.p, m, (uint32_t)blen, (uint32_t)llen,
+                                                                                   c->genome_words.p + ((c->seq_goff[i] + b0) >> 5),
+                                                                                   c->genome_nmask.p + ((c->seq_goff[i] + b0) >> 5), bad.p);
+                SCS_LAUNCHED(c);
+                SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            }
         }
     }
     cudaEventRecord(e1, c->st);
@@ -207,10 +259,11 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
     size_t got = sz > 0 ? fread(raw.data(), 1, (size_t)sz, f) : 0;
     fclose(f);
     raw[got] = '\n';
-    std::vector<std::string> names; std::vector<std::vector<char>> seqs;
-    // .fai side effect of FastaReference::open (lib/fastahack/Fasta.cpp:243-249): name, length, offset, line_blen, line_len
-    struct Fai { std::string name; uint64_t len, off; int blen, llen; };
-    std::vector<Fai> fai;
+    // One pass over the lines builds the .fai index (name, length, offset, bases per line, bytes per line): with a uniform
+    // line geometry (what the reference's fastahack reader requires, lib/fastahack/Fasta.cpp:304-334) the text is uploaded
+    // as it is and the newlines are skipped by index arithmetic on the device; otherwise the bases are gathered on the host.
+    struct Fai { std::string name; uint64_t len, off; uint32_t blen, llen; bool regular; uint64_t short_lines; };
+    std::vector<std::string> names; std::vector<Fai> fai;
     size_t pos = 0;
     while (pos < got) {
         char* s = &raw[pos];
@@ -219,22 +272,46 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
         size_t llen = len + 1;
         if (len > 0 && s[len - 1] == '\r') len--;
         if (len > 0 && s[0] == '>') {
-            names.push_back(std::string(s + 1, len - 1)); seqs.emplace_back();
+            names.push_back(std::string(s + 1, len - 1));
             std::string full(s + 1, len - 1);
-            fai.push_back({full.substr(0, full.find_first_of(" \t")), 0, (uint64_t)(pos + llen), 0, 0});
-        } else if (len > 0 && !seqs.empty()) {
-            seqs.back().insert(seqs.back().end(), s, s + len);
-            if (fai.back().blen == 0) { fai.back().blen = (int)len; fai.back().llen = (int)llen; }
+            fai.push_back({full.substr(0, full.find_first_of(" \t")), 0, (uint64_t)(pos + llen), 0, 0, true, 0});
+        } else if (!fai.empty()) {
+            Fai& a = fai.back();
+            if (len == 0) { if (a.len) a.short_lines++; }          // a blank line is fine only at the very end of a record
+            else {
+                if (a.blen == 0) { a.blen = (uint32_t)len; a.llen = (uint32_t)llen; }
+                if (a.short_lines) a.regular = false;               // bases after a short or blank line
+                if (len != a.blen || llen != a.llen) { if (len > a.blen) a.regular = false; a.short_lines++; }
+                a.len += len;
+            }
         }
         pos += llen;
     }
-    if (seqs.empty()) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
-    std::string faiPath = std::string(path) + ".fai";
+    if (fai.empty()) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
+    std::string faiPath = std::string(path) + ".fai";   // side effect of FastaReference::open (Fasta.cpp:243-249)
     if (FILE* t = fopen(faiPath.c_str(), "rb")) fclose(t);
     else if (FILE* o = fopen(faiPath.c_str(), "wb")) {
-        for (size_t i = 0; i < fai.size(); i++) fprintf(o, "%s\t%llu\t%llu\t%d\t%d\n", fai[i].name.c_str(), (unsigned long long)seqs[i].size(), (unsigned long long)fai[i].off, fai[i].blen, fai[i].llen);
+        for (size_t i = 0; i < fai.size(); i++) fprintf(o, "%s\t%llu\t%llu\t%u\t%u\n", fai[i].name.c_str(), (unsigned long long)fai[i].len, (unsigned long long)fai[i].off, fai[i].blen, fai[i].llen);
         fclose(o);
     }
+    // irregular records: gather their bases into contiguous host buffers (slow path)
+    std::vector<std::vector<char>> gathered(fai.size());
+    std::vector<SeqSrc> all(fai.size());
+    for (size_t i = 0; i < fai.size(); i++) {
+        if (fai[i].len > 0 && fai[i].len <= fai[i].blen) { all[i] = {&raw[fai[i].off], fai[i].len, 0, 0}; continue; }   // one line: already contiguous
+        if (fai[i].regular && fai[i].len > 0 && fai[i].llen <= (1u << 20)) { all[i] = {&raw[fai[i].off], fai[i].len, fai[i].blen, fai[i].llen}; continue; }
+        std::vector<char>& g = gathered[i]; g.reserve(fai[i].len);
+        size_t q = fai[i].off, end = (i + 1 < fai.size()) ? (size_t)fai[i + 1].off : got;
+        while (q < end && g.size() < fai[i].len) {
+            char* s = &raw[q]; char* e = (char*)memchr(s, '\n', got + 1 - q); size_t len = (size_t)(e - s); q += len + 1;
+            if (len > 0 && s[len - 1] == '\r') len--;
+            if (len > 0 && s[0] == '>') break;
+            g.insert(g.end(), s, s + len);
+        }
+        all[i] = {g.data(), g.size(), 0, 0};
+    }
+    struct SeqView { size_t size() const { return n; } uint64_t n; };
+    std::vector<SeqView> seqs(fai.size()); for (size_t i = 0; i < fai.size(); i++) seqs[i].n = all[i].len;
     // world > 1: this rank keeps a contiguous run of sequences, cut where the cumulative length crosses rank/world of the
     // total (sequence midpoints decide), so every rank holds about the same number of bases
     size_t lo = 0, hi = seqs.size();
@@ -249,15 +326,15 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
         }
         if (!started) lo = hi = 0;
     }
-    std::vector<const char*> np, sp; std::vector<uint64_t> lens;
-    for (size_t i = lo; i < hi; i++) { np.push_back(names[i].c_str()); sp.push_back(seqs[i].data()); lens.push_back(seqs[i].size()); }
+    std::vector<const char*> np; std::vector<SeqSrc> sp;
+    for (size_t i = lo; i < hi; i++) { np.push_back(names[i].c_str()); sp.push_back(all[i]); }
     if (np.empty()) {   // more ranks than sequences: this rank holds nothing but still takes part in the collectives
         c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear(); c->ref_len_sum = 0; c->ref_len_half = 0; c->genome_bases = 0;
         SCS_CUDA(c, c->genome_words.reserve(2)); SCS_CUDA(c, c->genome_nmask.reserve(2));
         c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
         return SCS_OK;
     }
-    return genome_from_host(c, (int)np.size(), np.data(), sp.data(), lens.data());
+    return genome_from_sources(c, (int)np.size(), np.data(), sp.data());
 }
 
 // ------------------------------------------------------------------------------ fragments (host)

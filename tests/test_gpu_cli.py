@@ -70,3 +70,40 @@ def test_cli_more_workers_than_sequences(tmp_path):
         assert r.returncode == 0, r.stderr.decode()
         outs[n] = H.read_bytes(os.path.join(tmp, f"g{n}.fq"))
     assert len(outs[1]) > 0 and outs[1] == outs[2]
+
+
+def test_fasta_layouts_load_identically(tmp_path):
+    """Fixed-width FASTA (newlines skipped on the GPU), CRLF line ends, a single-line record and a ragged record (host
+    gather) all pack to the same genome: identical FASTQ for the same seed."""
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_genome
+    tmp = str(tmp_path)
+    genome = synth_genome(1, 90_000, seed=51, diploid=True)
+    prof = H.profile_path("Illumina_HiSeq2500")
+
+    def write(path, width, eol=b"\n", ragged=False):
+        with open(path, "wb") as f:
+            for name, s in genome:
+                f.write(b">" + name.encode() + b" some description" + eol)
+                b = s.tobytes()
+                if ragged:
+                    i, w = 0, 37
+                    while i < len(b):
+                        f.write(b[i:i + w] + eol); i += w; w = 37 + (i % 11)
+                elif width is None:
+                    f.write(b + eol)
+                else:
+                    for i in range(0, len(b), width):
+                        f.write(b[i:i + width] + eol)
+    outs = []
+    for k, kw in enumerate([dict(width=60), dict(width=100, eol=b"\r\n"), dict(width=None), dict(width=None, ragged=True), dict(width=32)]):
+        fa = os.path.join(tmp, f"g{k}.fa")
+        write(fa, **{"width": kw.get("width"), "eol": kw.get("eol", b"\n"), "ragged": kw.get("ragged", False)})
+        with api.GenReads(gamma=3e-10, coverage=3.0, layout="PE", seed=5) as g:
+            g.load_profile(prof).load_genome(fa).create_frags().amplify()
+            outs.append(g.yield_reads_bytes())
+        fai = open(fa + ".fai").read().split("\n")[0].split("\t")
+        assert fai[0] == genome[0][0] and int(fai[1]) == 90_000
+    assert len(outs[0][0]) > 0
+    for o in outs[1:]:
+        assert o == outs[0]
