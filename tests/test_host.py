@@ -118,3 +118,28 @@ def test_cli_rejects_bad_flags_like_the_reference():
     assert r.returncode == 1 and b"reference file (.fasta) not specified" in r.stderr
     r = subprocess.run([exe, "genreads", "-i", "x.fa", "-m", "m.profile", "-o", "out", "-l", "XX"], capture_output=True)
     assert r.returncode == 1 and b"sequence layout incorrectly specified" in r.stderr
+
+
+def test_resampled_profile_is_a_valid_profile(tmp_path):
+    """bench.py derives a 150-bin profile from the shipped 125-bin HiSeq2500 one (read length is a property of the
+    .profile); both parsers must accept it and row j of the new tables must equal row floor(j*125/150) of the old ones."""
+    from scssim_b200.tools.resample_profile import resample
+    src = H.profile_path("Illumina_HiSeq2500")
+    dst = os.path.join(str(tmp_path), "hs2500_150.profile")
+    resample(src, dst, 150)
+    g_old = api.GenReads(device=-1).load_profile(src)
+    g_new = api.GenReads(device=-1).load_profile(dst)
+    assert g_old.read_length == 125 and g_new.read_length == 150
+    for j in (0, 1, 37, 88, 149):
+        for which, idx in ((3, 25), (4, 60), (5, 0), (5, 10)):
+            a, ea = g_new.thresholds(which, idx, j)
+            b, eb = g_old.thresholds(which, idx, j * 125 // 150)
+            assert ea == eb and np.array_equal(a, b)
+    L = H.oracle_lib()
+    err = C.create_string_buffer(256)
+    op = L.orc_profile_load(dst.encode(), 1, 260, err, 256)
+    assert op, err.value
+    info = (C.c_int * 9)()
+    L.orc_profile_info(op, info)
+    assert info[0] == 150 and info[1] == 150
+    L.orc_profile_free(op)
