@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN, help="(debug) override the workload size; invalidates the number")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="(debug) skip the CPU leg")
+    ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons (equal shards)")
     ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -189,12 +190,38 @@ def main():
         pinned = torch.empty(glen, dtype=torch.uint8, pin_memory=True)
         pinned.numpy()[:] = seq
         named = [(f"chrS{rank + 1}_1_{glen}", pinned.numpy())]
-        # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream
-        g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world, slab_bytes=a.slab_mb << 20)
+        # pinned D2H copy ceiling of this box, measured live with ALL ranks copying at once (the binding roof of the read
+        # stage, SURVEY.md §8d; on shared PCIe fabrics the per-GPU rate drops as N grows)
+        nb = 256 << 20
+        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda"); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        hbuf.copy_(dbuf, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(6):
+            hbuf.copy_(dbuf, non_blocking=True)
+        c1.record(); torch.cuda.synchronize()
+        mine = torch.tensor([6 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9], dtype=torch.float64, device="cuda")
+        per_rank = [torch.zeros_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, mine)
+        else:
+            per_rank = [mine]
+        d2h_per_rank = [float(x) for x in per_rank]
+        d2h_peak = sum(d2h_per_rank)            # aggregate over the N GPUs
+        d2h_slowest = min(d2h_per_rank)
+        del dbuf, hbuf
+        # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream. With several GPUs the
+        # read slots are cut in proportion to each GPU's measured D2H rate (balance=1), so a GPU behind a slower host link
+        # writes fewer reads; the rank-ordered shards are byte-identical to the single-GPU files
+        g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world,
+                         slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance))
+        if world > 1:
+            g.set_shard_weight(d2h_per_rank[rank])
         if world > 1:
             from scssim_b200.dist import make_collectives, make_device_allreduce
             g.set_collectives(*make_collectives(dist, device=f"cuda:{local}"))
-            g.set_device_collective(make_device_allreduce(dist, f"cuda:{local}"))
+            g.set_device_collective(*make_device_allreduce(dist, f"cuda:{local}"))
         g.load_profile(profile)
         g.set_genome(named).create_frags()
 
@@ -251,27 +278,6 @@ def main():
         value = reads_all * a.steps / dev_s / 1e6
         e2e_value = reads_all * e2e_steps / e2e_s / 1e6
 
-        # pinned D2H copy ceiling of this box, measured live with ALL ranks copying at once (the binding roof of the read
-        # stage, SURVEY.md §8d; on shared PCIe fabrics the per-GPU rate drops as N grows)
-        nb = 256 << 20
-        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda"); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-        hbuf.copy_(dbuf, non_blocking=True)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(6):
-            hbuf.copy_(dbuf, non_blocking=True)
-        c1.record(); torch.cuda.synchronize()
-        mine = torch.tensor([6 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9], dtype=torch.float64, device="cuda")
-        per_rank = [torch.zeros_like(mine) for _ in range(world)]
-        if world > 1:
-            dist.all_gather(per_rank, mine)
-        else:
-            per_rank = [mine]
-        d2h_per_rank = [float(x) for x in per_rank]
-        d2h_peak = sum(d2h_per_rank)            # aggregate over the N GPUs
-        d2h_slowest = min(d2h_per_rank)
-        del dbuf, hbuf
         cpu = None
         if rank == 0 and not a.no_cpu_baseline:
             v, cores, sample, sec, kind, _ = run_reference_cpu(tmp, profile, 1, 0)
@@ -311,8 +317,8 @@ def main():
                                  "frac": (bytes_all * a.steps / dev_s / 1e9 / d2h_peak) if d2h_peak else None,
                                  "frac_read_stage_rank0": (bytes_all / world / (reads_ms / a.steps / 1e3) / 1e9 / d2h_per_rank[0]) if reads_ms else None,
                                  "per_gpu_peak": [round(x, 1) for x in d2h_per_rank],
-                                 "weak_scaling_ceiling": world * d2h_slowest,
-                                 "note": "FASTQ bytes landing in pinned host memory over the whole step, against the pinned D2H copy rate measured in this run with all ranks copying at once; this, not HBM, is the binding roof of the path. With equal shards the slowest GPU's link sets the pace: ceiling = N x slowest"}},
+                                 "equal_shard_ceiling": world * d2h_slowest, "balanced": bool(world > 1 and not a.no_balance),
+                                 "note": "FASTQ bytes landing in pinned host memory over the whole step, against the pinned D2H copy rate measured in this run with all ranks copying at once; this, not HBM, is the binding roof of the path. With equal shards the slowest GPU's link would set the pace (N x slowest); for N > 1 the read slots are cut in proportion to the measured per-GPU rates"}},
             "cpu_baseline": cpu, "clocks": clk,
         }
         emit(out)

@@ -50,7 +50,10 @@ typedef struct scs_params {
     int32_t device;       /* CUDA device ordinal */
     int32_t rank;         /* shard index in [0, world) */
     int32_t world;        /* number of shards (GPUs) */
-    int32_t reserved;
+    int32_t balance;      /* world > 1 only. 0: every rank writes the reads of its own amplicons. 1: the packed genome and the
+                             amplicon table are replicated over the ranks (all-reduce over NVLink) and the cell's read slots are
+                             cut into contiguous ranges in proportion to scs_set_shard_weight(), so a GPU behind a slower host
+                             link gets fewer reads; the shards then concatenate (rank order) to exactly the 1-GPU files */
     uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (64 MiB) */
 } scs_params;
 
@@ -79,7 +82,12 @@ int scs_set_collectives(scs_ctx* ctx, scs_allreduce_u64_fn fu, scs_allreduce_f64
  * ncclAllReduce over NVLink without a host round trip). The library's stream is idle when the hook is called and the
  * hook must have completed the reduction when it returns. Without it the host hook above is used. */
 typedef int (*scs_allreduce_dev_f64_fn)(void* user, double* dev_buf, size_t n);
-int scs_set_device_collective(scs_ctx* ctx, scs_allreduce_dev_f64_fn fn, void* user);
+/* Same for 64-bit integers (balance = 1: genome words, amplicon descriptors, error lists — every element is non-zero on
+ * exactly one rank, so the sum is a gather). */
+typedef int (*scs_allreduce_dev_i64_fn)(void* user, int64_t* dev_buf, size_t n);
+int scs_set_device_collective(scs_ctx* ctx, scs_allreduce_dev_f64_fn fn_f64, scs_allreduce_dev_i64_fn fn_i64, void* user);
+/* Relative share of the cell's reads this rank should write when balance = 1 (e.g. its measured D2H rate). Default 1. */
+int scs_set_shard_weight(scs_ctx* ctx, double weight);
 
 int scs_create_frags(scs_ctx* ctx);   /* Genome::splitToFrags, Genome.cpp:753-782 */
 int scs_amplify(scs_ctx* ctx);        /* Malbac::amplify, Malbac.cpp:173-201 */

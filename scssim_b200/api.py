@@ -34,7 +34,7 @@ class ScsError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
                 ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("reserved", C.c_int32), ("slab_bytes", C.c_uint64)]
+                ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -64,10 +64,11 @@ SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
 AR_U64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_size_t)
 AR_F64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_size_t)
 AR_DEV_F64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+AR_DEV_I64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 
 # every symbol include/scssim_b200.h declares
 EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", "scs_load_profile", "scs_read_length",
-           "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_create_frags", "scs_amplify",
+           "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_set_shard_weight", "scs_create_frags", "scs_amplify",
            "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version"]
@@ -93,7 +94,8 @@ def lib():
         L.scs_load_genome.argtypes = [C.c_void_p, C.c_char_p]
         L.scs_set_genome.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.scs_set_collectives.argtypes = [C.c_void_p, AR_U64_FN, AR_F64_FN, C.c_void_p]
-        L.scs_set_device_collective.argtypes = [C.c_void_p, AR_DEV_F64_FN, C.c_void_p]
+        L.scs_set_device_collective.argtypes = [C.c_void_p, AR_DEV_F64_FN, AR_DEV_I64_FN, C.c_void_p]
+        L.scs_set_shard_weight.argtypes = [C.c_void_p, C.c_double]
         for f in ("scs_create_frags", "scs_amplify", "scs_set_read_counts"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.scs_yield_reads_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
@@ -142,7 +144,7 @@ class GenReads:
 
     def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
                  layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
-                 slab_bytes: int = 0):
+                 slab_bytes: int = 0, balance: bool = False):
         if layout not in ("SE", "PE"):
             raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
         L = lib()
@@ -150,6 +152,7 @@ class GenReads:
         L.scs_default_params(C.byref(p))
         p.primers, p.gamma, p.coverage, p.isize = primers, gamma, coverage, isize
         p.paired, p.seed, p.device, p.rank, p.world, p.slab_bytes = int(layout == "PE"), seed, device, rank, world, slab_bytes
+        p.balance = int(balance)
         self._h = C.c_void_p()
         rc = L.scs_create(C.byref(p), C.byref(self._h))
         if rc != SCS_OK:
@@ -226,13 +229,21 @@ class GenReads:
         self._ck(lib().scs_set_collectives(self._h, self._cb[0], self._cb[1], None))
         return self
 
-    def set_device_collective(self, allreduce_dev_f64):
-        """allreduce_dev_f64(device_pointer: int, n: int) -> None, in place on device memory."""
+    def set_device_collective(self, allreduce_dev_f64, allreduce_dev_i64):
+        """allreduce_dev_*(device_pointer: int, n: int) -> None, in place on device memory."""
         def fd(_u, ptr, n):
             allreduce_dev_f64(int(ptr), int(n))
             return 0
-        self._cb_dev = AR_DEV_F64_FN(fd)
-        self._ck(lib().scs_set_device_collective(self._h, self._cb_dev, None))
+
+        def fi(_u, ptr, n):
+            allreduce_dev_i64(int(ptr), int(n))
+            return 0
+        self._cb_dev = (AR_DEV_F64_FN(fd), AR_DEV_I64_FN(fi))
+        self._ck(lib().scs_set_device_collective(self._h, self._cb_dev[0], self._cb_dev[1], None))
+        return self
+
+    def set_shard_weight(self, w: float):
+        self._ck(lib().scs_set_shard_weight(self._h, float(w)))
         return self
 
     def create_frags(self):                     # malbac.createFrags()

@@ -40,6 +40,19 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(const double* __rest
     w[i] = wg[g]; counts[i] = v; slot_gbase[i] = sbase_g[g]; slots[i] = paired ? (v >> 1) : v;
 }
 
+// balance = 1: this rank's amplicons scattered into the cell-wide table, rebased to the cell-wide genome / error pool
+__global__ void __launch_bounds__(256) scatter_amplicons_kernel(const uint64_t* __restrict__ desc, const uint64_t* __restrict__ errref,
+                                                                const uint64_t* __restrict__ gidx, uint64_t n, uint64_t base_bases, uint64_t err_base,
+                                                                uint64_t* __restrict__ gdesc, uint64_t* __restrict__ gerrref) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t g = gidx[i];
+    Tmpl t = unpack_desc(desc[i]);
+    gdesc[g] = pack_desc(t.gstart + base_bases, t.rc, t.len);
+    const uint64_t er = errref[i];
+    gerrref[g] = (er & 0xFFFFull) ? ((((er >> 16) + err_base) << 16) | (er & 0xFFFFull)) : 0ull;
+}
+
 __global__ void __launch_bounds__(256) weights_kernel(DrawSrc src, const double* __restrict__ gcf_tape, const uint64_t* __restrict__ gidx, uint64_t n,
                                                       const uint64_t* __restrict__ desc, const uint32_t* __restrict__ gc,
                                                       const double* __restrict__ gcMeans, double gcStd, double* __restrict__ w) {
@@ -247,6 +260,59 @@ int set_read_counts(scs_ctx* c) {
         }
     }
     SCS_CUDA(c, cudaMemcpyAsync(c->slot_base.p + n, &c->n_slots, 8, cudaMemcpyHostToDevice, c->st));
+    c->global_view = false;
+    if (multi && c->P.balance) {
+        // ---- replicate genome + amplicon table over the ranks and cut the cell's slots by shard weight ----
+        const int W = c->P.world, R = c->P.rank;
+        unsigned long long etop = 0;
+        SCS_CUDA(c, memcpy_sync(c, &etop, c->err_top.p, 8, cudaMemcpyDeviceToHost));
+        const uint64_t my_words = c->genome_bases / 32, my_errs = (etop + 1) & ~1ull;   // error sections padded to 8 bytes
+        std::vector<uint64_t> v(3 * (size_t)W, 0);
+        v[R] = my_words; v[W + R] = my_errs; v[2 * W + R] = (uint64_t)c->genome_has_n;
+        if (int rc = allreduce_u64(c, v.data(), v.size())) return rc;
+        uint64_t word_base = 0, err_base = 0, tot_words = 0, tot_errs = 0; int any_n = 0;
+        for (int r = 0; r < W; r++) { if (r < R) { word_base += v[r]; err_base += v[W + r]; } tot_words += v[r]; tot_errs += v[W + r]; any_n |= (int)v[2 * W + r]; }
+        const uint64_t mask_words = (tot_words + 1) & ~1ull;
+        SCS_CUDA(c, c->g_words.reserve(tot_words + 2)); SCS_CUDA(c, c->g_nmask.reserve(mask_words + 2));
+        SCS_CUDA(c, c->g_desc.reserve(N + 1)); SCS_CUDA(c, c->g_errref.reserve(N + 1)); SCS_CUDA(c, c->g_errs.reserve(tot_errs + 2));
+        SCS_CUDA(c, c->g_slot_base.reserve(N + 2));
+        SCS_CUDA(c, cudaMemsetAsync(c->g_words.p, 0, tot_words * 8, c->st));
+        if (my_words) SCS_CUDA(c, cudaMemcpyAsync(c->g_words.p + word_base, c->genome_words.p, my_words * 8, cudaMemcpyDeviceToDevice, c->st));
+        if (int rc = allreduce_dev_i64(c, c->g_words.p, tot_words)) return rc;
+        if (any_n) {
+            SCS_CUDA(c, cudaMemsetAsync(c->g_nmask.p, 0, mask_words * 4, c->st));
+            if (my_words) {
+                if (c->genome_has_n) SCS_CUDA(c, cudaMemcpyAsync(c->g_nmask.p + word_base, c->genome_nmask.p, my_words * 4, cudaMemcpyDeviceToDevice, c->st));
+            }
+            if (int rc = allreduce_dev_i64(c, c->g_nmask.p, mask_words / 2)) return rc;
+        }
+        SCS_CUDA(c, cudaMemsetAsync(c->g_errs.p, 0, (tot_errs + 2) * 4, c->st));
+        if (etop) SCS_CUDA(c, cudaMemcpyAsync(c->g_errs.p + err_base, c->err_pool.p, etop * 4, cudaMemcpyDeviceToDevice, c->st));
+        if (int rc = allreduce_dev_i64(c, c->g_errs.p, tot_errs / 2)) return rc;
+        SCS_CUDA(c, cudaMemsetAsync(c->g_desc.p, 0, N * 8, c->st)); SCS_CUDA(c, cudaMemsetAsync(c->g_errref.p, 0, N * 8, c->st));
+        if (n) {
+            scatter_amplicons_kernel<<<nbl, 256, 0, c->st>>>(c->fulls.desc.p, c->fulls.errref.p, c->full_gidx.p, n, word_base * 32, err_base, c->g_desc.p, c->g_errref.p);
+            SCS_LAUNCHED(c);
+        }
+        if (int rc = allreduce_dev_i64(c, c->g_desc.p, N)) return rc;
+        if (int rc = allreduce_dev_i64(c, c->g_errref.p, N)) return rc;
+        // cell-wide slot prefix (identical on every rank) and this rank's range by weight
+        uint64_t total_slots = 0;
+        { unsigned long long last_base = 0; uint32_t last_slots = 0;
+          SCS_CUDA(c, memcpy_sync(c, &last_base, sbase_g.p + (N - 1), 8, cudaMemcpyDeviceToHost));
+          SCS_CUDA(c, memcpy_sync(c, &last_slots, tmp.p + (N - 1), 4, cudaMemcpyDeviceToHost));
+          total_slots = last_base + last_slots; }
+        SCS_CUDA(c, cudaMemcpyAsync(c->g_slot_base.p, sbase_g.p, N * 8, cudaMemcpyDeviceToDevice, c->st));
+        SCS_CUDA(c, cudaMemcpyAsync(c->g_slot_base.p + N, &total_slots, 8, cudaMemcpyHostToDevice, c->st));
+        std::vector<double> wts((size_t)W, 0.0); wts[R] = c->shard_weight;
+        if (int rc = allreduce_f64(c, wts.data(), W)) return rc;
+        double wsum = 0; for (double x : wts) wsum += x;
+        double acc = 0; uint64_t lo = 0, hi = 0;
+        for (int r = 0; r <= R; r++) { lo = hi; acc += wts[r]; hi = (r == W - 1) ? total_slots : (uint64_t)((long double)total_slots * (acc / wsum)); }
+        c->g_slot_lo = lo; c->g_slot_hi = std::max(lo, hi); c->g_n_amp = N; c->g_bases = tot_words * 32; c->g_has_n = any_n;
+        c->global_view = true;
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    }
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_alloc = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
     c->have_counts = true;

@@ -16,7 +16,7 @@ const char* scs_version(void) { return "scssim_b200 0.1 (sm_100a)"; }
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
     p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
-    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->slab_bytes = 0;
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0;
 }
 
 int scs_create(const scs_params* p, scs_ctx** out) {
@@ -95,9 +95,14 @@ int scs_set_collectives(scs_ctx* c, scs_allreduce_u64_fn fu, scs_allreduce_f64_f
     return SCS_OK;
 }
 
-int scs_set_device_collective(scs_ctx* c, scs_allreduce_dev_f64_fn fn, void* user) {
+int scs_set_device_collective(scs_ctx* c, scs_allreduce_dev_f64_fn fn_f64, scs_allreduce_dev_i64_fn fn_i64, void* user) {
     if (!c) return SCS_E_ARG;
-    c->ar_dev_f64 = fn; c->ar_dev_user = user;
+    c->ar_dev_f64 = fn_f64; c->ar_dev_i64 = fn_i64; c->ar_dev_user = user;
+    return SCS_OK;
+}
+int scs_set_shard_weight(scs_ctx* c, double w) {
+    if (!c || !(w > 0)) return SCS_E_ARG;
+    c->shard_weight = w; c->have_counts = false;
     return SCS_OK;
 }
 

@@ -147,7 +147,11 @@ struct scs_ctx {
     scs::ReadScratch rscratch;
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
-    scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; void* ar_dev_user = nullptr;
+    scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; scs_allreduce_dev_i64_fn ar_dev_i64 = nullptr; void* ar_dev_user = nullptr;
+    double shard_weight = 1.0;
+    // balance = 1: cell-wide copies (identical on every rank) that the read stage works from, and this rank's slot range
+    scs::DevBuf<uint64_t> g_words, g_desc, g_errref, g_slot_base; scs::DevBuf<uint32_t> g_nmask, g_errs;
+    bool global_view = false; uint64_t g_n_amp = 0, g_slot_lo = 0, g_slot_hi = 0, g_bases = 0; int g_has_n = 0;
     scs_stats stats{};
 
     // FASTQ slabs
@@ -202,6 +206,8 @@ uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, ui
 // device exclusive scan: out[i] = sum_{j<i} in[j] (u64), returns total through *total_dev (device pointer, may be null)
 int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n);
 int allreduce_f64(scs_ctx* c, double* v, size_t n);
+// in-place sum over ranks of n 64-bit words in device memory (NCCL hook if set, else staged through the host hook)
+int allreduce_dev_i64(scs_ctx* c, void* dev, size_t n);
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
 // same for n <= 2048*2048 without allocation or synchronisation: scratch holds 2048+8 u64, the total is left in *total_dev
 int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev);

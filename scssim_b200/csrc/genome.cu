@@ -376,6 +376,19 @@ int allreduce_f64(scs_ctx* c, double* v, size_t n) {
     return c->ar_f64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
 }
 
+int allreduce_dev_i64(scs_ctx* c, void* dev, size_t n) {
+    if (c->P.world <= 1 || n == 0) return SCS_OK;
+    if (c->ar_dev_i64) {
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        return c->ar_dev_i64(c->ar_dev_user, (int64_t*)dev, n) ? c->fail(SCS_E_STATE, "device allreduce callback failed") : SCS_OK;
+    }
+    std::vector<uint64_t> h(n);
+    SCS_CUDA(c, memcpy_sync(c, h.data(), dev, n * 8, cudaMemcpyDeviceToHost));
+    if (int rc = allreduce_u64(c, h.data(), n)) return rc;
+    SCS_CUDA(c, memcpy_sync(c, dev, h.data(), n * 8, cudaMemcpyHostToDevice));
+    return SCS_OK;
+}
+
 int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782
     if (!c->have_genome) return c->fail(SCS_E_STATE, "scs_create_frags: no genome loaded");
     const uint32_t fragMin = 10000, fragMax = 100000;   // Fragment.cpp:15-16

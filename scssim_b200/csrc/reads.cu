@@ -283,6 +283,7 @@ struct SlabArgs {
     const uint64_t* desc; const uint64_t* errref; const uint32_t* err_pool;
     const uint32_t* hdr_no;            // slow path: fragCount per slot (0 = dropped); nullptr -> slot index + 1
     const uint32_t* nfail;             // slow path: failed insert-size attempts before the slot's success
+    uint64_t fail_base;                // hdr_no / nfail are indexed by (slot - fail_base)
     uint64_t slab_cap;                 // bytes available in each output slab (emit bounds check)
 };
 
@@ -328,8 +329,8 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     const Tmpl F = unpack_desc(__ldg(A.desc + a));
     const int RL = T.RL; const int ampLen = (int)F.len;
     const uint64_t sb = __ldg(A.slot_base + a);
-    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot] : (uint32_t)(slot - sb) + 1u;
-    const uint32_t ampIdx = (uint32_t)__ldg(A.amp_gidx + a);
+    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot - A.fail_base] : (uint32_t)(slot - sb) + 1u;
+    const uint32_t ampIdx = A.amp_gidx ? (uint32_t)__ldg(A.amp_gidx + a) : (uint32_t)a;
     const uint64_t entity = __ldg(A.slot_gbase + a) + (slot - sb);
     if (fragNo == 0 || ampLen < RL) {   // dropped slot / Amplicon.cpp:442
         if (!EMIT && lane == 0) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; }
@@ -339,7 +340,7 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     uint32_t cr = 0, ci = 0;
     int pos = 0, isz = RL;
     if (T.paired) {
-        if (A.nfail) cr = A.nfail[slot];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
+        if (A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
         isz = T.minInsert + warp_count_le(T.isize, T.isizeEff, S.at(E_REAL, cr), lane);
         cr += 1;
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
@@ -442,8 +443,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, Draw
 
 // ---- slow path (insert sizes that can exceed an amplicon, -s large): failed attempts per slot -----
 __global__ void __launch_bounds__(256) fail_count_kernel(DrawSrc dsrc, ReadTables T, SlabArgs A, uint32_t* __restrict__ nfail) {
-    uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= A.nslots) return;
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nslots) return;
+    const uint64_t slot = A.fail_base + k;
     uint64_t lo = 0, hi = A.n_amp;
     while (hi - lo > 1) { uint64_t mid = (lo + hi) >> 1; if (A.slot_base[mid] <= slot) lo = mid; else hi = mid; }
     const int ampLen = (int)unpack_desc(A.desc[lo]).len;
@@ -454,17 +456,18 @@ __global__ void __launch_bounds__(256) fail_count_kernel(DrawSrc dsrc, ReadTable
         int isz = T.minInsert + count_le(T.isize, T.isizeEff, S.at(E_REAL, f));
         if (!(isz < T.RL || isz > ampLen)) break;
     }
-    nfail[slot] = f;
+    nfail[k] = f;
 }
 // per amplicon: fragCount numbering and the ">1000 failures -> give up" rule (Amplicon.cpp:448-490)
 __global__ void __launch_bounds__(256) fail_scan_kernel(SlabArgs A, const uint32_t* __restrict__ nfail, uint32_t* __restrict__ hdr_no) {
-    uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= A.n_amp) return;
+    // amplicons [A.slot0, A.slot0 + n): A.slot0 is reused as the first amplicon index here
+    uint64_t a = A.slot0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A.slot0 + A.nslots) return;
     uint64_t s0 = A.slot_base[a], s1 = A.slot_base[a + 1];
     uint32_t cum = 0; bool dead = false;
     for (uint64_t s = s0; s < s1; s++) {
-        if (!dead) { cum += nfail[s]; if (cum > 1000u) dead = true; }
-        hdr_no[s] = dead ? 0u : (uint32_t)(s - s0) + 1u + cum;
+        if (!dead) { cum += nfail[s - A.fail_base]; if (cum > 1000u) dead = true; }
+        hdr_no[s - A.fail_base] = dead ? 0u : (uint32_t)(s - s0) + 1u + cum;
     }
 }
 
@@ -526,7 +529,10 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     if (c->P.paired && !P.hasISize) return c->fail(SCS_E_ARG, "Error: unrecognized parameter name \"insertSize\"");   // Profile.cpp:1484 -> Config.cpp:71-78
     c->stats.records = 0; c->stats.fastq_bytes[0] = c->stats.fastq_bytes[1] = 0;
     c->stats.ms_reads = c->stats.ms_reads_kernels = c->stats.ms_emit_kernel = 0; c->stats.emit_launches = 0; c->stats.genome_window_bytes = 0;
-    const uint64_t nslots = c->n_slots;
+    // what this rank reads from: its own amplicons and genome, or (balance = 1) the cell-wide copies and a slot range
+    const bool gv = c->global_view;
+    const uint64_t slot_lo = gv ? c->g_slot_lo : 0, slot_hi = gv ? c->g_slot_hi : c->n_slots;
+    const uint64_t nslots = slot_hi - slot_lo;
     if (nslots == 0) return SCS_OK;
     const int nfiles = c->P.paired ? 2 : 1;
     const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
@@ -550,6 +556,12 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     DrawSrc dsrc = draw_src(c, D_READ);
     SlabArgs A; A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
     A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
+    A.fail_base = 0;
+    if (gv) {
+        g.words = c->g_words.p; g.nmask = c->g_nmask.p; g.n_bases = c->g_bases; g.has_n = c->g_has_n;
+        A.slot_gbase = c->g_slot_base.p; A.amp_gidx = nullptr; A.n_amp = c->g_n_amp; A.slot_base = c->g_slot_base.p;
+        A.desc = c->g_desc.p; A.errref = c->g_errref.p; A.err_pool = c->g_errs.p;
+    }
     ReadScratch& W = c->rscratch;
     SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
@@ -571,11 +583,22 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     cudaEventRecord(e0, c->st);
     // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
     if (c->P.paired && P.maxInsert > 1000) {
-        SCS_CUDA(c, W.nfail.reserve(nslots + 1)); SCS_CUDA(c, W.hdrno.reserve(nslots + 1));
-        SlabArgs F = A; F.slot0 = 0; F.nslots = nslots;
-        fail_count_kernel<<<(unsigned)((nslots + 255) / 256), 256, 0, c->st>>>(dsrc, T, F, W.nfail.p); SCS_LAUNCHED(c);
-        fail_scan_kernel<<<(unsigned)((A.n_amp + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
-        A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p;
+        // the numbering of an amplicon's pairs depends on all of its earlier pairs: cover whole amplicons around the range
+        uint64_t a_first = 0, a_last = A.n_amp - 1, ext_lo = slot_lo, ext_hi = slot_hi;
+        if (gv) {
+            std::vector<uint64_t> hb(A.n_amp + 1);
+            SCS_CUDA(c, memcpy_sync(c, hb.data(), A.slot_base, (A.n_amp + 1) * 8, cudaMemcpyDeviceToHost));
+            a_first = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), slot_lo) - hb.begin()) - 1;
+            a_last = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), slot_hi - 1) - hb.begin()) - 1;
+            ext_lo = hb[a_first]; ext_hi = hb[a_last + 1];
+        }
+        const uint64_t ext_n = ext_hi - ext_lo;
+        SCS_CUDA(c, W.nfail.reserve(ext_n + 1)); SCS_CUDA(c, W.hdrno.reserve(ext_n + 1));
+        SlabArgs F = A; F.fail_base = ext_lo; F.nslots = ext_n;
+        fail_count_kernel<<<(unsigned)((ext_n + 255) / 256), 256, 0, c->st>>>(dsrc, T, F, W.nfail.p); SCS_LAUNCHED(c);
+        F.slot0 = a_first; F.nslots = a_last - a_first + 1;
+        fail_scan_kernel<<<(unsigned)((F.nslots + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
+        A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p; A.fail_base = ext_lo;
     }
     struct Pending { bool live = false; uint64_t bytes[2] = {0, 0}; } pend[2];
     auto drain = [&](int b) -> int {
@@ -590,8 +613,8 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     const bool trace = getenv("SCS_TRACE") != nullptr, no_d2h = getenv("SCS_NO_D2H") != nullptr;
     auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double tr0 = now_ms();
-    for (uint64_t s0 = 0; s0 < nslots; s0 += batch, bi ^= 1) {
-        const uint64_t m = std::min(batch, nslots - s0);
+    for (uint64_t s0 = slot_lo; s0 < slot_hi; s0 += batch, bi ^= 1) {
+        const uint64_t m = std::min(batch, slot_hi - s0);
         const double ta = now_ms();
         if (int rc = drain(bi)) return rc;   // buffer bi is free again once its previous copy has been consumed
         const double tb = now_ms();

@@ -30,20 +30,22 @@ def make_collectives(dist, device="cuda"):
 
 
 def make_device_allreduce(dist, device):
-    """Return f(ptr, n): in-place NCCL sum of n float64 in device memory at `ptr` (zero-copy view through
-    __cuda_array_interface__), finished when it returns."""
+    """Return (f64, i64): f(ptr, n) = in-place NCCL sum of n 8-byte elements in device memory at `ptr` (zero-copy view
+    through __cuda_array_interface__), finished when it returns."""
     import torch
 
     class _View:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+        def __init__(self, ptr, n, typestr):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
-    def ar(ptr: int, n: int):
-        t = torch.as_tensor(_View(ptr, n), device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream(t.device).synchronize()
+    def make(typestr):
+        def ar(ptr: int, n: int):
+            t = torch.as_tensor(_View(ptr, n, typestr), device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream(t.device).synchronize()
+        return ar
 
-    return ar
+    return make("<f8"), make("<i8")
 
 
 class ThreadCollectives:
@@ -69,3 +71,21 @@ class ThreadCollectives:
 
     def pair(self):
         return self._sum, self._sum
+
+    def device_pair(self, device="cuda:0"):
+        """Device-memory hooks for the in-process test: staged through the host sums above."""
+        import torch
+
+        class _View:
+            def __init__(self, ptr, n, typestr):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+        def make(typestr):
+            def ar(ptr, n):
+                t = torch.as_tensor(_View(ptr, n, typestr), device=device)
+                h = t.cpu().numpy().copy()
+                self._sum(h)
+                t.copy_(torch.from_numpy(h))
+                torch.cuda.synchronize()
+            return ar
+        return make("<f8"), make("<i8")

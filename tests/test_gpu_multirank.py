@@ -54,3 +54,41 @@ def test_two_ranks_equal_one_rank(tmp_path, layout, gamma, isize):
     for f in range(2 if layout == "PE" else 1):
         assert _records(out[0][0][f] + out[1][0][f]) == _records(one[f]), f"file {f}: shards differ from the single-rank output"
     assert len(one[0]) > 0
+
+
+@pytest.mark.parametrize("layout,isize,weights", [("PE", 260, (1.0, 1.0)), ("PE", 1200, (1.0, 2.5)), ("SE", 260, (3.0, 1.0))])
+def test_balanced_shards_concatenate_to_the_single_rank_files(tmp_path, layout, isize, weights):
+    """balance=1: genome and amplicon table are replicated (device all-reduce hooks), the cell's read slots are cut by shard
+    weight; rank-ordered concatenation of the shards must be byte-identical to the single-rank output."""
+    from scssim_b200 import api
+    from scssim_b200.dist import ThreadCollectives
+    prof = H.profile_path("Illumina_HiSeq2500")
+    genome = H.write_genome_with_n(os.path.join(str(tmp_path), "n.fa"), 200_000, 19)   # 2 haplotypes with N runs
+    kw = dict(gamma=3e-10, coverage=5.0, isize=isize, layout=layout, seed=4321)
+    with api.GenReads(**kw) as g:
+        g.load_profile(prof).set_genome(genome).create_frags().amplify()
+        one = g.yield_reads_bytes()
+    world = 2
+    coll = ThreadCollectives(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            with api.GenReads(rank=rank, world=world, balance=True, **kw) as g:
+                g.set_collectives(*coll.pair())
+                g.set_device_collective(*coll.device_pair())
+                g.set_shard_weight(weights[rank])
+                g.load_profile(prof).set_genome(genome[rank:rank + 1]).create_frags().amplify()
+                out[rank] = (g.yield_reads_bytes(), g.stats())
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            coll.bar.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for f in range(2 if layout == "PE" else 1):
+        assert out[0][0][f] + out[1][0][f] == one[f], f"file {f}"
+    share = out[0][1]["records"] / (out[0][1]["records"] + out[1][1]["records"])
+    assert abs(share - weights[0] / sum(weights)) < 0.02
