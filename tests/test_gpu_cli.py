@@ -35,7 +35,7 @@ def test_cli_missing_profile_exits_like_reference(tmp_path):
 
 
 def test_cli_two_gpu_workers_write_the_same_records(tmp_path):
-    """--gpus 2 (both workers on this GPU via the test hook): the concatenated shards hold exactly the records of --gpus 1."""
+    """--gpus 2 (both workers on this GPU via the test hook): the concatenated shards are byte-identical to --gpus 1."""
     tmp = str(tmp_path)
     fa = os.path.join(tmp, "cell.fa")
     H.write_genome(fa, 2, 120_000, seed=33)          # 4 sequences -> 2 per worker
@@ -49,11 +49,8 @@ def test_cli_two_gpu_workers_write_the_same_records(tmp_path):
         outs[n] = [H.read_bytes(os.path.join(tmp, f"g{n}_{k}.fq")) for k in (1, 2)]
         assert not os.path.exists(os.path.join(tmp, f"g{n}.rank0_1.fq"))
 
-    def recs(b):
-        ls = b.split(b"\n")[:-1]
-        return sorted(b"\n".join(ls[i:i + 4]) for i in range(0, len(ls), 4))
-    for k in range(2):
-        assert len(outs[1][k]) > 0 and recs(outs[1][k]) == recs(outs[2][k])
+    for k in range(2):   # the workers write contiguous ranges of the cell's read slots: identical files
+        assert len(outs[1][k]) > 0 and outs[1][k] == outs[2][k]
 
 
 def test_cli_more_workers_than_sequences(tmp_path):
