@@ -119,6 +119,54 @@ typedef struct scs_stats {
 } scs_stats;
 int scs_get_stats(const scs_ctx* ctx, scs_stats* out);
 
+/* ---- simuvars -------------------------------------------------------------
+ * The `scssim simuvars` subcommand: main's `genome.loadData(); genome.saveSequence();` (src/scssim.cpp:33-38), i.e.
+ * Genome::loadAbers / loadSNPs / loadRefSeq (lib/genome/Genome.cpp:35-198, lib/snp/snp.cpp:147-203) and
+ * Genome::saveSequence / generateSegment (Genome.cpp:329-691). Flags of parseArgs_simuVars (src/scssim.cpp:109-172):
+ * -r ref FASTA, -s SNP file (may be NULL/empty), -v variation file (may be NULL/empty), -o output FASTA.
+ * The host turns the variant files into an edit plan (piece table); CUDA kernels materialise the haplotypes.
+ * Output is byte-identical to the reference's, which is deterministic: it draws from libc rand() without seeding it. */
+typedef struct scs_simuvars_params {
+    int32_t ploidy;       /* Config.cpp:35: 2 */
+    uint32_t libc_seed;   /* state of libc rand(): 1 = never seeded, what the reference runs with */
+    int32_t line_width;   /* bases per FASTA line, Genome.cpp:371: 100 */
+    int32_t reserved;
+} scs_simuvars_params;
+void scs_simuvars_default_params(scs_simuvars_params* p);
+/* Writes the simulated cell as FASTA (`>chr_k_len` records, Genome.cpp:365-383). */
+int scs_simuvars(scs_ctx* ctx, const scs_simuvars_params* p, const char* ref_fasta, const char* snp_file, const char* var_file, const char* out_fasta);
+/* Same, the bytes of the output file handed to `sink` in file order (file = 0) from pinned host memory. */
+int scs_simuvars_sink(scs_ctx* ctx, const scs_simuvars_params* p, const char* ref_fasta, const char* snp_file, const char* var_file, scs_sink_fn sink, void* user);
+/* Same cell, but it never leaves the device: the haplotypes are packed straight into this context's genome, as if the
+ * output FASTA had been written and then read by scs_load_genome (world > 1: this rank keeps its share of the haplotypes). */
+int scs_simuvars_to_genome(scs_ctx* ctx, const scs_simuvars_params* p, const char* ref_fasta, const char* snp_file, const char* var_file);
+typedef struct scs_simuvars_stats {
+    uint64_t n_chroms, n_haps, n_segments, n_pieces, n_subs;
+    uint64_t n_cnv, n_snv, n_ins, n_del, n_snp;             /* what the reference reports while loading */
+    uint64_t ref_bases, out_bases, out_bytes, h2d_bytes;
+    uint64_t normalize_bytes, materialize_bytes;            /* algorithmic HBM bytes of the two kernels */
+    uint64_t launches;
+    double ms_read, ms_plan, ms_device, ms_kernels, ms_total;   /* host clock, except ms_kernels (CUDA events) */
+} scs_simuvars_stats;
+int scs_simuvars_get_stats(const scs_ctx* ctx, scs_simuvars_stats* out);
+/* Warnings the reference prints while loading (malformed SNP lines); empty string if none. */
+const char* scs_simuvars_warnings(const scs_ctx* ctx);
+
+/* Host-only test hooks (no GPU): the edit plan itself. */
+typedef struct scs_svplan scs_svplan;
+/* chrom_names/chrom_lens describe the reference (names already stripped of "chr"); returns NULL and fills err on failure. */
+scs_svplan* scs_svplan_create(int n_chroms, const char* const* chrom_names, const uint64_t* chrom_lens, const char* snp_file, const char* var_file,
+                              int ploidy, uint32_t libc_seed, char* err, size_t errcap);
+void scs_svplan_destroy(scs_svplan* plan);
+enum scs_svplan_dump { SCS_SVP_HAPS = 0,      /* u64 x7 per haplotype: chrom, hap, length, piece_lo, piece_hi, sub_lo, sub_hi */
+                       SCS_SVP_PIECES = 1,    /* u64 x3 per piece: out offset, source (bit 63: literal pool), length */
+                       SCS_SVP_SUBS = 2,      /* u64 x2 per substitution: out offset, base */
+                       SCS_SVP_LITERALS = 3,  /* bytes */
+                       SCS_SVP_NAMES = 4      /* record names, '\n' separated */ };
+int64_t scs_svplan_dump(const scs_svplan* plan, int what, void* buf, uint64_t cap);
+/* The first n values of libc rand() after srand(seed), as reproduced by the library. */
+int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out);
+
 /* ---- replay ("recorded draws", BASELINE north_star correctness part 1) -------------------------
  * Tapes are the u32 logs of the patched reference run with -t 1; marks give, per entity, the tape
  * position of its first "real"-engine and "int"-engine draw (written by the CPU oracle). All

@@ -14,6 +14,7 @@
 #include <string>
 
 #include "genreads.h"
+#include "simuvars.h"
 
 using namespace orc;
 
@@ -30,8 +31,34 @@ static void dump_str(const std::string& path, const std::string& s) {
     fclose(f);
 }
 
+/*   scs_oracle simuvars -r <ref.fa> [-s <snp file>] [-v <variation file>] -o <out.fa> [--seed <libc seed, default 1>] */
+static int simuvars_main(int argc, char** argv) {
+    SimuVars sv; std::string ref, snp, var, out;
+    for (int i = 2; i < argc; i++) {
+        std::string a = argv[i];
+        auto val = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(1); } return argv[++i]; };
+        if (a == "-r" || a == "--ref") ref = val();
+        else if (a == "-s" || a == "--snp") snp = val();
+        else if (a == "-v" || a == "--var") var = val();
+        else if (a == "-o" || a == "--output") out = val();
+        else if (a == "--seed") sv.seed = (unsigned)strtoul(val(), NULL, 0);
+        else if (a == "--ploidy") sv.ploidy = atoi(val());
+        else { fprintf(stderr, "oracle: unknown option %s\n", a.c_str()); return 1; }
+    }
+    if (ref.empty() || out.empty()) { fprintf(stderr, "oracle: missing arguments\n"); return 1; }
+    auto t0 = std::chrono::steady_clock::now();
+    std::string text;
+    if (!sv.load_vars(var) || !sv.load_snps(snp) || !sv.load_fasta(ref) || !sv.run(text)) { fprintf(stderr, "oracle: %s\n", sv.err.c_str()); return 3; }
+    auto t1 = std::chrono::steady_clock::now();
+    dump_str(out, text);
+    fprintf(stderr, "{\"cnv\": %ld, \"snv\": %ld, \"ins\": %ld, \"del\": %ld, \"snp\": %ld, \"bytes\": %zu, \"t_run\": %.4f}\n", sv.nCnv, sv.nSnv, sv.nIns,
+            sv.nDel, sv.nSnp, text.size(), std::chrono::duration<double>(t1 - t0).count());
+    return 0;
+}
+
 extern "C" int orc_main(int argc, char** argv) {
-    if (argc < 2 || strcmp(argv[1], "genreads") != 0) { fprintf(stderr, "usage: scs_oracle genreads ...\n"); return 1; }
+    if (argc >= 2 && strcmp(argv[1], "simuvars") == 0) return simuvars_main(argc, argv);
+    if (argc < 2 || strcmp(argv[1], "genreads") != 0) { fprintf(stderr, "usage: scs_oracle genreads|simuvars ...\n"); return 1; }
     Sim sim; std::string fa, model, out, tape, dump; uint64_t seed = 0; bool haveSeed = false, noFastq = false;
     for (int i = 2; i < argc; i++) {
         std::string a = argv[i];

@@ -54,6 +54,20 @@ class Stats(C.Structure):
         return d
 
 
+class SimuVarsParams(C.Structure):
+    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SimuVarsStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_chroms", "n_haps", "n_segments", "n_pieces", "n_subs", "n_cnv", "n_snv", "n_ins", "n_del",
+                                          "n_snp", "ref_bases", "out_bases", "out_bytes", "h2d_bytes", "normalize_bytes",
+                                          "materialize_bytes", "launches")] + \
+               [(n, C.c_double) for n in ("ms_read", "ms_plan", "ms_device", "ms_kernels", "ms_total")]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 class Replay(C.Structure):
     _fields_ = [("wreal", C.c_void_p), ("n_wreal", C.c_uint64), ("wint", C.c_void_p), ("n_wint", C.c_uint64),
                 ("mrand", C.c_void_p), ("n_mrand", C.c_uint64), ("mreal", C.c_void_p), ("n_mreal", C.c_uint64),
@@ -71,7 +85,9 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_set_shard_weight", "scs_create_frags", "scs_amplify",
            "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
-           "scs_version"]
+           "scs_version",
+           "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
+           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand"]
 
 _lib = None
 
@@ -111,6 +127,22 @@ def lib():
         L.scs_profile_thresholds.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         L.scs_shard_range.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.scs_shard_range.restype = None
+        L.scs_simuvars_default_params.argtypes = [C.POINTER(SimuVarsParams)]
+        L.scs_simuvars_default_params.restype = None
+        L.scs_simuvars.argtypes = [C.c_void_p, C.POINTER(SimuVarsParams), C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.scs_simuvars_sink.argtypes = [C.c_void_p, C.POINTER(SimuVarsParams), C.c_char_p, C.c_char_p, C.c_char_p, SINK_FN, C.c_void_p]
+        L.scs_simuvars_to_genome.argtypes = [C.c_void_p, C.POINTER(SimuVarsParams), C.c_char_p, C.c_char_p, C.c_char_p]
+        L.scs_simuvars_get_stats.argtypes = [C.c_void_p, C.POINTER(SimuVarsStats)]
+        L.scs_simuvars_warnings.argtypes = [C.c_void_p]
+        L.scs_simuvars_warnings.restype = C.c_char_p
+        L.scs_svplan_create.restype = C.c_void_p
+        L.scs_svplan_create.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_char_p, C.c_char_p, C.c_int, C.c_uint32,
+                                        C.c_char_p, C.c_size_t]
+        L.scs_svplan_destroy.argtypes = [C.c_void_p]
+        L.scs_svplan_destroy.restype = None
+        L.scs_svplan_dump.restype = C.c_int64
+        L.scs_svplan_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.scs_test_libc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -294,6 +326,47 @@ class GenReads:
         self._ck(lib().scs_yield_reads_sink(self._h, cb, None))
         return pos
 
+    # --- simuvars (the reference's other producer subcommand) -----------------------
+    def _sv_params(self, ploidy, libc_seed, line_width):
+        p = SimuVarsParams()
+        lib().scs_simuvars_default_params(C.byref(p))
+        p.ploidy, p.libc_seed, p.line_width = ploidy, libc_seed, line_width
+        return p
+
+    def simuvars(self, ref: str, snp: str | None, var: str | None, out: str, ploidy: int = 2, libc_seed: int = 1, line_width: int = 100):
+        """`scssim simuvars -r ref -s snp -v var -o out` (genome.loadData(); genome.saveSequence())."""
+        p = self._sv_params(ploidy, libc_seed, line_width)
+        self._ck(lib().scs_simuvars(self._h, C.byref(p), ref.encode(), (snp or "").encode(), (var or "").encode(), out.encode()))
+        return self
+
+    def simuvars_bytes(self, ref: str, snp: str | None, var: str | None, ploidy: int = 2, libc_seed: int = 1, line_width: int = 100,
+                       discard: bool = False):
+        """The output FASTA as bytes (tests), or only its length when discard=True (bench: bytes land in pinned memory)."""
+        parts, total = [], [0]
+
+        def sink(_u, _f, data, n):
+            total[0] += n
+            if not discard:
+                parts.append(C.string_at(data, n))
+            return 0
+        cb = SINK_FN(sink)
+        p = self._sv_params(ploidy, libc_seed, line_width)
+        self._ck(lib().scs_simuvars_sink(self._h, C.byref(p), ref.encode(), (snp or "").encode(), (var or "").encode(), cb, None))
+        return total[0] if discard else b"".join(parts)
+
+    def simuvars_to_genome(self, ref: str, snp: str | None, var: str | None, ploidy: int = 2, libc_seed: int = 1):
+        """simuvars whose output stays on the device as this context's packed genome (no FASTA round trip)."""
+        p = self._sv_params(ploidy, libc_seed, 100)
+        self._ck(lib().scs_simuvars_to_genome(self._h, C.byref(p), ref.encode(), (snp or "").encode(), (var or "").encode()))
+        return self
+
+    def simuvars_stats(self) -> dict:
+        s = SimuVarsStats()
+        self._ck(lib().scs_simuvars_get_stats(self._h, C.byref(s)))
+        d = s.as_dict()
+        d["warnings"] = lib().scs_simuvars_warnings(self._h).decode()
+        return d
+
     def stats(self) -> dict:
         s = Stats()
         self._ck(lib().scs_get_stats(self._h, C.byref(s)))
@@ -349,3 +422,62 @@ class GenReads:
         eff = C.c_int()
         n = self._ck(lib().scs_profile_thresholds(self._h, which, idx, row, out.ctypes.data, 4096, C.byref(eff)))
         return out[:n].copy(), eff.value
+
+
+# --- simuvars edit plan, host only (test hook) ---------------------------------------------------------
+SVP_HAPS, SVP_PIECES, SVP_SUBS, SVP_LITERALS, SVP_NAMES = range(5)
+SV_LITERAL = 1 << 63
+
+
+class SimuVarsPlan:
+    """The edit plan `scs_simuvars*` hands to the GPU, built on the host: per haplotype a list of copy runs
+    (out offset, source, length) over the chromosome / the pool of inserted sequences and a list of point substitutions."""
+
+    def __init__(self, chroms, snp: str | None, var: str | None, ploidy: int = 2, libc_seed: int = 1):
+        """chroms: list of (name without "chr", length)."""
+        n = len(chroms)
+        names = (C.c_char_p * n)(*[nm.encode() for nm, _ in chroms])
+        lens = (C.c_uint64 * n)(*[int(l) for _, l in chroms])
+        err = C.create_string_buffer(1024)
+        self._h = lib().scs_svplan_create(n, names, lens, (snp or "").encode(), (var or "").encode(), ploidy, libc_seed, err, 1024)
+        if not self._h:
+            raise ScsError(SCS_E_IO, err.value.decode())
+
+    def _dump(self, what):
+        n = lib().scs_svplan_dump(self._h, what, None, 0)
+        buf = np.zeros(max(int(n), 1), dtype=np.uint8)
+        lib().scs_svplan_dump(self._h, what, buf.ctypes.data, buf.nbytes)
+        return buf[:n]
+
+    @property
+    def haps(self):
+        return self._dump(SVP_HAPS).view(np.uint64).reshape(-1, 7)
+
+    @property
+    def pieces(self):
+        return self._dump(SVP_PIECES).view(np.uint64).reshape(-1, 3)
+
+    @property
+    def subs(self):
+        return self._dump(SVP_SUBS).view(np.uint64).reshape(-1, 2)
+
+    @property
+    def literals(self):
+        return self._dump(SVP_LITERALS)
+
+    @property
+    def names(self):
+        return self._dump(SVP_NAMES).tobytes().decode().split("\n")[:-1]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().scs_svplan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+def libc_rand(seed: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.uint32)
+    lib().scs_test_libc_rand(seed, n, out.ctypes.data)
+    return out

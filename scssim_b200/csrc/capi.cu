@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "ctx.h"
+#include "simuvars_plan.h"
 
 using namespace scs;
 
@@ -134,6 +135,76 @@ int scs_yield_reads(scs_ctx* c, const char* prefix) {   // Malbac.cpp:426-435: <
     int rc = scs_yield_reads_sink(c, file_sink, &s);
     fclose(s.f[0]); if (s.f[1]) fclose(s.f[1]);
     return rc;
+}
+
+// ---- simuvars
+void scs_simuvars_default_params(scs_simuvars_params* p) { if (p) { p->ploidy = 2; p->libc_seed = 1; p->line_width = 100; p->reserved = 0; } }
+
+static int simuvars_entry(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var, scs_sink_fn sink, void* user, bool to_genome) {
+    if (!c) return SCS_E_ARG;
+    if (!ref || !*ref) return c->fail(SCS_E_ARG, "Use --ref to specify the reference file (fasta).");   // src/scssim.cpp:146-150
+    scs_simuvars_params sp; scs_simuvars_default_params(&sp); if (p) sp = *p;
+    if (sp.ploidy < 1) return c->fail(SCS_E_ARG, "simuvars: ploidy must be positive");
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: simuvars has no CPU fallback");
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
+    return simuvars_run(c, sp, ref, snp, var, sink, user, to_genome);
+}
+int scs_simuvars_sink(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var, scs_sink_fn sink, void* user) {
+    if (!sink) return SCS_E_ARG;
+    return simuvars_entry(c, p, ref, snp, var, sink, user, false);
+}
+int scs_simuvars_to_genome(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var) {
+    return simuvars_entry(c, p, ref, snp, var, nullptr, nullptr, true);
+}
+static int one_file_sink(void* user, int, const char* data, size_t n) { return fwrite(data, 1, n, (FILE*)user) == n ? 0 : 1; }
+int scs_simuvars(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var, const char* out) {
+    if (!c) return SCS_E_ARG;
+    if (!out || !*out) return c->fail(SCS_E_ARG, "Use --output to specify the output file.");   // src/scssim.cpp:162-166
+    FILE* f = fopen(out, "wb");
+    if (!f) return c->fail(SCS_E_IO, std::string("can not open file ") + out);   // Genome.cpp:337-340
+    setvbuf(f, nullptr, _IOFBF, 8 << 20);
+    int rc = simuvars_entry(c, p, ref, snp, var, one_file_sink, f, false);
+    if (fclose(f) != 0 && rc == SCS_OK) rc = c->fail(SCS_E_IO, std::string("can not write file ") + out);
+    return rc;
+}
+int scs_simuvars_get_stats(const scs_ctx* c, scs_simuvars_stats* out) { if (!c || !out) return SCS_E_ARG; *out = c->sv_stats; return SCS_OK; }
+const char* scs_simuvars_warnings(const scs_ctx* c) { return c ? c->sv_warnings.c_str() : ""; }
+
+struct scs_svplan { sv::Plan plan; };
+scs_svplan* scs_svplan_create(int n, const char* const* names, const uint64_t* lens, const char* snp, const char* var, int ploidy, uint32_t seed, char* err, size_t errcap) {
+    std::vector<sv::ChromIn> chroms;
+    for (int i = 0; i < n; i++) chroms.push_back({names[i], lens[i]});
+    scs_svplan* h = new scs_svplan();
+    if (!sv::build_plan(h->plan, chroms, snp, var, ploidy, seed)) {
+        if (err && errcap) { strncpy(err, h->plan.err.c_str(), errcap - 1); err[errcap - 1] = 0; }
+        delete h; return nullptr;
+    }
+    return h;
+}
+void scs_svplan_destroy(scs_svplan* h) { delete h; }
+int64_t scs_svplan_dump(const scs_svplan* h, int what, void* buf, uint64_t cap) {
+    if (!h) return SCS_E_ARG;
+    const sv::Plan& P = h->plan;
+    std::vector<uint64_t> v; std::string s; const void* src = nullptr; uint64_t need = 0;
+    switch (what) {
+        case SCS_SVP_HAPS: for (auto& x : P.haps) { v.insert(v.end(), {(uint64_t)x.chrom, (uint64_t)x.hap, x.len, x.piece_lo, x.piece_hi, x.sub_lo, x.sub_hi}); } break;
+        case SCS_SVP_PIECES: for (auto& x : P.pieces) { v.insert(v.end(), {x.out, x.src, (uint64_t)x.len}); } break;
+        case SCS_SVP_SUBS: for (auto& x : P.subs) { v.insert(v.end(), {x.out, (uint64_t)x.ch}); } break;
+        case SCS_SVP_LITERALS: s = P.literals; break;
+        case SCS_SVP_NAMES: for (auto& x : P.haps) { s += x.name; s += '\n'; } break;
+        default: return SCS_E_ARG;
+    }
+    if (what == SCS_SVP_LITERALS || what == SCS_SVP_NAMES) { src = s.data(); need = s.size(); } else { src = v.data(); need = v.size() * 8; }
+    if (!buf) return (int64_t)need;
+    if (cap < need) return SCS_E_ARG;
+    if (need) memcpy(buf, src, need);
+    return (int64_t)need;
+}
+int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out) {
+    if (!out || n < 0) return SCS_E_ARG;
+    sv::LibcRand r(seed);
+    for (int i = 0; i < n; i++) out[i] = r.next();
+    return SCS_OK;
 }
 
 int scs_get_stats(const scs_ctx* c, scs_stats* out) {

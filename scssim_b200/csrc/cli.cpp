@@ -1,5 +1,5 @@
-// `scssim genreads` drop-in: same flags, defaults, validation messages, stderr progress lines and
-// output files as the reference's CLI (/root/reference/src/scssim.cpp:23-76,285-404,464-485), driving
+// `scssim genreads` and `scssim simuvars` drop-in: same flags, defaults, validation messages, stderr progress lines and
+// output files as the reference's CLI (/root/reference/src/scssim.cpp:23-76,109-172,285-404,421-485), driving
 // the CUDA path through the C ABI. `-t` is accepted (the reference's worker-thread count) and ignored:
 // the work runs on the GPU. Extra long-only flags: --seed <u64>, --device <n>.
 #include <getopt.h>
@@ -26,7 +26,71 @@ static void usage(const char* app) {
          << "    -h, --help                      give this information" << endl
          << "    -v, --version <string>          print software version" << endl << endl
          << "Available subcmds:" << endl
+         << "    simuvars          simulate the genome sequence of single cells" << endl
          << "    genreads          simulate sequencing reads of single cell" << endl << endl;
+}
+
+static void usage_simuVars(const char* app) {
+    cerr << "Usage: scssim " << app << " [options]" << endl << endl
+         << "Options:" << endl
+         << "    -h, --help                      give this information" << endl
+         << "    -r, --ref <string>              reference file (.fasta)" << endl
+         << "    -s, --snp <string>              SNP file containing the SNPs to be simulated [Default:null]" << endl
+         << "    -v, --var <string>              variation file containing the genomic variations to be simulated [Default:null]" << endl
+         << "    -o, --output <string>           output file (.fasta) to save generated sequences" << endl
+         << "        --device <int>              CUDA device ordinal [Default:0]" << endl << endl
+         << "Example:" << endl
+         << "    scssim " << app << " -r /path/to/hg19.fa -s /path/to/hg19.snp138.1based.txt -v /path/to/variation.txt -o /path/to/results.fa" << endl << endl;
+}
+
+static int die(scs_ctx* c, int rc);
+
+// `scssim simuvars`: parseArgs_simuVars + main's simuvars branch (src/scssim.cpp:33-38,109-172)
+static int main_simuvars(int argc, char* argv[], time_t start_t) {
+    string refFile, snpFile, varFile, outFile; int device = 0;
+    struct option long_options[] = {{"help", no_argument, 0, 'h'}, {"ref", required_argument, 0, 'r'}, {"snp", required_argument, 0, 's'},
+                                    {"var", required_argument, 0, 'v'}, {"output", required_argument, 0, 'o'}, {"device", required_argument, 0, 1001},
+                                    {0, 0, 0, 0}};
+    int c;
+    while ((c = getopt_long(argc, argv, "hr:s:v:o:", long_options, NULL)) != -1) {
+        switch (c) {
+            case 'h': usage_simuVars(argv[0]); return 0;
+            case 'r': refFile = optarg; break;
+            case 's': snpFile = optarg; break;
+            case 'v': varFile = optarg; break;
+            case 'o': outFile = optarg; break;
+            case 1001: device = atoi(optarg); break;
+            default: usage_simuVars(argv[0]); return 1;
+        }
+    }
+    if (refFile.empty()) { cerr << "Use --ref to specify the reference file (fasta)." << endl; usage_simuVars(argv[0]); return 1; }
+    if (snpFile.empty()) cerr << "Warning: SNP file not specified!" << endl << "No SNPs will be inserted into the genome." << endl;
+    if (varFile.empty()) cerr << "Warning: variation file not specified!" << endl << "No variations will be inserted into the genome." << endl;
+    if (outFile.empty()) { cerr << "Use --output to specify the output file." << endl; usage_simuVars(argv[0]); return 1; }
+    scs_params P; scs_default_params(&P); P.device = device;
+    scs_ctx* ctx = nullptr;
+    int rc = scs_create(&P, &ctx);
+    if (rc) return die(nullptr, rc);
+    string fa = refFile;   // .gz input: gunzipped beside the input (lib/genome/Genome.cpp:183-187)
+    if (fa.size() > 3 && fa.substr(fa.size() - 3) == ".gz") {
+        string cmd = "gzip -cd " + fa + " > " + fa.substr(0, fa.size() - 3);
+        if (system(cmd.c_str()) != 0) { cerr << "could not open " << fa << endl; scs_destroy(ctx); return 1; }
+        fa = fa.substr(0, fa.size() - 3);
+    }
+    scs_simuvars_params sp; scs_simuvars_default_params(&sp);
+    rc = scs_simuvars(ctx, &sp, fa.c_str(), snpFile.c_str(), varFile.c_str(), outFile.c_str());
+    scs_simuvars_stats st; scs_simuvars_get_stats(ctx, &st);
+    cerr << scs_simuvars_warnings(ctx);
+    if (rc) return die(ctx, rc);
+    // what Genome::loadAbers / loadSNPs / loadRefSeq report (Genome.cpp:160-164,173,197)
+    if (!varFile.empty()) cerr << "\nDetails of the aberrations loaded from file " << varFile << " are as follows:" << endl << "CNV: " << st.n_cnv << endl
+                               << "SNV: " << st.n_snv << endl << "Insert: " << st.n_ins << endl << "Deletion: " << st.n_del << endl;
+    if (!snpFile.empty()) cerr << "\n" << st.n_snp << " SNPs to simulate were loaded from file " << snpFile << endl;
+    cerr << "\nReference sequence was loaded from file " << refFile << endl;
+    scs_destroy(ctx);
+    long used = (long)(time(NULL) - start_t);
+    cerr << "\nElapsed time: " << used / 60 << " minutes and " << used % 60 << " seconds!\n" << endl;
+    return 0;
 }
 
 static void usage_genReads(const char* app) {
@@ -96,8 +160,9 @@ int main(int argc, char* argv[]) {
     string subcmd = argv[1];
     if (subcmd == "-h" || subcmd == "--help") { usage(argv[0]); return 0; }
     if (subcmd == "-v" || subcmd == "--version") { cerr << "SCSsim version 1.0" << endl; return 0; }
-    if (subcmd == "simuvars" || subcmd == "learn") {
-        cerr << "Error: subcommand \"" << subcmd << "\" is not part of the B200 genreads build; use the reference scssim for it." << endl;
+    if (subcmd == "simuvars") return main_simuvars(argc - 1, argv + 1, start_t);
+    if (subcmd == "learn") {
+        cerr << "Error: subcommand \"" << subcmd << "\" is not part of the B200 build; use the reference scssim for it." << endl;
         return 1;
     }
     if (subcmd != "genreads") { cerr << "Error: unrecognized subcommand \"" << subcmd << "\"." << endl; usage(argv[0]); return 0; }

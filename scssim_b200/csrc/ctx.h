@@ -153,6 +153,7 @@ struct scs_ctx {
     scs::DevBuf<uint64_t> g_words, g_desc, g_errref, g_slot_base; scs::DevBuf<uint32_t> g_nmask, g_errs;
     bool global_view = false; uint64_t g_n_amp = 0, g_slot_lo = 0, g_slot_hi = 0, g_bases = 0; int g_has_n = 0;
     scs_stats stats{};
+    scs_simuvars_stats sv_stats{}; std::string sv_warnings;
 
     // FASTQ slabs
     scs::DevBuf<char> slab_dev[2][2];   // [buffer][file]
@@ -189,6 +190,12 @@ namespace scs {
 // stage entry points (one .cu each)
 int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens);
 int genome_from_fasta(scs_ctx* c, const char* path);
+// one sequence of the cell: contiguous ASCII bases (blen == 0; in device memory if dev) or FASTA text with a fixed line geometry
+struct SeqSrc { const char* p; uint64_t len; uint32_t blen, llen; bool dev; };
+int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src);
+// [lo, hi) of the sequences this rank keeps (midpoint rule, see genome_from_fasta)
+void shard_by_midpoint(const std::vector<uint64_t>& lens, int rank, int world, size_t* lo, size_t* hi);
+int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, const char* snp, const char* var, scs_sink_fn sink, void* user, bool to_genome);
 int upload_profile(scs_ctx* c);
 int create_frags(scs_ctx* c);
 int amplify(scs_ctx* c);

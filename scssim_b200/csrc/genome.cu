@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "ctx.h"
+#include "fasta_host.h"
 
 namespace scs {
 
@@ -176,16 +177,14 @@ static std::string ref_seq_name(const std::string& header) {   // lib/fastahack/
 }
 
 // one sequence of the cell on the host: contiguous ASCII bases (blen == 0) or FASTA text with a fixed line geometry
-struct SeqSrc { const char* p; uint64_t len; uint32_t blen, llen; };
-static int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src);
 
 int genome_from_host(scs_ctx* c, int n, const char* const* names, const char* const* seqs, const uint64_t* lens) {
     std::vector<SeqSrc> src((size_t)std::max(n, 0));
-    for (int i = 0; i < n; i++) src[i] = {seqs[i], lens[i], 0, 0};
+    for (int i = 0; i < n; i++) src[i] = {seqs[i], lens[i], 0, 0, false};
     return genome_from_sources(c, n, names, src.data());
 }
 
-static int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src) {
+int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSrc* src) {
     std::vector<uint64_t> lens_v((size_t)std::max(n, 0)); for (int i = 0; i < n; i++) lens_v[i] = src[i].len;
     const uint64_t* lens = lens_v.data();
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device: the genreads path has no CPU fallback");
@@ -213,7 +212,11 @@ static int genome_from_sources(scs_ctx* c, int n, const char* const* names, cons
     DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(chunk + (chunk >> 4) + 4096));
     cudaEventRecord(e0, c->st);
     for (int i = 0; i < n; i++) {
-        if (src[i].blen == 0) {
+        if (src[i].dev) {   // contiguous bases already in device memory (simuvars -> genome without a text round trip)
+            uint64_t nw = (lens[i] + 31) >> 5;
+            if (nw) { pack_genome_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, c->st>>>((const uint8_t*)src[i].p, lens[i], c->genome_words.p + (c->seq_goff[i] >> 5),
+                                                                                        c->genome_nmask.p + (c->seq_goff[i] >> 5), bad.p); SCS_LAUNCHED(c); }
+        } else if (src[i].blen == 0) {
             for (uint64_t off = 0; off < lens[i]; off += chunk) {
                 uint64_t m = std::min(chunk, lens[i] - off);
                 SCS_CUDA(c, cudaMemcpyAsync(stage.p, src[i].p + off, m, cudaMemcpyHostToDevice, c->st));
@@ -252,80 +255,26 @@ static int genome_from_sources(scs_ctx* c, int n, const char* const* names, cons
 }
 
 int genome_from_fasta(scs_ctx* c, const char* path) {
-    FILE* f = fopen(path, "rb");
-    if (!f) return c->fail(SCS_E_IO, std::string("could not open ") + path);
-    fseek(f, 0, SEEK_END); long long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    std::vector<char> raw((size_t)sz + 1);
-    size_t got = sz > 0 ? fread(raw.data(), 1, (size_t)sz, f) : 0;
-    fclose(f);
-    raw[got] = '\n';
     // One pass over the lines builds the .fai index (name, length, offset, bases per line, bytes per line): with a uniform
     // line geometry (what the reference's fastahack reader requires, lib/fastahack/Fasta.cpp:304-334) the text is uploaded
     // as it is and the newlines are skipped by index arithmetic on the device; otherwise the bases are gathered on the host.
-    struct Fai { std::string name; uint64_t len, off; uint32_t blen, llen; bool regular; uint64_t short_lines; };
-    std::vector<std::string> names; std::vector<Fai> fai;
-    size_t pos = 0;
-    while (pos < got) {
-        char* s = &raw[pos];
-        char* e = (char*)memchr(s, '\n', got + 1 - pos);
-        size_t len = (size_t)(e - s);
-        size_t llen = len + 1;
-        if (len > 0 && s[len - 1] == '\r') len--;
-        if (len > 0 && s[0] == '>') {
-            names.push_back(std::string(s + 1, len - 1));
-            std::string full(s + 1, len - 1);
-            fai.push_back({full.substr(0, full.find_first_of(" \t")), 0, (uint64_t)(pos + llen), 0, 0, true, 0});
-        } else if (!fai.empty()) {
-            Fai& a = fai.back();
-            if (len == 0) { if (a.len) a.short_lines++; }          // a blank line is fine only at the very end of a record
-            else {
-                if (a.blen == 0) { a.blen = (uint32_t)len; a.llen = (uint32_t)llen; }
-                if (a.short_lines) a.regular = false;               // bases after a short or blank line
-                if (len != a.blen || llen != a.llen) { if (len > a.blen) a.regular = false; a.short_lines++; }
-                a.len += len;
-            }
-        }
-        pos += llen;
-    }
-    if (fai.empty()) return c->fail(SCS_E_IO, "ERROR: reference sequence cannot be empty!");
-    std::string faiPath = std::string(path) + ".fai";   // side effect of FastaReference::open (Fasta.cpp:243-249)
-    if (FILE* t = fopen(faiPath.c_str(), "rb")) fclose(t);
-    else if (FILE* o = fopen(faiPath.c_str(), "wb")) {
-        for (size_t i = 0; i < fai.size(); i++) fprintf(o, "%s\t%llu\t%llu\t%u\t%u\n", fai[i].name.c_str(), (unsigned long long)fai[i].len, (unsigned long long)fai[i].off, fai[i].blen, fai[i].llen);
-        fclose(o);
-    }
+    std::vector<char> raw; size_t got = 0; std::vector<FaiRec> fai; std::string ferr;
+    if (!fasta_read_and_index(path, raw, got, fai, &ferr)) return c->fail(SCS_E_IO, ferr);
+    fasta_write_fai(path, fai);
+    std::vector<std::string> names; for (auto& r : fai) names.push_back(r.header);
     // irregular records: gather their bases into contiguous host buffers (slow path)
     std::vector<std::vector<char>> gathered(fai.size());
     std::vector<SeqSrc> all(fai.size());
     for (size_t i = 0; i < fai.size(); i++) {
-        if (fai[i].len > 0 && fai[i].len <= fai[i].blen) { all[i] = {&raw[fai[i].off], fai[i].len, 0, 0}; continue; }   // one line: already contiguous
-        if (fai[i].regular && fai[i].len > 0 && fai[i].llen <= (1u << 20)) { all[i] = {&raw[fai[i].off], fai[i].len, fai[i].blen, fai[i].llen}; continue; }
-        std::vector<char>& g = gathered[i]; g.reserve(fai[i].len);
-        size_t q = fai[i].off, end = (i + 1 < fai.size()) ? (size_t)fai[i + 1].off : got;
-        while (q < end && g.size() < fai[i].len) {
-            char* s = &raw[q]; char* e = (char*)memchr(s, '\n', got + 1 - q); size_t len = (size_t)(e - s); q += len + 1;
-            if (len > 0 && s[len - 1] == '\r') len--;
-            if (len > 0 && s[0] == '>') break;
-            g.insert(g.end(), s, s + len);
-        }
-        all[i] = {g.data(), g.size(), 0, 0};
+        if (fai[i].len > 0 && fai[i].len <= fai[i].blen) { all[i] = {&raw[fai[i].off], fai[i].len, 0, 0, false}; continue; }   // one line: already contiguous
+        if (fai[i].regular && fai[i].len > 0 && fai[i].llen <= (1u << 20)) { all[i] = {&raw[fai[i].off], fai[i].len, fai[i].blen, fai[i].llen, false}; continue; }
+        fasta_gather(raw, got, fai, i, gathered[i]);
+        all[i] = {gathered[i].data(), gathered[i].size(), 0, 0, false};
     }
-    struct SeqView { size_t size() const { return n; } uint64_t n; };
-    std::vector<SeqView> seqs(fai.size()); for (size_t i = 0; i < fai.size(); i++) seqs[i].n = all[i].len;
-    // world > 1: this rank keeps a contiguous run of sequences, cut where the cumulative length crosses rank/world of the
-    // total (sequence midpoints decide), so every rank holds about the same number of bases
-    size_t lo = 0, hi = seqs.size();
-    if (c->P.world > 1) {
-        long double total = 0; for (auto& s : seqs) total += s.size();
-        long double acc = 0; lo = hi = seqs.size(); bool started = false;
-        for (size_t i = 0; i < seqs.size(); i++) {
-            long double mid = acc + seqs[i].size() / 2.0L;
-            int owner = std::min(c->P.world - 1, (int)(mid * c->P.world / (total > 0 ? total : 1)));
-            if (owner == c->P.rank) { if (!started) { lo = i; started = true; } hi = i + 1; }
-            acc += seqs[i].size();
-        }
-        if (!started) lo = hi = 0;
-    }
+    // world > 1: this rank keeps a contiguous run of sequences holding about 1/world of the bases
+    std::vector<uint64_t> slens(fai.size()); for (size_t i = 0; i < fai.size(); i++) slens[i] = all[i].len;
+    size_t lo = 0, hi = fai.size();
+    shard_by_midpoint(slens, c->P.rank, c->P.world, &lo, &hi);
     std::vector<const char*> np; std::vector<SeqSrc> sp;
     for (size_t i = lo; i < hi; i++) { np.push_back(names[i].c_str()); sp.push_back(all[i]); }
     if (np.empty()) {   // more ranks than sequences: this rank holds nothing but still takes part in the collectives

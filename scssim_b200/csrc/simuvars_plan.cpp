@@ -1,0 +1,458 @@
+// See simuvars_plan.h. Host-only; no CUDA here.
+#include "simuvars_plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+
+#include "fasta_host.h"
+
+namespace scs {
+namespace sv {
+
+// ------------------------------------------------------------------------------------------ libc rand()
+void LibcRand::reseed(uint32_t seed) {
+    if (seed == 0) seed = 1;
+    r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+        int32_t hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        int32_t w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = w;
+    }
+    f = 3; b = 0;
+    for (int i = 0; i < 310; i++) next();
+}
+uint32_t LibcRand::next() {
+    uint32_t v = (uint32_t)r[f] + (uint32_t)r[b];
+    r[f] = (int32_t)v;
+    if (++f == 31) f = 0;
+    if (++b == 31) b = 0;
+    return v >> 1;
+}
+long LibcRand::integer(long a, long b2) { return (long)(a + (b2 - a) * (next() / 2147483648.0)); }
+
+// ------------------------------------------------------------------------------------------ variant files
+namespace {
+
+struct Cnv { long spos, epos; float cn, mcn; };
+struct PointVar { long pos; uint8_t ch; bool het; };            // SNP (het unused) or SNV
+struct InsVar { long pos; uint64_t lit_off; uint32_t len; bool het; };
+struct DelVar { long pos; int len; bool het; };
+
+// variants of one chromosome in file order + an index sorted by position for range queries
+template <class T> struct VarList {
+    std::vector<T> v; std::vector<uint32_t> ord; bool indexed = false;
+    void index() {
+        ord.resize(v.size()); for (uint32_t i = 0; i < ord.size(); i++) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return v[a].pos < v[b].pos; });
+        indexed = true;
+    }
+    // file-order indices of the variants with s <= pos <= e
+    void in_range(long s, long e, std::vector<uint32_t>& out) {
+        if (!indexed) index();
+        out.clear();
+        auto lo = std::lower_bound(ord.begin(), ord.end(), s, [&](uint32_t a, long x) { return v[a].pos < x; });
+        for (; lo != ord.end() && v[*lo].pos <= e; ++lo) out.push_back(*lo);
+        std::sort(out.begin(), out.end());
+    }
+};
+struct ChromVars { std::vector<Cnv> cnv; VarList<PointVar> snp, snv; VarList<InsVar> ins; VarList<DelVar> del; };
+
+// std::getline-on-stringstream field splitting (lib/split/split.cpp:3-15): no empty field after a trailing delimiter
+std::vector<std::string> split_fields(const std::string& s, char d) {
+    std::vector<std::string> out; size_t p = 0;
+    while (p < s.size()) {
+        size_t q = s.find(d, p);
+        if (q == std::string::npos) { out.push_back(s.substr(p)); break; }
+        out.push_back(s.substr(p, q - p)); p = q + 1;
+    }
+    return out;
+}
+
+bool parse_zygosity(const std::string& t, bool& het) { if (t == "het") { het = true; return true; } if (t == "homo") { het = false; return true; } return false; }
+
+// Genome::loadAbers, Genome.cpp:35-165
+bool load_variations(Plan& P, const char* path, std::map<std::string, ChromVars>& by_chr) {
+    if (!path || !*path) return true;
+    std::ifstream ifs(path);
+    if (!ifs.is_open()) { P.err = std::string("can not open file ") + path; return false; }
+    std::string line; int ln = 0;
+    auto fail = [&](const std::string& head) { P.err = head + "\n" + line; return false; };
+    auto fields_err = [&]() { return fail("ERROR: line " + std::to_string(ln) + " has wrong number of fields in file " + path); };
+    while (std::getline(ifs, line)) {
+        ln++;
+        if (line.empty() || line[0] == '#') continue;
+        std::vector<std::string> f = split_fields(line, '\t');
+        const std::string kind = f.empty() ? std::string() : f[0];
+        if (kind == "c") {
+            if (f.size() != 6) return fields_err();
+            float cn = (float)atof(f[4].c_str()), mcn = (float)atof(f[5].c_str());
+            if (cn < mcn) return fail("ERROR: total copy number should be not lower than major copy number at line " + std::to_string(ln) + " in file " + path);
+            if (cn - mcn > mcn) mcn = cn - mcn;
+            by_chr[strip_chr_prefix(f[1])].cnv.push_back({atol(f[2].c_str()), atol(f[3].c_str()), cn, mcn});
+            P.n_cnv++;
+        } else if (kind == "s") {
+            if (f.size() != 6) return fields_err();
+            if (f[3].empty() || f[4].empty()) return fields_err();   // reference: std::out_of_range from at(0)
+            if (f[3][0] == f[4][0]) return fail("ERROR: the mutated allele should be not same as the reference allele at line " + std::to_string(ln) + " in file " + path);
+            bool het; if (!parse_zygosity(f[5], het)) return fail("ERROR: unrecognized SNV type at line " + std::to_string(ln) + " in file " + path);
+            by_chr[strip_chr_prefix(f[1])].snv.v.push_back({atol(f[2].c_str()), (uint8_t)toupper((unsigned char)f[4][0]), het});
+            P.n_snv++;
+        } else if (kind == "i") {
+            if (f.size() != 5) return fields_err();
+            bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized insert type at line " + std::to_string(ln) + " in file " + path);
+            std::string seq = f[3];
+            for (char& ch : seq) ch = (char)toupper((unsigned char)ch);   // the segment is upper-cased as a whole at the end, Genome.cpp:683-687
+            by_chr[strip_chr_prefix(f[1])].ins.v.push_back({atol(f[2].c_str()), (uint64_t)P.literals.size(), (uint32_t)seq.size(), het});
+            P.literals += seq;
+            P.n_ins++;
+        } else if (kind == "d") {
+            if (f.size() != 5) return fields_err();
+            bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized deletion type at line " + std::to_string(ln) + " in file " + path);
+            by_chr[strip_chr_prefix(f[1])].del.v.push_back({atol(f[2].c_str()), atoi(f[3].c_str()), het});
+            P.n_del++;
+        } else return fail("ERROR: unrecognized aberraton type at line " + std::to_string(ln) + " in file " + path);
+    }
+    return true;
+}
+
+uint8_t snp_complement(uint8_t c) {   // SNP::getComplement, snp.cpp:96-110
+    switch (c) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+        case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+        default: return 'N';
+    }
+}
+
+// SNPOnChr::readSNPs + SNP::SNP, snp.cpp:13-36,147-203: id, chromosome, position, observed "X/Y", strand, reference base
+bool load_snps(Plan& P, const char* path, std::map<std::string, ChromVars>& by_chr) {
+    if (!path || !*path) return true;
+    FILE* fp = fopen(path, "r");
+    if (!fp) { P.err = std::string("can not open SNP file ") + path; return false; }
+    char buf[1000]; long ln = 0;
+    while (fgets(buf, sizeof buf, fp)) {
+        ln++;
+        char* col[8]; int nc = 0; col[nc++] = buf;
+        bool too_many = false;
+        for (char* p = buf; *p; p++) if (*p == '\t') { *p = 0; if (nc < 8) col[nc++] = p + 1; else too_many = true; }
+        const char* slash = (nc == 6 && !too_many) ? strchr(col[3], '/') : nullptr;
+        if (nc != 6 || too_many || !slash || slash == col[3] || slash[1] == 0) {
+            if (P.warnings.size() < 4096) P.warnings += std::string("Warning: malformed snp file ") + path + ", there should be 6 fields @line " + std::to_string(ln) + "\n";
+            continue;
+        }
+        uint8_t first = (uint8_t)col[3][0], second = (uint8_t)slash[1];
+        uint8_t strand = (uint8_t)*col[4], ref = (uint8_t)*col[5];
+        if (strand == '-') ref = snp_complement(ref);
+        uint8_t nuc = (first == ref) ? second : first;
+        if (strand == '-') nuc = snp_complement(nuc);
+        by_chr[strip_chr_prefix(col[1])].snp.v.push_back({(long)atoll(col[2]), (uint8_t)toupper(nuc), false});
+        P.n_snp++;
+    }
+    fclose(fp);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ piece table
+// A std::string stand-in that stores runs instead of characters. insert/erase follow std::string: position > size
+// fails (the reference dies with std::out_of_range there), erase clamps its count to the end of the string.
+struct Run { uint64_t src; uint64_t q; uint32_t len; };   // q: position in the segment's pre-indel string (reference runs only)
+
+class Rope {
+    static constexpr size_t kChunk = 512;
+    std::vector<std::vector<Run>> ch; std::vector<uint64_t> clen; uint64_t total = 0;
+
+    // chunk holding position pos (pos == total -> last chunk), *base = first position of that chunk
+    size_t chunk_of(uint64_t pos, uint64_t* base) const {
+        uint64_t acc = 0; size_t c = 0;
+        for (; c + 1 < ch.size(); c++) { if (pos < acc + clen[c]) break; acc += clen[c]; }
+        *base = acc; return c;
+    }
+    // make sure a run starts at pos; returns (chunk, index) of it (index == size of the last chunk when pos == total)
+    void boundary(uint64_t pos, size_t& ci, size_t& pi) {
+        uint64_t base; ci = chunk_of(pos, &base);
+        std::vector<Run>& v = ch[ci];
+        uint64_t at = base; pi = 0;
+        while (pi < v.size() && at + v[pi].len <= pos) { at += v[pi].len; pi++; }
+        if (pi == v.size() || at == pos) {
+            if (pi == v.size() && ci + 1 < ch.size()) { ci++; pi = 0; }   // boundary at the start of the next chunk
+            return;
+        }
+        const uint32_t k = (uint32_t)(pos - at);
+        Run tail = v[pi]; tail.src += k; tail.q += k; tail.len -= k;
+        v[pi].len = k;
+        v.insert(v.begin() + pi + 1, tail);
+        pi++;
+    }
+    void rebalance(size_t ci) {
+        if (ch[ci].size() <= kChunk) return;
+        const size_t half = ch[ci].size() / 2;
+        std::vector<Run> hi(ch[ci].begin() + half, ch[ci].end());
+        ch[ci].resize(half);
+        uint64_t l = 0; for (const Run& r : hi) l += r.len;
+        clen[ci] -= l;
+        ch.insert(ch.begin() + ci + 1, std::move(hi)); clen.insert(clen.begin() + ci + 1, l);
+    }
+
+  public:
+    uint64_t size() const { return total; }
+    void append(const Run& r) {
+        if (r.len == 0) return;
+        if (ch.empty() || ch.back().size() >= kChunk) { ch.emplace_back(); clen.push_back(0); }
+        ch.back().push_back(r); clen.back() += r.len; total += r.len;
+    }
+    bool insert(uint64_t pos, const Run& r) {
+        if (pos > total) return false;
+        if (r.len == 0) return true;
+        if (ch.empty()) { append(r); return true; }
+        size_t ci, pi; boundary(pos, ci, pi);
+        ch[ci].insert(ch[ci].begin() + pi, r); clen[ci] += r.len; total += r.len;
+        rebalance(ci);
+        return true;
+    }
+    bool erase(uint64_t pos, uint64_t n) {
+        if (pos > total) return false;
+        n = std::min(n, total - pos);
+        if (n == 0) return true;
+        size_t c1, p1, c2, p2;
+        boundary(pos + n, c2, p2); boundary(pos, c1, p1); boundary(pos + n, c2, p2);   // the second split may have moved the first
+        if (c1 == c2) ch[c1].erase(ch[c1].begin() + p1, ch[c1].begin() + p2);
+        else {
+            ch[c1].resize(p1);
+            ch[c2].erase(ch[c2].begin(), ch[c2].begin() + p2);
+            ch.erase(ch.begin() + c1 + 1, ch.begin() + c2); clen.erase(clen.begin() + c1 + 1, clen.begin() + c2);
+        }
+        total -= n;
+        for (size_t c = c1; c < ch.size() && c <= c1 + 1; c++) { uint64_t l = 0; for (const Run& r : ch[c]) l += r.len; clen[c] = l; }
+        for (size_t c = std::min(c1 + 1, ch.size() - 1) + 1; c-- > c1;) if (ch[c].empty() && ch.size() > 1) { ch.erase(ch.begin() + c); clen.erase(clen.begin() + c); }
+        return true;
+    }
+    template <class F> void for_each(F fn) const { for (const auto& v : ch) for (const Run& r : v) fn(r); }
+};
+
+// Fenwick tree over the sorted distinct in-segment positions of the indels: "sum of lengths recorded at positions <= x".
+// std::map::insert keeps the FIRST length recorded at a position (Genome.cpp:573,600,644,675), hence `seen`.
+struct OffsetIndex {
+    const std::vector<int>* keys = nullptr; std::vector<long> bit; std::vector<char> seen;
+    void init(const std::vector<int>* k) { keys = k; bit.assign(k->size() + 1, 0); seen.assign(k->size(), 0); }
+    void record(int pos, int len) {
+        size_t i = (size_t)(std::lower_bound(keys->begin(), keys->end(), pos) - keys->begin());
+        if (seen[i]) return;
+        seen[i] = 1;
+        for (size_t x = i + 1; x < bit.size(); x += x & (~x + 1)) bit[x] += len;
+    }
+    long upto(int pos) const {   // sum over recorded positions <= pos
+        size_t i = (size_t)(std::upper_bound(keys->begin(), keys->end(), pos) - keys->begin());
+        long s = 0; for (size_t x = i; x > 0; x -= x & (~x + 1)) s += bit[x];
+        return s;
+    }
+};
+
+struct HapBuild { std::vector<Piece> pieces; std::vector<Sub> subs; uint64_t len = 0; };
+
+void hap_append(HapBuild& h, uint64_t src, uint32_t len) {
+    if (len == 0) return;
+    if (!h.pieces.empty()) {
+        Piece& p = h.pieces.back();
+        if (p.src + p.len == src && ((p.src ^ src) & kLiteral) == 0 && (uint64_t)p.len + len < (1ull << 31)) { p.len += len; h.len += len; return; }
+    }
+    h.pieces.push_back({h.len, src, len}); h.len += len;
+}
+
+struct Planner {
+    Plan& P; LibcRand rng; int ploidy;
+    std::vector<uint32_t> hits;
+    Planner(Plan& p, uint32_t seed, int pl) : P(p), rng(seed), ploidy(pl) {}
+
+    // Genome::generateSegment, Genome.cpp:388-691, for the 1-based inclusive chromosome range [s, e]
+    bool segment(std::vector<HapBuild>& hap, ChromVars* cv, const std::string& chr, long chrLen, long s, long e, int CN, int mCN) {
+        if (CN == 0) return true;
+        if (s - 1 < 0 || e - s + 1 < 1) { P.err = "Error: cannot construct subsequence with negative offset or length < 1"; return false; }
+        if (e > chrLen) { P.err = "ERROR: segment " + std::to_string(s) + "-" + std::to_string(e) + " lies past the end of chromosome " + chr; return false; }
+        const unsigned int refSize = (unsigned int)(e - s + 1);
+        P.n_segments++;
+        int i, j, k, n;
+        std::vector<int> major, reps;
+        auto has = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+        std::vector<int> copies(ploidy, 0);   // how many copies of the segment each haplotype carries
+
+        if (CN < ploidy) {   // :411-425: CN distinct haplotypes keep one copy, the first mCN drawn are the major ones
+            for (i = 0; i < CN; i++) for (;;) { j = (int)rng.integer(0, ploidy); if (!has(reps, j)) { reps.push_back(j); break; } }
+            for (i = 0; i < mCN; i++) major.push_back(reps[i]);
+            for (int h : reps) copies[h] = 1;
+        } else {             // :426-467
+            reps.assign(ploidy, 1);
+            n = CN - ploidy;
+            k = (int)rng.integer(0, ploidy);
+            for (i = n; i >= 0; i--) {
+                if (reps[k] + i == mCN) { reps[k] += i; major.push_back(k); break; }
+                else if (reps[k] + i == CN - mCN) { reps[k] += i; for (j = 0; j < ploidy; j++) if (j != k) major.push_back(j); break; }
+            }
+            if (i >= 0) {
+                n -= i;
+                if (n > 0 && ploidy < 2) { P.err = "ERROR: copy number cannot be distributed over one haplotype"; return false; }   // reference: endless loop
+                while (n > 0) { j = (int)rng.integer(0, ploidy); if (j != k) { reps[j]++; n--; } }
+            } else {
+                while (n > 0) { j = (int)rng.integer(0, ploidy); reps[j]++; n--; }
+                for (i = 0; i < ploidy; i++) major.push_back(i);
+            }
+            copies = reps;
+        }
+        std::vector<char> in_major(ploidy, 0); for (int h : major) if (h >= 0 && h < ploidy) in_major[h] = 1;
+        // a het variant goes to the major haplotypes when k == 0 and to the others when k == 1 (:496-499 and alike)
+        auto skipped = [&](int kk, int jj) { return (kk == 0 && !in_major[jj]) || (kk == 1 && in_major[jj]); };
+
+        std::vector<Rope> rope(ploidy);
+        for (j = 0; j < ploidy; j++) for (int t = 0; t < copies[j]; t++) rope[j].append({(uint64_t)(s - 1), (uint64_t)t * refSize, refSize});
+        std::vector<std::vector<std::pair<uint32_t, uint8_t>>> point(ploidy);   // (position in the segment, base), in application order
+
+        if (cv) {
+            k = 0;   // SNPs :489-508
+            cv->snp.in_range(s, e, hits);
+            for (uint32_t id : hits) {
+                const PointVar& v = cv->snp.v[id];
+                for (j = 0; j < ploidy; j++) if (!skipped(k, j) && copies[j]) point[j].push_back({(uint32_t)(v.pos - s), v.ch});
+                k = (k + 1) % 2;
+            }
+            k = 0;   // SNVs :510-544
+            cv->snv.in_range(s, e, hits);
+            for (uint32_t id : hits) {
+                const PointVar& v = cv->snv.v[id];
+                for (j = 0; j < ploidy; j++) if (!(v.het && skipped(k, j)) && copies[j]) point[j].push_back({(uint32_t)(v.pos - s), v.ch});
+                if (v.het) k = (k + 1) % 2;
+            }
+            // indels :546-679
+            std::vector<uint32_t> ins_hits, del_hits;
+            cv->ins.in_range(s, e, ins_hits); cv->del.in_range(s, e, del_hits);
+            std::vector<int> ins_keys, del_keys;
+            for (uint32_t id : ins_hits) ins_keys.push_back((int)(cv->ins.v[id].pos - s));
+            for (uint32_t id : del_hits) del_keys.push_back((int)(cv->del.v[id].pos - s));
+            std::sort(ins_keys.begin(), ins_keys.end()); ins_keys.erase(std::unique(ins_keys.begin(), ins_keys.end()), ins_keys.end());
+            std::sort(del_keys.begin(), del_keys.end()); del_keys.erase(std::unique(del_keys.begin(), del_keys.end()), del_keys.end());
+            std::vector<OffsetIndex> insAt(ploidy), delAt(ploidy);
+            for (j = 0; j < ploidy; j++) { insAt[j].init(&ins_keys); delAt[j].init(&del_keys); }
+            std::vector<int> insLen(ploidy, 0), delLen(ploidy, 0);
+            k = 0;
+            for (uint32_t id : ins_hits) {
+                const InsVar& v = cv->ins.v[id];
+                const int sindx = (int)(v.pos - s);
+                for (j = 0; j < ploidy; j++) {
+                    if (v.het && skipped(k, j)) continue;
+                    const int offset = (int)insAt[j].upto(sindx);
+                    Rope& q = rope[j];
+                    if (refSize + insLen[j] == 0) { P.err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
+                    n = (int)(q.size() / (refSize + insLen[j]));
+                    const int len = (int)v.len;
+                    for (int t = 0; t < n; t++) {
+                        const unsigned int at = sindx + offset + t * (refSize + insLen[j] + len);   // the reference's 32-bit arithmetic, :567-569
+                        if (!q.insert(at, {kLiteral | v.lit_off, 0, v.len})) {
+                            P.err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
+                            return false;
+                        }
+                    }
+                    insLen[j] += len;
+                    insAt[j].record(sindx, len);
+                }
+                if (v.het) k = (k + 1) % 2;
+            }
+            // k is not reset between the two loops in the reference (:608 has no `k = 0`)
+            for (uint32_t id : del_hits) {
+                const DelVar& v = cv->del.v[id];
+                const int sindx = (int)(v.pos - s);
+                const int dl = v.len;
+                for (j = 0; j < ploidy; j++) {
+                    if (v.het && skipped(k, j)) continue;
+                    const int offset = (int)(insAt[j].upto(sindx) - delAt[j].upto(sindx));
+                    if (sindx + offset < 0) continue;
+                    Rope& q = rope[j];
+                    if (refSize + insLen[j] - delLen[j] == 0) { P.err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
+                    n = (int)(q.size() / (refSize + insLen[j] - delLen[j]));
+                    for (int t = 0; t < n; t++) {
+                        const unsigned int at = sindx + offset + t * (refSize + insLen[j] - delLen[j] - dl);   // :637-639
+                        // std::string::erase(pos, n) takes n as size_t: a negative length becomes "to the end"
+                        if (!q.erase(at, (uint64_t)(size_t)(long)dl)) {
+                            P.err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
+                            return false;
+                        }
+                    }
+                    delLen[j] += dl;
+                    delAt[j].record(sindx, dl);
+                }
+                if (v.het) k = (k + 1) % 2;
+            }
+        }
+        // flatten: runs -> pieces of the haplotype; point substitutions -> output positions (a base that was deleted has none)
+        for (j = 0; j < ploidy; j++) {
+            HapBuild& H = hap[j];
+            const uint64_t base = H.len;
+            std::vector<std::pair<uint64_t, uint64_t>> qmap;   // (q, offset in this segment's output) of reference runs, q ascending
+            std::vector<uint32_t> qlen;
+            uint64_t at = 0;
+            rope[j].for_each([&](const Run& r) {
+                if (!(r.src & kLiteral)) { qmap.push_back({r.q, at}); qlen.push_back(r.len); }
+                hap_append(H, r.src, r.len); at += r.len;
+            });
+            std::vector<std::pair<uint32_t, uint8_t>>& pv = point[j];
+            if (pv.empty() || qmap.empty()) continue;
+            std::stable_sort(pv.begin(), pv.end(), [](const std::pair<uint32_t, uint8_t>& a, const std::pair<uint32_t, uint8_t>& b) { return a.first < b.first; });
+            for (size_t x = 0; x < pv.size(); x++) {
+                if (x + 1 < pv.size() && pv[x + 1].first == pv[x].first) continue;   // a later write to the same base wins
+                for (int t = 0; t < copies[j]; t++) {
+                    const uint64_t q = (uint64_t)pv[x].first + (uint64_t)t * refSize;
+                    size_t r = (size_t)(std::upper_bound(qmap.begin(), qmap.end(), q, [](uint64_t x, const std::pair<uint64_t, uint64_t>& e) { return x < e.first; }) - qmap.begin());
+                    if (r == 0) continue;
+                    r--;
+                    if (q >= qmap[r].first + qlen[r]) continue;
+                    H.subs.push_back({base + qmap[r].second + (q - qmap[r].first), pv[x].second});
+                }
+            }
+        }
+        return true;
+    }
+};
+
+}  // namespace
+
+bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_file, const char* var_file, int ploidy, uint32_t libc_seed) {
+    P = Plan(); P.ploidy = ploidy; P.chroms = chroms;
+    if (ploidy < 1 || ploidy > 64) { P.err = "ERROR: ploidy out of range"; return false; }
+    std::map<std::string, ChromVars> by_chr;
+    if (!load_variations(P, var_file, by_chr)) return false;   // Genome::loadData order: loadAbers, loadSNPs, loadRefSeq (Genome.cpp:18-25)
+    if (!load_snps(P, snp_file, by_chr)) return false;
+    if (chroms.empty()) { P.err = "ERROR: reference sequence cannot be empty!"; return false; }
+    Planner pl(P, libc_seed, ploidy);
+    const int mCN = (int)ceilf((float)ploidy / 2);
+    // Genome::saveSequence, Genome.cpp:329-386
+    for (size_t c = 0; c < chroms.size(); c++) {
+        const std::string& chr = chroms[c].name;
+        const long chrLen = (long)chroms[c].len;
+        auto it = by_chr.find(chr);
+        ChromVars* cv = it == by_chr.end() ? nullptr : &it->second;
+        std::vector<HapBuild> hap(ploidy);
+        long segStart = 1;
+        if (cv) for (Cnv cnv : cv->cnv) {
+            if (segStart > chrLen) break;
+            cnv.epos = std::min(cnv.epos, chrLen);
+            if (segStart < cnv.spos && !pl.segment(hap, cv, chr, chrLen, segStart, cnv.spos - 1, ploidy, mCN)) return false;
+            if (!pl.segment(hap, cv, chr, chrLen, cnv.spos, cnv.epos, (int)cnv.cn, (int)cnv.mcn)) return false;
+            segStart = cnv.epos + 1;
+        }
+        if (segStart <= chrLen && !pl.segment(hap, cv, chr, chrLen, segStart, chrLen, ploidy, mCN)) return false;
+        for (int j = 0; j < ploidy; j++) {
+            if (hap[j].len >= (1ull << 32)) { P.err = "ERROR: haplotype longer than 2^32-1 bases (Genome.cpp:370 uses unsigned int)"; return false; }
+            Hap h; h.chrom = (uint32_t)c; h.hap = (uint32_t)j; h.len = hap[j].len;
+            h.piece_lo = P.pieces.size(); P.pieces.insert(P.pieces.end(), hap[j].pieces.begin(), hap[j].pieces.end()); h.piece_hi = P.pieces.size();
+            h.sub_lo = P.subs.size(); P.subs.insert(P.subs.end(), hap[j].subs.begin(), hap[j].subs.end()); h.sub_hi = P.subs.size();
+            h.name = chr + "_" + std::to_string(j + 1) + "_" + std::to_string(chrLen);
+            P.haps.push_back(h);
+        }
+    }
+    return true;
+}
+
+}  // namespace sv
+}  // namespace scs

@@ -176,3 +176,147 @@ def write_genome_with_n(path: str, glen: int = 300_000, seed: int = 77, width: i
         out.append((name, s))
     write_fasta(path, out, width=width)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ simuvars
+def ref_bin():
+    """The compiled reference (oracle/_ref/bin/scssim, stock behaviour + the five missing returns); None if never built."""
+    p = os.path.join(ORACLE_DIR, "_ref", "bin", "scssim")
+    if os.path.exists(p):
+        return p
+    if os.path.isdir("/root/reference/lib"):
+        subprocess.run(["bash", os.path.join(ORACLE_DIR, "build_ref.sh")], check=True)
+        return p if os.path.exists(p) else None
+    return None
+
+
+def make_simuvars_case(d: str, seed: int, chrom_lens=(60_000, 35_000), n_snp=300, n_snv=40, n_ins=40, n_del=40, n_cnv=6, width=100,
+                       names=None, max_cn=5, lower=True):
+    """Random `scssim simuvars` inputs in directory d: ref.fa (soft-masked stretch + an N run per chromosome), snp.txt (6 columns:
+    id, chr, pos, observed, strand, ref — both strands, both allele orders) and vars.txt (i/d/s/c records, het and homo,
+    copy numbers 0..max_cn). Returns (ref, snp, var) paths."""
+    from scssim_b200.synth import synth_sequence, write_fasta
+    os.makedirs(d, exist_ok=True)
+    rng = np.random.default_rng(seed)
+    names = names or [f"chr{i + 1}" for i in range(len(chrom_lens))]
+    seqs = []
+    for i, L in enumerate(chrom_lens):
+        s = synth_sequence(L, seed * 100 + i)
+        if lower and L > 1000:
+            a = int(rng.integers(0, L - 500)); s[a:a + 500] |= 0x20
+            b = int(rng.integers(0, L - 50)); s[b:b + 50] = ord("N")
+        seqs.append((names[i], s))
+    ref, snp, var = os.path.join(d, "ref.fa"), os.path.join(d, "snp.txt"), os.path.join(d, "vars.txt")
+    write_fasta(ref, seqs, width)
+    if os.path.exists(ref + ".fai"):
+        os.remove(ref + ".fai")
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+    with open(snp, "w") as f:
+        for nm, s in seqs:
+            L = len(s)
+            for p in sorted(rng.integers(1, L + 1, size=n_snp).tolist()):
+                r = chr(s[p - 1]).upper()
+                alts = [b for b in "ACGT" if b != r]
+                alt = alts[int(rng.integers(0, len(alts)))]
+                if rng.integers(0, 2):
+                    obs = f"{r}/{alt}" if rng.integers(0, 2) else f"{alt}/{r}"
+                    f.write(f"rs{p}\t{nm}\t{p}\t{obs}\t+\t{r}\n")
+                else:
+                    f.write(f"rs{p}\t{nm}\t{p}\t{comp.get(r, 'N')}/{comp[alt]}\t-\t{r}\n")
+    with open(var, "w") as f:
+        f.write("#type\tchr\tfields\n\n")
+        for nm, s in seqs:
+            L = len(s)
+            zyg = lambda: "homo" if rng.integers(0, 2) else "het"
+            for _ in range(n_ins):
+                p = int(rng.integers(1, L + 1)); l = int(rng.integers(1, 12))
+                f.write(f"i\t{nm}\t{p}\t{''.join('acgt'[x] for x in rng.integers(0, 4, size=l))}\t{zyg()}\n")
+            for _ in range(n_del):
+                p = int(rng.integers(1, max(2, L - 30))); l = int(rng.integers(1, 20))
+                f.write(f"d\t{nm}\t{p}\t{l}\t{zyg()}\n")
+            for _ in range(n_snv):
+                p = int(rng.integers(1, L + 1)); r = chr(s[p - 1])
+                alt = [b for b in "ACGT" if b != r.upper()][int(rng.integers(0, 3))]
+                f.write(f"s\t{nm}\t{p}\t{r}\t{alt}\t{zyg()}\n")
+            cuts = sorted(rng.integers(1, L, size=2 * n_cnv).tolist())
+            for c in range(n_cnv):
+                a, b = cuts[2 * c], cuts[2 * c + 1]
+                if b <= a:
+                    continue
+                cn = int(rng.integers(0, max_cn + 1)); mcn = int(rng.integers((cn + 1) // 2, cn + 1))
+                f.write(f"c\t{nm}\t{a}\t{b}\t{cn}\t{mcn}\n")
+    return ref, snp, var
+
+
+def run_oracle_simuvars(ref, snp, var, out, seed=None, check=True):
+    cmd = [oracle_bin(), "simuvars", "-r", ref, "-o", out]
+    if snp:
+        cmd += ["-s", snp]
+    if var:
+        cmd += ["-v", var]
+    if seed is not None:
+        cmd += ["--seed", str(seed)]
+    r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    if check:
+        assert r.returncode == 0, r.stderr.decode()
+    return r
+
+
+def run_reference_simuvars(ref, snp, var, out):
+    """The reference binary itself; removes the .fai side file first so it indexes from scratch."""
+    exe = ref_bin()
+    assert exe is not None
+    if os.path.exists(ref + ".fai"):
+        os.remove(ref + ".fai")
+    cmd = [exe, "simuvars", "-r", ref, "-o", out]
+    if snp:
+        cmd += ["-s", snp]
+    if var:
+        cmd += ["-v", var]
+    return subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+
+
+def read_fasta_records(path):
+    """[(header, uint8 bases)] of a FASTA file."""
+    names, seqs = [], []
+    for line in read_bytes(path).split(b"\n"):
+        if line.startswith(b">"):
+            names.append(line[1:].decode()); seqs.append([])
+        elif names:
+            seqs[-1].append(line)
+    return [(n, np.frombuffer(b"".join(s), dtype=np.uint8)) for n, s in zip(names, seqs)]
+
+
+def strip_chr(name: str) -> str:
+    i = name.find("chrom")
+    if i < 0:
+        i = name.find("chr")
+        return name[i + 3:] if i >= 0 else name
+    return name[i + 5:]
+
+
+def materialize_plan(ref, snp, var, ploidy=2, seed=1, width=100) -> bytes:
+    """Test-side numpy execution of the library's host-built edit plan (what the CUDA kernels do on the device):
+    copy runs, then point substitutions, then FASTA line breaking."""
+    from scssim_b200 import api
+    recs = read_fasta_records(ref)
+    P = api.SimuVarsPlan([(strip_chr(n.split()[0]), len(s)) for n, s in recs], snp, var, ploidy, seed)
+    haps, pieces, subs, lits, names = P.haps, P.pieces, P.subs, P.literals, P.names
+    out = []
+    for h, nm in zip(haps, names):
+        c, L = int(h[0]), int(h[2])
+        refu = np.frombuffer(recs[c][1].tobytes().upper(), dtype=np.uint8)
+        buf = np.zeros(L, dtype=np.uint8)
+        for o, src, ln in pieces[int(h[3]):int(h[4])].tolist():
+            if src & api.SV_LITERAL:
+                src &= ~api.SV_LITERAL
+                buf[o:o + ln] = lits[src:src + ln]
+            else:
+                buf[o:o + ln] = refu[src:src + ln]
+        for o, ch in subs[int(h[5]):int(h[6])].tolist():
+            buf[o] = ch
+        out.append(b">" + nm.encode() + b"\n")
+        t = buf.tobytes()
+        out.extend(t[i:i + width] + b"\n" for i in range(0, L, width))
+    P.close()
+    return b"".join(out)
