@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-len", type=int, default=GENOME_LEN, help="(debug) override the workload size; invalidates the number")
+    ap.add_argument("--coverage", type=float, default=COVERAGE, help="(debug) override -c; invalidates the number")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="(debug) skip the CPU leg")
     ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons (equal shards)")
     ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
@@ -214,7 +215,7 @@ def main():
         # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream. With several GPUs the
         # read slots are cut in proportion to each GPU's measured D2H rate (balance=1), so a GPU behind a slower host link
         # writes fewer reads; the rank-ordered shards are byte-identical to the single-GPU files
-        g = api.GenReads(gamma=GAMMA, coverage=COVERAGE, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world,
+        g = api.GenReads(gamma=GAMMA, coverage=a.coverage, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world,
                          slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance))
         if world > 1:
             g.set_shard_weight(d2h_per_rank[rank])
@@ -302,7 +303,7 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name() if glen == GENOME_LEN else f"DEBUG {glen} bp", "per_gpu": "one 250 Mb chromosome per rank; ranks form one cell (global read allocation over NCCL)", "layout": "PE", "read_length": READ_LEN,
+            "config": {"workload": workload_name() if (glen == GENOME_LEN and a.coverage == COVERAGE) else f"DEBUG {glen} bp per rank, -c {a.coverage}", "per_gpu": "one 250 Mb chromosome per rank; ranks form one cell (global read allocation over NCCL)", "layout": "PE", "read_length": READ_LEN,
                        "reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": bytes_all * a.steps / dev_s / 1e9,
                        "full_amplicons": n_fulls, "semi_amplicons": n_semis,
                        "l2": "every step streams ~5 GB of FASTQ through L2 (>> 126 MB), evicting the 62 MB packed genome between steps",

@@ -144,3 +144,38 @@ def test_cli_simuvars_drop_in(tmp_path):
     assert r.returncode == 1 and b"Use --output to specify the output file." in r.stderr
     r = subprocess.run([EXE, "simuvars", "-r", ref, "-v", os.path.join(d, "nope.txt"), "-o", os.path.join(d, "x.fa")], capture_output=True)
     assert r.returncode != 0 and b"can not open file" in r.stderr
+
+
+def test_to_genome_two_ranks_equal_one_rank(tmp_path):
+    """world = 2: every rank builds the same plan and materialises only its share of the haplotypes; together the ranks
+    write exactly the records of the single-rank run (global ids key headers and Philox streams)."""
+    import threading
+    from scssim_b200.dist import ThreadCollectives
+    d = str(tmp_path)
+    ref, snp, var = H.make_simuvars_case(d, 23, chrom_lens=(120_000, 110_000), n_cnv=3)
+    prof = H.profile_path("Illumina_HiSeq2500")
+    kw = dict(gamma=2e-10, coverage=4.0, seed=55, layout="SE")
+    with api.GenReads(**kw) as g:
+        g.load_profile(prof).simuvars_to_genome(ref, snp, var).create_frags().amplify()
+        one = g.yield_reads_bytes()[0]
+        n_seq = g.stats()["n_sequences"]
+    assert n_seq == 4
+    world, coll, out, errs = 2, ThreadCollectives(2), [None, None], []
+
+    def run(rank):
+        try:
+            with api.GenReads(rank=rank, world=world, **kw) as g:
+                g.set_collectives(*coll.pair())
+                g.load_profile(prof).simuvars_to_genome(ref, snp, var).create_frags().amplify()
+                out[rank] = (g.yield_reads_bytes()[0], g.stats())
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+            coll.bar.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert out[0][1]["n_sequences"] + out[1][1]["n_sequences"] == 4 and out[0][1]["n_sequences"] in (1, 2, 3)
+    rec = lambda fq: sorted(b"\n".join(l) for l in zip(*[iter(fq.split(b"\n")[:-1])] * 4))
+    assert len(one) > 50_000 and rec(out[0][0] + out[1][0]) == rec(one)
