@@ -55,6 +55,8 @@ typedef struct scs_params {
                              cut into contiguous ranges in proportion to scs_set_shard_weight(), so a GPU behind a slower host
                              link gets fewer reads; the shards then concatenate (rank order) to exactly the 1-GPU files */
     uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (64 MiB) */
+    int32_t io_threads;   /* host threads that pwrite() each slab to the output files (the CLI's -t); 0 -> default (4) */
+    int32_t reserved;
 } scs_params;
 
 void scs_default_params(scs_params* p);

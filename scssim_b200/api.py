@@ -34,7 +34,8 @@ class ScsError(RuntimeError):
 class Params(C.Structure):
     _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
                 ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
-                ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64)]
+                ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64), ("io_threads", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -176,7 +177,7 @@ class GenReads:
 
     def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
                  layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
-                 slab_bytes: int = 0, balance: bool = False):
+                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0):
         if layout not in ("SE", "PE"):
             raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
         L = lib()
@@ -185,6 +186,7 @@ class GenReads:
         p.primers, p.gamma, p.coverage, p.isize = primers, gamma, coverage, isize
         p.paired, p.seed, p.device, p.rank, p.world, p.slab_bytes = int(layout == "PE"), seed, device, rank, world, slab_bytes
         p.balance = int(balance)
+        p.io_threads = io_threads
         self._h = C.c_void_p()
         rc = L.scs_create(C.byref(p), C.byref(self._h))
         if rc != SCS_OK:

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "ctx.h"
+#include "file_sink.h"
 #include "simuvars_plan.h"
 
 using namespace scs;
@@ -17,7 +18,7 @@ const char* scs_version(void) { return "scssim_b200 0.1 (sm_100a)"; }
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
     p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
-    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0;
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0;
 }
 
 int scs_create(const scs_params* p, scs_ctx** out) {
@@ -117,23 +118,16 @@ int scs_yield_reads_sink(scs_ctx* c, scs_sink_fn sink, void* user) {
     return yield_reads(c, sink, user);
 }
 
-namespace { struct FileSink { FILE* f[2]; }; }
-static int file_sink(void* user, int file, const char* data, size_t n) {
-    FileSink* s = (FileSink*)user;
-    return fwrite(data, 1, n, s->f[file]) == n ? 0 : 1;
-}
 int scs_yield_reads(scs_ctx* c, const char* prefix) {   // Malbac.cpp:426-435: <prefix>_1.fq/_2.fq or <prefix>.fq
     if (!c || !prefix) return SCS_E_ARG;
     std::string base = prefix;
     if (c->P.world > 1) base += ".rank" + std::to_string(c->P.rank);
-    FileSink s{{nullptr, nullptr}};
     std::string n1 = c->P.paired ? base + "_1.fq" : base + ".fq", n2 = base + "_2.fq";
-    s.f[0] = fopen(n1.c_str(), "wb");
-    if (!s.f[0]) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n1);
-    if (c->P.paired) { s.f[1] = fopen(n2.c_str(), "wb"); if (!s.f[1]) { fclose(s.f[0]); return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n2); } }
-    setvbuf(s.f[0], nullptr, _IOFBF, 8 << 20); if (s.f[1]) setvbuf(s.f[1], nullptr, _IOFBF, 8 << 20);
-    int rc = scs_yield_reads_sink(c, file_sink, &s);
-    fclose(s.f[0]); if (s.f[1]) fclose(s.f[1]);
+    ParallelFileWriter w(c->P.io_threads > 0 ? c->P.io_threads : 4);
+    if (!w.open(0, n1)) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n1);
+    if (c->P.paired && !w.open(1, n2)) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n2);
+    int rc = scs_yield_reads_sink(c, parallel_file_sink, &w);
+    if (w.close() != 0 && rc == SCS_OK) rc = c->fail(SCS_E_IO, "Error: can not write fastq file:\n" + n1);
     return rc;
 }
 
@@ -156,15 +150,13 @@ int scs_simuvars_sink(scs_ctx* c, const scs_simuvars_params* p, const char* ref,
 int scs_simuvars_to_genome(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var) {
     return simuvars_entry(c, p, ref, snp, var, nullptr, nullptr, true);
 }
-static int one_file_sink(void* user, int, const char* data, size_t n) { return fwrite(data, 1, n, (FILE*)user) == n ? 0 : 1; }
 int scs_simuvars(scs_ctx* c, const scs_simuvars_params* p, const char* ref, const char* snp, const char* var, const char* out) {
     if (!c) return SCS_E_ARG;
     if (!out || !*out) return c->fail(SCS_E_ARG, "Use --output to specify the output file.");   // src/scssim.cpp:162-166
-    FILE* f = fopen(out, "wb");
-    if (!f) return c->fail(SCS_E_IO, std::string("can not open file ") + out);   // Genome.cpp:337-340
-    setvbuf(f, nullptr, _IOFBF, 8 << 20);
-    int rc = simuvars_entry(c, p, ref, snp, var, one_file_sink, f, false);
-    if (fclose(f) != 0 && rc == SCS_OK) rc = c->fail(SCS_E_IO, std::string("can not write file ") + out);
+    ParallelFileWriter w(c->P.io_threads > 0 ? c->P.io_threads : 4);
+    if (!w.open(0, out)) return c->fail(SCS_E_IO, std::string("can not open file ") + out);   // Genome.cpp:337-340
+    int rc = simuvars_entry(c, p, ref, snp, var, parallel_file_sink, &w, false);
+    if (w.close() != 0 && rc == SCS_OK) rc = c->fail(SCS_E_IO, std::string("can not write file ") + out);
     return rc;
 }
 int scs_simuvars_get_stats(const scs_ctx* c, scs_simuvars_stats* out) { if (!c || !out) return SCS_E_ARG; *out = c->sv_stats; return SCS_OK; }

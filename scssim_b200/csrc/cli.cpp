@@ -1,7 +1,7 @@
 // `scssim genreads` and `scssim simuvars` drop-in: same flags, defaults, validation messages, stderr progress lines and
 // output files as the reference's CLI (/root/reference/src/scssim.cpp:23-76,109-172,285-404,421-485), driving
-// the CUDA path through the C ABI. `-t` is accepted (the reference's worker-thread count) and ignored:
-// the work runs on the GPU. Extra long-only flags: --seed <u64>, --device <n>.
+// the CUDA path through the C ABI. `-t` (the reference's worker-thread count) sets the number of host
+// threads that write the FASTQ slabs to the files: the compute runs on the GPU. Extra long-only flags: --seed <u64>, --device <n>.
 #include <getopt.h>
 
 #include <condition_variable>
@@ -106,7 +106,7 @@ static void usage_genReads(const char* app) {
          << "    -l, --layout <string>           read layout (SE for single end, PE for paired-end) [Default:PE]" << endl
          << "    -c, --coverage <float>          sequencing coverage [Default:5]" << endl
          << "    -s, --isize <int>               mean insert size for paired-end sequencing [Default:260]" << endl
-         << "    -t, --threads <int>             number of threads to use [Default:1] (accepted; work runs on the GPU)" << endl
+         << "    -t, --threads <int>             number of threads to use [Default:1] (host threads writing the files; compute runs on the GPU)" << endl
          << "    -o, --output <string>           the prefix of output file" << endl
          << "        --seed <int>                random seed [Default:time]" << endl
          << "        --device <int>              CUDA device ordinal [Default:0]" << endl
@@ -170,7 +170,7 @@ int main(int argc, char* argv[]) {
     string modelFile, inputFile, outputPrefix, layout = "PE";
     scs_params P; scs_default_params(&P);
     P.seed = (uint64_t)start_t;
-    int threads = 1, gpus = 1;
+    int threads = 1, gpus = 1; bool threads_given = false;
     struct option long_options[] = {{"help", no_argument, 0, 'h'},          {"input", required_argument, 0, 'i'},
                                     {"primers", required_argument, 0, 'p'}, {"gamma", required_argument, 0, 'r'},
                                     {"model", required_argument, 0, 'm'},   {"layout", required_argument, 0, 'l'},
@@ -190,7 +190,7 @@ int main(int argc, char* argv[]) {
             case 'l': layout = optarg; break;
             case 'c': P.coverage = atof(optarg); break;
             case 's': P.isize = atoi(optarg); break;
-            case 't': threads = atoi(optarg); break;
+            case 't': threads = atoi(optarg); threads_given = true; break;
             case 'o': outputPrefix = optarg; break;
             case 1000: P.seed = strtoull(optarg, NULL, 0); break;
             case 1001: P.device = atoi(optarg); break;
@@ -208,6 +208,7 @@ int main(int argc, char* argv[]) {
     if (P.coverage <= 0) { cerr << "Error: sequencing coverage not properly specified!" << endl; return 1; }
     if (threads < 1) { cerr << "Error: number of threads should be a positive integer!" << endl; return 1; }
     P.paired = layout == "PE";
+    P.io_threads = threads_given ? threads : 0;   // the reference's worker threads become the host threads that write the FASTQ slabs
     if (gpus < 1) { cerr << "Error: number of GPUs should be a positive integer!" << endl; return 1; }
 
     if (gpus > 1) {

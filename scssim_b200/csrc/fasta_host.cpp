@@ -1,5 +1,10 @@
 #include "fasta_host.h"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstring>
 
@@ -13,41 +18,65 @@ std::string strip_chr_prefix(const std::string& in) {
     return name;
 }
 
-bool fasta_read_and_index(const char* path, std::vector<char>& raw, size_t& got, std::vector<FaiRec>& fai, std::string* err) {
-    FILE* f = fopen(path, "rb");
-    if (!f) { if (err) *err = std::string("could not open ") + path; return false; }
-    fseek(f, 0, SEEK_END); long long sz = ftell(f); fseek(f, 0, SEEK_SET);
-    raw.assign((size_t)(sz > 0 ? sz : 0) + 1, 0);
-    got = sz > 0 ? fread(raw.data(), 1, (size_t)sz, f) : 0;
-    fclose(f);
-    raw[got] = '\n';
+FastaFile::~FastaFile() { if (map_) munmap(map_, map_len_); }
+
+bool FastaFile::open(const char* path, std::string* err) {
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) { if (err) *err = std::string("could not open ") + path; return false; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { ::close(fd); if (err) *err = std::string("could not open ") + path; return false; }
+    size = (size_t)sb.st_size;
+    if (size) {
+        map_ = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+        if (map_ == MAP_FAILED) { map_ = nullptr; ::close(fd); if (err) *err = std::string("could not map ") + path; return false; }
+        map_len_ = size;
+        madvise(map_, map_len_, MADV_SEQUENTIAL);
+    }
+    ::close(fd);
+    data = (const char*)map_;
     fai.clear();
-    size_t pos = 0;
-    while (pos < got) {
-        char* s = &raw[pos];
-        char* e = (char*)memchr(s, '\n', got + 1 - pos);
+    const char* const end = data + size;
+    const char* s = data;
+    FaiRec* a = nullptr;
+    while (s < end) {
+        const char* e = (const char*)memchr(s, '\n', (size_t)(end - s));
+        if (!e) e = end;                       // last line without a terminator
         size_t len = (size_t)(e - s);
-        size_t llen = len + 1;
+        const size_t llen = len + 1;
         if (len > 0 && s[len - 1] == '\r') len--;
         if (len > 0 && s[0] == '>') {
-            FaiRec r; r.header.assign(s + 1, len - 1);
-            r.name = r.header.substr(0, r.header.find_first_of(" \t"));
-            r.off = (uint64_t)(pos + llen);
-            fai.push_back(r);
-        } else if (!fai.empty()) {
-            FaiRec& a = fai.back();
-            if (len == 0) { if (a.len) a.short_lines++; }          // a blank line is fine only at the very end of a record
+            fai.emplace_back(); a = &fai.back();
+            a->header.assign(s + 1, len - 1);
+            a->name = a->header.substr(0, a->header.find_first_of(" \t"));
+            a->off = (uint64_t)(s - data) + llen;
+        } else if (a) {
+            if (len == 0) { if (a->len) a->short_lines++; }          // a blank line is fine only at the very end of a record
             else {
-                if (a.blen == 0) { a.blen = (uint32_t)len; a.llen = (uint32_t)llen; }
-                if (a.short_lines) a.regular = false;               // bases after a short or blank line
-                if (len != a.blen || llen != a.llen) { if (len > a.blen) a.regular = false; a.short_lines++; }
-                a.len += len;
+                if (a->blen == 0) { a->blen = (uint32_t)len; a->llen = (uint32_t)llen; }
+                if (a->short_lines) a->regular = false;               // bases after a short or blank line
+                if (len != a->blen || llen != a->llen) { if (len > a->blen) a->regular = false; a->short_lines++; }
+                a->len += len;
             }
         }
-        pos += llen;
+        s = e + 1;
     }
     if (fai.empty()) { if (err) *err = "ERROR: reference sequence cannot be empty!"; return false; }
     return true;
+}
+
+void FastaFile::gather(size_t i, std::vector<char>& g) const {
+    g.clear(); g.reserve(fai[i].len);
+    const char* s = data + fai[i].off;
+    const char* const end = (i + 1 < fai.size()) ? data + fai[i + 1].off : data + size;
+    while (s < end && g.size() < fai[i].len) {
+        const char* e = (const char*)memchr(s, '\n', (size_t)(end - s));
+        if (!e) e = end;
+        size_t len = (size_t)(e - s);
+        if (len > 0 && s[len - 1] == '\r') len--;
+        if (len > 0 && s[0] == '>') break;
+        g.insert(g.end(), s, s + len);
+        s = e + 1;
+    }
 }
 
 void fasta_write_fai(const char* path, const std::vector<FaiRec>& fai) {
@@ -56,17 +85,6 @@ void fasta_write_fai(const char* path, const std::vector<FaiRec>& fai) {
     if (FILE* o = fopen(faiPath.c_str(), "wb")) {
         for (const FaiRec& r : fai) fprintf(o, "%s\t%llu\t%llu\t%u\t%u\n", r.name.c_str(), (unsigned long long)r.len, (unsigned long long)r.off, r.blen, r.llen);
         fclose(o);
-    }
-}
-
-void fasta_gather(const std::vector<char>& raw, size_t got, const std::vector<FaiRec>& fai, size_t i, std::vector<char>& g) {
-    g.clear(); g.reserve(fai[i].len);
-    size_t q = fai[i].off, end = (i + 1 < fai.size()) ? (size_t)fai[i + 1].off : got;
-    while (q < end && g.size() < fai[i].len) {
-        const char* s = &raw[q]; const char* e = (const char*)memchr(s, '\n', got + 1 - q); size_t len = (size_t)(e - s); q += len + 1;
-        if (len > 0 && s[len - 1] == '\r') len--;
-        if (len > 0 && s[0] == '>') break;
-        g.insert(g.end(), s, s + len);
     }
 }
 

@@ -17,12 +17,24 @@ struct FaiRec {
     uint64_t short_lines = 0;
 };
 
-// Reads the whole file into `raw` (one extra '\n' appended) and indexes it. Returns false with *err set.
-bool fasta_read_and_index(const char* path, std::vector<char>& raw, size_t& got, std::vector<FaiRec>& fai, std::string* err);
+// A FASTA file mapped read-only (no copy of its bytes is made on the host) and its index.
+struct FastaFile {
+    const char* data = nullptr; size_t size = 0;
+    std::vector<FaiRec> fai;
+    FastaFile() = default;
+    FastaFile(const FastaFile&) = delete;
+    FastaFile& operator=(const FastaFile&) = delete;
+    ~FastaFile();
+    // maps and indexes the file; false with *err set (messages of FastaReference::open / Genome::loadRefSeq)
+    bool open(const char* path, std::string* err);
+    // bases of record i gathered into one contiguous buffer (slow path for ragged records)
+    void gather(size_t i, std::vector<char>& out) const;
+
+  private:
+    void* map_ = nullptr; size_t map_len_ = 0;
+};
 // Writes <path>.fai if it does not exist yet (side effect of FastaReference::open, Fasta.cpp:243-249).
 void fasta_write_fai(const char* path, const std::vector<FaiRec>& fai);
-// Bases of record i gathered into one contiguous buffer (slow path for ragged records).
-void fasta_gather(const std::vector<char>& raw, size_t got, const std::vector<FaiRec>& fai, size_t i, std::vector<char>& out);
 // "chr"/"chrom" prefix stripping of sequence names (lib/fastahack/Fasta.cpp:57-68, MyDefine.cpp:310-323).
 std::string strip_chr_prefix(const std::string& name);
 

@@ -258,8 +258,9 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
     // One pass over the lines builds the .fai index (name, length, offset, bases per line, bytes per line): with a uniform
     // line geometry (what the reference's fastahack reader requires, lib/fastahack/Fasta.cpp:304-334) the text is uploaded
     // as it is and the newlines are skipped by index arithmetic on the device; otherwise the bases are gathered on the host.
-    std::vector<char> raw; size_t got = 0; std::vector<FaiRec> fai; std::string ferr;
-    if (!fasta_read_and_index(path, raw, got, fai, &ferr)) return c->fail(SCS_E_IO, ferr);
+    FastaFile ff; std::string ferr;
+    if (!ff.open(path, &ferr)) return c->fail(SCS_E_IO, ferr);
+    const std::vector<FaiRec>& fai = ff.fai; const char* raw = ff.data;
     fasta_write_fai(path, fai);
     std::vector<std::string> names; for (auto& r : fai) names.push_back(r.header);
     // irregular records: gather their bases into contiguous host buffers (slow path)
@@ -268,7 +269,7 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
     for (size_t i = 0; i < fai.size(); i++) {
         if (fai[i].len > 0 && fai[i].len <= fai[i].blen) { all[i] = {&raw[fai[i].off], fai[i].len, 0, 0, false}; continue; }   // one line: already contiguous
         if (fai[i].regular && fai[i].len > 0 && fai[i].llen <= (1u << 20)) { all[i] = {&raw[fai[i].off], fai[i].len, fai[i].blen, fai[i].llen, false}; continue; }
-        fasta_gather(raw, got, fai, i, gathered[i]);
+        ff.gather(i, gathered[i]);
         all[i] = {gathered[i].data(), gathered[i].size(), 0, 0, false};
     }
     // world > 1: this rank keeps a contiguous run of sequences holding about 1/world of the bases

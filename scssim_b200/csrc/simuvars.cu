@@ -35,75 +35,106 @@ __device__ __forceinline__ uint32_t upper4(uint32_t w) {
     return w - (lower >> 2);
 }
 
+// 16 bytes starting at an arbitrary address: two aligned 16-byte loads (the second one is the neighbour thread's first,
+// an L1 hit) and a word/byte shifter. The caller guarantees 31 readable bytes past p (buffers are padded).
+__device__ __forceinline__ void load16(const uint8_t* p, uint32_t X[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const uint32_t sh = (uint32_t)(a & 15), s8 = (sh & 3) * 8;
+    uint32_t t[6], u[5];
+#pragma unroll
+    for (int i = 0; i < 6; i++) t[i] = (sh & 8) ? w[i + 2] : w[i];
+#pragma unroll
+    for (int i = 0; i < 5; i++) u[i] = (sh & 4) ? t[i + 1] : t[i];
+#pragma unroll
+    for (int m = 0; m < 4; m++) X[m] = __funnelshift_r(u[m], u[m + 1], s8);
+}
+// word m of a 16-byte vector: mask of the bytes whose index in the vector is below k (k may be <= 0 or >= 16)
+__device__ __forceinline__ uint32_t below_mask(int k, int m) {
+    const int km = k - 4 * m;
+    return km <= 0 ? 0u : (km >= 4 ? 0xffffffffu : (1u << (8 * km)) - 1u);
+}
+
+constexpr int kSvTile = kSvThreads * 16;   // bytes (bases) one CTA produces
+
+// One thread = 16 output bases. FASTA text with a fixed line geometry: the bases sit at text[line * llen + col]; a vector
+// crosses at most one line terminator (blen >= 16), which is cut out by merging two shifted 16-byte windows.
 __global__ void __launch_bounds__(kSvThreads) sv_normalize_kernel(const uint8_t* __restrict__ text, uint64_t n_bases, uint32_t blen, uint32_t llen,
                                                                   uint8_t* __restrict__ out) {
-    const uint64_t base = ((uint64_t)blockIdx.x * kSvThreads + threadIdx.x) * 16;
+    __shared__ uint64_t s_line0; __shared__ uint32_t s_col0;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kSvTile;
+    if (blen && threadIdx.x == 0) { s_line0 = tile0 / blen; s_col0 = (uint32_t)(tile0 - s_line0 * blen); }   // one 64-bit division per CTA
+    __syncthreads();
+    const uint64_t base = tile0 + (uint64_t)threadIdx.x * 16;
     if (base >= n_bases) return;
-    uint32_t w[4] = {0, 0, 0, 0};
-    if (blen == 0 && base + 16 <= n_bases && ((reinterpret_cast<uintptr_t>(text + base) & 15) == 0)) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(text + base));
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-    } else {
-        uint64_t line = blen ? base / blen : 0; uint32_t col = blen ? (uint32_t)(base - line * blen) : 0;
-        const uint8_t* p = blen ? text + line * llen + col : text + base;
+    uint32_t X[4];
+    if (blen == 0) load16(text + base, X);
+    else {
+        const uint32_t c = s_col0 + threadIdx.x * 16, dl = c / blen, col = c - dl * blen;
+        const uint8_t* p = text + (s_line0 + dl) * llen + col;
+        if (blen >= 16) {
+            load16(p, X);
+            const int k = (int)(blen - col);   // bases left on this line
+            if (k < 16) {
+                uint32_t Y[4]; load16(p + (llen - blen), Y);
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            if (base + k < n_bases) w[k >> 2] |= (uint32_t)(*p) << (8 * (k & 3));
-            if (blen && ++col == blen) { col = 0; p += llen - blen + 1; } else p++;
+                for (int m = 0; m < 4; m++) { const uint32_t lo = below_mask(k, m); X[m] = (X[m] & lo) | (Y[m] & ~lo); }
+            }
+        } else {   // very narrow lines: bytewise
+            uint32_t cc = col;
+            X[0] = X[1] = X[2] = X[3] = 0;
+            for (int k = 0; k < 16; k++) {
+                if (base + k < n_bases) X[k >> 2] |= (uint32_t)(*p) << (8 * (k & 3));
+                if (++cc == blen) { cc = 0; p += llen - blen + 1; } else p++;
+            }
         }
     }
-    uint4 o; o.x = upper4(w[0]); o.y = upper4(w[1]); o.z = upper4(w[2]); o.w = upper4(w[3]);
+    uint4 o; o.x = upper4(X[0]); o.y = upper4(X[1]); o.z = upper4(X[2]); o.w = upper4(X[3]);
     *reinterpret_cast<uint4*>(out + base) = o;   // the buffer is padded to a multiple of 16
 }
 
 struct SvHapArgs {
     const uint64_t* pout;   // [n_pieces + 1] first output base of each run, pout[n_pieces] = n_bases
     const uint64_t* psrc;   // [n_pieces] device address of the run's first source byte
+    const uint32_t* blk;    // [n_bases / kSvBlock + 1] run that holds base k * kSvBlock (coarse index: no binary search)
     uint32_t n_pieces; uint32_t W;   // W = bases per output line, 0 = no line terminators (bases only)
     uint64_t n_bases, text_len;
     uint8_t* text;
 };
+constexpr uint32_t kSvBlockShift = 11, kSvBlock = 1u << kSvBlockShift;
 
 __global__ void __launch_bounds__(kSvThreads) sv_materialize_kernel(const SvHapArgs A) {
-    const uint64_t b0 = ((uint64_t)blockIdx.x * kSvThreads + threadIdx.x) * 16;
-    if (b0 >= A.text_len) return;
+    __shared__ uint64_t s_line0; __shared__ uint32_t s_col0;
     const uint32_t W = A.W;
-    uint64_t i0 = b0; uint32_t k_nl = 16, col = 0;
-    if (W) { const uint64_t line = b0 / (W + 1); col = (uint32_t)(b0 - line * (W + 1)); i0 = line * W + col; k_nl = W - col; }
+    const uint64_t tile0 = (uint64_t)blockIdx.x * kSvTile;
+    if (W && threadIdx.x == 0) { s_line0 = tile0 / (W + 1); s_col0 = (uint32_t)(tile0 - s_line0 * (W + 1)); }
+    __syncthreads();
+    const uint64_t b0 = tile0 + (uint64_t)threadIdx.x * 16;
+    if (b0 >= A.text_len) return;
+    uint64_t i0 = b0; uint32_t col = 0; int k_nl = 16;   // k_nl: byte of the vector that holds the line terminator (>= 16: none)
+    if (W) { const uint32_t c = s_col0 + threadIdx.x * 16, dl = c / (W + 1); col = c - dl * (W + 1); i0 = (s_line0 + dl) * W + col; k_nl = (int)(W - col); }
     const bool whole = W ? (b0 + 16 < A.text_len && W >= 16) : (b0 + 16 <= A.text_len);   // W: the last byte of the text is handled bytewise
-    // run holding base i0 (clamped to the last run for the vector that is only the final line terminator)
-    uint32_t lo = 0, hi = A.n_pieces;
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(A.pout + mid) <= i0) lo = mid; else hi = mid; }
-    uint32_t p = lo;
+    // run holding base i0, from the coarse index (clamped for the vector that is only the final line terminator)
+    const uint64_t iq = i0 < A.n_bases ? i0 : A.n_bases - 1;
+    uint32_t p = __ldg(A.blk + (iq >> kSvBlockShift));
+    while (__ldg(A.pout + p + 1) <= iq) p++;
     const uint32_t nb = k_nl < 16 ? 15 : 16;
     if (whole && i0 + nb <= __ldg(A.pout + p + 1)) {
-        const uint64_t a = __ldg(A.psrc + p) + (i0 - __ldg(A.pout + p));
-        const uint4* q = reinterpret_cast<const uint4*>(a & ~15ull);
-        const uint4 v0 = __ldg(q), v1 = __ldg(q + 1);   // source buffers carry 32 bytes of padding
-        const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        const uint32_t sh = (uint32_t)(a & 15), s8 = (sh & 3) * 8;
-        uint32_t t[6], u[5], X[4];
+        uint32_t X[4];
+        load16(reinterpret_cast<const uint8_t*>(__ldg(A.psrc + p) + (i0 - __ldg(A.pout + p))), X);
+        // splice '\n' in at byte k_nl (branch-free; k_nl >= 16 leaves X as it is): bytes above it come from X shifted up by one
+        uint32_t Y[4];
+        Y[0] = X[0] << 8;
 #pragma unroll
-        for (int i = 0; i < 6; i++) t[i] = (sh & 8) ? w[i + 2] : w[i];
+        for (int m = 1; m < 4; m++) Y[m] = __funnelshift_l(X[m - 1], X[m], 8);
+        uint4 o; uint32_t* O = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int i = 0; i < 5; i++) u[i] = (sh & 4) ? t[i + 1] : t[i];
-#pragma unroll
-        for (int m = 0; m < 4; m++) X[m] = __funnelshift_r(u[m], u[m + 1], s8);
-        if (k_nl < 16) {   // splice '\n' in at byte k_nl: bytes above it come from X shifted up by one byte
-            uint32_t Y[4];
-            Y[0] = X[0] << 8;
-#pragma unroll
-            for (int m = 1; m < 4; m++) Y[m] = __funnelshift_l(X[m - 1], X[m], 8);
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int km = (int)k_nl - 4 * m;
-                const uint32_t below = km <= 0 ? 0u : (km >= 4 ? 0xffffffffu : (1u << (8 * km)) - 1u);
-                const uint32_t upto = km < 0 ? 0u : (km >= 3 ? 0xffffffffu : (1u << (8 * (km + 1))) - 1u);
-                const uint32_t nl = (km >= 0 && km < 4) ? (0x0Au << (8 * km)) : 0u;
-                X[m] = (X[m] & below) | nl | (Y[m] & ~upto);
-            }
+        for (int m = 0; m < 4; m++) {
+            const uint32_t lo = below_mask(k_nl, m), upto = below_mask(k_nl + 1, m);
+            O[m] = (X[m] & lo) | (0x0A0A0A0Au & upto & ~lo) | (Y[m] & ~upto);
         }
-        uint4 o; o.x = X[0]; o.y = X[1]; o.z = X[2]; o.w = X[3];
         *reinterpret_cast<uint4*>(A.text + b0) = o;
         return;
     }
@@ -165,8 +196,9 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
     scs_simuvars_stats& S = c->sv_stats; S = scs_simuvars_stats{};
     const uint32_t W = to_genome ? 0u : (uint32_t)(sp.line_width > 0 ? sp.line_width : 100);
 
-    std::vector<char> raw; size_t got = 0; std::vector<FaiRec> fai; std::string ferr;
-    if (!fasta_read_and_index(ref, raw, got, fai, &ferr)) return c->fail(SCS_E_IO, ferr);
+    FastaFile ff; std::string ferr;
+    if (!ff.open(ref, &ferr)) return c->fail(SCS_E_IO, ferr);
+    const std::vector<FaiRec>& fai = ff.fai; const char* raw = ff.data;
     fasta_write_fai(ref, fai);
     std::vector<sv::ChromIn> chroms;
     for (const FaiRec& r : fai) chroms.push_back({strip_chr_prefix(r.name), r.len});
@@ -233,7 +265,7 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
             std::vector<char> gathered; const char* src = &raw[r.off]; uint64_t nbytes = r.len; uint32_t blen = 0, llen = 0;
             if (r.len > r.blen) {
                 if (r.regular && r.llen <= (1u << 20)) { blen = r.blen; llen = r.llen; nbytes = r.len + (r.len - 1) / blen * (llen - blen); }
-                else { fasta_gather(raw, got, fai, H.chrom, gathered); src = gathered.data(); nbytes = gathered.size(); }
+                else { ff.gather(H.chrom, gathered); src = gathered.data(); nbytes = gathered.size(); }
             }
             DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(nbytes + 64));
             dref.reset(new DevBuf<uint8_t>()); SCS_CUDA(c, dref->reserve(((r.len + 15) & ~15ull) + 64));
@@ -255,7 +287,8 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
         SCS_CUDA(c, J->text.reserve(((J->text_len + 15) & ~15ull) + 64));
         SCS_CUDA(c, cudaEventCreateWithFlags(&J->done, cudaEventDisableTiming));
         if (H.len) {
-            std::vector<uint64_t> tab(2 * np + 1 + ns);
+            const uint64_t nblk = (H.len >> kSvBlockShift) + 1;
+            std::vector<uint64_t> tab(2 * np + 1 + ns + (nblk + 1) / 2);
             for (uint64_t k = 0; k < np; k++) {
                 const sv::Piece& P = plan.pieces[H.piece_lo + k];
                 tab[k] = P.out;
@@ -263,17 +296,23 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
             }
             tab[np] = H.len;
             for (uint64_t k = 0; k < ns; k++) { const sv::Sub& s = plan.subs[H.sub_lo + k]; tab[2 * np + 1 + k] = (s.out << 8) | s.ch; }
+            uint32_t* blk = reinterpret_cast<uint32_t*>(tab.data() + 2 * np + 1 + ns);   // run holding base k * kSvBlock
+            for (uint64_t k = 0, pc = 0; k < nblk; k++) {
+                const uint64_t at = std::min<uint64_t>(k << kSvBlockShift, H.len - 1);
+                while (pc + 1 < np && plan.pieces[H.piece_lo + pc + 1].out <= at) pc++;
+                blk[k] = (uint32_t)pc;
+            }
             SCS_CUDA(c, J->tables.reserve(tab.size() + 2));
             SCS_CUDA(c, cudaMemcpyAsync(J->tables.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->st));
             SCS_CUDA(c, cudaStreamSynchronize(c->st));   // `tab` is pageable and goes out of scope
             S.h2d_bytes += tab.size() * 8;
-            SvHapArgs A; A.pout = J->tables.p; A.psrc = J->tables.p + np + 1; A.n_pieces = (uint32_t)np; A.W = W; A.n_bases = H.len; A.text_len = J->text_len; A.text = J->text.p;
+            SvHapArgs A; A.pout = J->tables.p; A.psrc = J->tables.p + np + 1; A.blk = reinterpret_cast<const uint32_t*>(J->tables.p + 2 * np + 1 + ns); A.n_pieces = (uint32_t)np; A.W = W; A.n_bases = H.len; A.text_len = J->text_len; A.text = J->text.p;
             timed_begin();
             sv_materialize_kernel<<<(unsigned)((J->text_len + 16 * kSvThreads - 1) / (16 * kSvThreads)), kSvThreads, 0, c->st>>>(A);
             SCS_LAUNCHED(c); S.launches++;
             if (ns) { sv_scatter_kernel<<<(unsigned)((ns + kSvThreads - 1) / kSvThreads), kSvThreads, 0, c->st>>>(J->tables.p + 2 * np + 1, ns, W, J->text.p); SCS_LAUNCHED(c); S.launches++; }
             timed_end();
-            S.materialize_bytes += H.len + J->text_len + 16 * np + 9 * ns;
+            S.materialize_bytes += H.len + J->text_len + 16 * np + 9 * ns + 4 * nblk;
         }
         SCS_CUDA(c, cudaEventRecord(J->done, c->st));
         S.out_bases += H.len;

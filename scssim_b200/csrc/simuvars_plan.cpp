@@ -2,6 +2,7 @@
 #include "simuvars_plan.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -63,6 +64,18 @@ template <class T> struct VarList {
 };
 struct ChromVars { std::vector<Cnv> cnv; VarList<PointVar> snp, snv; VarList<InsVar> ins; VarList<DelVar> del; };
 
+// by_chr[strip_chr_prefix(raw)] with a one-entry cache: variant files list one chromosome after the other
+struct ChromLookup {
+    std::map<std::string, ChromVars>& m; std::string last_raw; ChromVars* last = nullptr;
+    explicit ChromLookup(std::map<std::string, ChromVars>& mm) : m(mm) {}
+    ChromVars& operator()(const char* raw, size_t n) {
+        if (last && last_raw.size() == n && memcmp(last_raw.data(), raw, n) == 0) return *last;
+        last_raw.assign(raw, n); last = &m[strip_chr_prefix(last_raw)];
+        return *last;
+    }
+    ChromVars& operator()(const std::string& raw) { return (*this)(raw.data(), raw.size()); }
+};
+
 // std::getline-on-stringstream field splitting (lib/split/split.cpp:3-15): no empty field after a trailing delimiter
 std::vector<std::string> split_fields(const std::string& s, char d) {
     std::vector<std::string> out; size_t p = 0;
@@ -82,6 +95,7 @@ bool load_variations(Plan& P, const char* path, std::map<std::string, ChromVars>
     std::ifstream ifs(path);
     if (!ifs.is_open()) { P.err = std::string("can not open file ") + path; return false; }
     std::string line; int ln = 0;
+    ChromLookup chrom(by_chr);
     auto fail = [&](const std::string& head) { P.err = head + "\n" + line; return false; };
     auto fields_err = [&]() { return fail("ERROR: line " + std::to_string(ln) + " has wrong number of fields in file " + path); };
     while (std::getline(ifs, line)) {
@@ -94,27 +108,27 @@ bool load_variations(Plan& P, const char* path, std::map<std::string, ChromVars>
             float cn = (float)atof(f[4].c_str()), mcn = (float)atof(f[5].c_str());
             if (cn < mcn) return fail("ERROR: total copy number should be not lower than major copy number at line " + std::to_string(ln) + " in file " + path);
             if (cn - mcn > mcn) mcn = cn - mcn;
-            by_chr[strip_chr_prefix(f[1])].cnv.push_back({atol(f[2].c_str()), atol(f[3].c_str()), cn, mcn});
+            chrom(f[1]).cnv.push_back({atol(f[2].c_str()), atol(f[3].c_str()), cn, mcn});
             P.n_cnv++;
         } else if (kind == "s") {
             if (f.size() != 6) return fields_err();
             if (f[3].empty() || f[4].empty()) return fields_err();   // reference: std::out_of_range from at(0)
             if (f[3][0] == f[4][0]) return fail("ERROR: the mutated allele should be not same as the reference allele at line " + std::to_string(ln) + " in file " + path);
             bool het; if (!parse_zygosity(f[5], het)) return fail("ERROR: unrecognized SNV type at line " + std::to_string(ln) + " in file " + path);
-            by_chr[strip_chr_prefix(f[1])].snv.v.push_back({atol(f[2].c_str()), (uint8_t)toupper((unsigned char)f[4][0]), het});
+            chrom(f[1]).snv.v.push_back({atol(f[2].c_str()), (uint8_t)toupper((unsigned char)f[4][0]), het});
             P.n_snv++;
         } else if (kind == "i") {
             if (f.size() != 5) return fields_err();
             bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized insert type at line " + std::to_string(ln) + " in file " + path);
             std::string seq = f[3];
             for (char& ch : seq) ch = (char)toupper((unsigned char)ch);   // the segment is upper-cased as a whole at the end, Genome.cpp:683-687
-            by_chr[strip_chr_prefix(f[1])].ins.v.push_back({atol(f[2].c_str()), (uint64_t)P.literals.size(), (uint32_t)seq.size(), het});
+            chrom(f[1]).ins.v.push_back({atol(f[2].c_str()), (uint64_t)P.literals.size(), (uint32_t)seq.size(), het});
             P.literals += seq;
             P.n_ins++;
         } else if (kind == "d") {
             if (f.size() != 5) return fields_err();
             bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized deletion type at line " + std::to_string(ln) + " in file " + path);
-            by_chr[strip_chr_prefix(f[1])].del.v.push_back({atol(f[2].c_str()), atoi(f[3].c_str()), het});
+            chrom(f[1]).del.v.push_back({atol(f[2].c_str()), atoi(f[3].c_str()), het});
             P.n_del++;
         } else return fail("ERROR: unrecognized aberraton type at line " + std::to_string(ln) + " in file " + path);
     }
@@ -135,6 +149,7 @@ bool load_snps(Plan& P, const char* path, std::map<std::string, ChromVars>& by_c
     FILE* fp = fopen(path, "r");
     if (!fp) { P.err = std::string("can not open SNP file ") + path; return false; }
     char buf[1000]; long ln = 0;
+    ChromLookup chrom(by_chr);
     while (fgets(buf, sizeof buf, fp)) {
         ln++;
         char* col[8]; int nc = 0; col[nc++] = buf;
@@ -150,7 +165,7 @@ bool load_snps(Plan& P, const char* path, std::map<std::string, ChromVars>& by_c
         if (strand == '-') ref = snp_complement(ref);
         uint8_t nuc = (first == ref) ? second : first;
         if (strand == '-') nuc = snp_complement(nuc);
-        by_chr[strip_chr_prefix(col[1])].snp.v.push_back({(long)atoll(col[2]), (uint8_t)toupper(nuc), false});
+        chrom(col[1], strlen(col[1])).snp.v.push_back({(long)atoll(col[2]), (uint8_t)toupper(nuc), false});
         P.n_snp++;
     }
     fclose(fp);
@@ -163,7 +178,7 @@ bool load_snps(Plan& P, const char* path, std::map<std::string, ChromVars>& by_c
 struct Run { uint64_t src; uint64_t q; uint32_t len; };   // q: position in the segment's pre-indel string (reference runs only)
 
 class Rope {
-    static constexpr size_t kChunk = 512;
+    static constexpr size_t kChunk = 64;
     std::vector<std::vector<Run>> ch; std::vector<uint64_t> clen; uint64_t total = 0;
 
     // chunk holding position pos (pos == total -> last chunk), *base = first position of that chunk
@@ -219,7 +234,7 @@ class Rope {
         n = std::min(n, total - pos);
         if (n == 0) return true;
         size_t c1, p1, c2, p2;
-        boundary(pos + n, c2, p2); boundary(pos, c1, p1); boundary(pos + n, c2, p2);   // the second split may have moved the first
+        boundary(pos, c1, p1); boundary(pos + n, c2, p2);   // the second split lies behind the first: (c1, p1) stays valid
         if (c1 == c2) ch[c1].erase(ch[c1].begin() + p1, ch[c1].begin() + p2);
         else {
             ch[c1].resize(p1);
@@ -421,8 +436,13 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
     P = Plan(); P.ploidy = ploidy; P.chroms = chroms;
     if (ploidy < 1 || ploidy > 64) { P.err = "ERROR: ploidy out of range"; return false; }
     std::map<std::string, ChromVars> by_chr;
+    using clk = std::chrono::steady_clock;
+    auto ms_since = [](clk::time_point a) { return std::chrono::duration<double, std::milli>(clk::now() - a).count(); };
+    auto t0 = clk::now();
     if (!load_variations(P, var_file, by_chr)) return false;   // Genome::loadData order: loadAbers, loadSNPs, loadRefSeq (Genome.cpp:18-25)
+    P.ms_parse_var = ms_since(t0); t0 = clk::now();
     if (!load_snps(P, snp_file, by_chr)) return false;
+    P.ms_parse_snp = ms_since(t0); t0 = clk::now();
     if (chroms.empty()) { P.err = "ERROR: reference sequence cannot be empty!"; return false; }
     Planner pl(P, libc_seed, ploidy);
     const int mCN = (int)ceilf((float)ploidy / 2);
@@ -451,6 +471,8 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
             P.haps.push_back(h);
         }
     }
+    P.ms_segments = ms_since(t0);
+    if (getenv("SCS_TRACE")) fprintf(stderr, "[scs trace] simuvars plan: parse var %.1f ms, parse snp %.1f ms, segments %.1f ms\n", P.ms_parse_var, P.ms_parse_snp, P.ms_segments);
     return true;
 }
 

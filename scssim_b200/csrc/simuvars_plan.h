@@ -46,6 +46,7 @@ struct Plan {
     std::vector<Sub> subs;
     std::string literals;                // inserted sequences, upper-cased
     long n_cnv = 0, n_snv = 0, n_ins = 0, n_del = 0, n_snp = 0, n_segments = 0;
+    double ms_parse_var = 0, ms_parse_snp = 0, ms_segments = 0;
     std::string warnings;                // what the reference prints to stderr while loading
     std::string err;
 };
