@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <chrono>
+
 #include "ctx.h"
 
 namespace scs {
@@ -306,9 +308,13 @@ namespace {
 
 struct Round {
     scs_ctx* c; Genome g; uint32_t thr_ber;
-    DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
     uint64_t pending_count = 0, semi_len_sum_global = 0;
-    DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created, gbitmaps;
+    // scratch lives in the context: reused by every pass and every run
+    DevBuf<unsigned long long>&dcount, &ticket; DevBuf<int>& flags;
+    DevBuf<uint64_t>&slot_off, &cprefix, &tdesc, &terr; DevBuf<uint32_t>&tgc, &created, &gbitmaps;
+    explicit Round(scs_ctx* ctx) : c(ctx), dcount(ctx->ascratch.dcount), ticket(ctx->ascratch.ticket), flags(ctx->ascratch.flags), slot_off(ctx->ascratch.slot_off),
+                                   cprefix(ctx->ascratch.cprefix), tdesc(ctx->ascratch.tdesc), terr(ctx->ascratch.terr), tgc(ctx->ascratch.tgc),
+                                   created(ctx->ascratch.created), gbitmaps(ctx->ascratch.gbitmaps) {}
 
     int allreduce_u64(uint64_t* v, size_t n) { return scs::allreduce_u64(c, v, n); }
 
@@ -363,6 +369,9 @@ struct Round {
     // one amplification pass over `n` templates; products appended to `dst`
     template <bool FROM_FRAG>
     int pass(int round, uint64_t n, const uint64_t* desc, const uint32_t* primers, const uint64_t* errref, AmpList& dst, ListGeom& geom) {
+        const bool trace = getenv("SCS_TRACE") != nullptr;
+        auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double tr0 = now_ms(); double tr_alloc = 0, tr_kernel = 0, tr_scan = 0;
         uint64_t total_slots = 0;
         SCS_CUDA(c, slot_off.reserve(n + 1)); SCS_CUDA(c, cprefix.reserve(n + 1)); SCS_CUDA(c, created.reserve(n + 1));
         uint64_t made_total = 0;
@@ -377,6 +386,7 @@ struct Round {
             SCS_CUDA(c, c->err_pool.reserve(need, etop, c->st));
             SCS_CUDA(c, cudaMemsetAsync(flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(ticket.p, 0, 8, c->st));
             AmpParams ap = params(round, !FROM_FRAG, FROM_FRAG ? D_AMPF : D_AMPS);
+            if (trace) { cudaStreamSynchronize(c->st); tr_alloc = now_ms(); }
             int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             if (FROM_FRAG) {
                 constexpr int W = 8, BW = kSiteCap, CTAS = 5;
@@ -396,9 +406,11 @@ struct Round {
             int hflags = 0;
             SCS_CUDA(c, cudaMemcpyAsync(&hflags, flags.p, 4, cudaMemcpyDeviceToHost, c->st));
             SCS_CUDA(c, cudaStreamSynchronize(c->st));
+            tr_kernel = now_ms();
             if (hflags & 2) return c->fail(SCS_E_NOMEM, "amplify: error pool overflow");
             if (hflags & 1) return c->fail(SCS_E_UNSUPPORTED, "amplify: more than 96 substitutions on one amplicon");
             if (int rc = exclusive_scan_u32(c, created.p, cprefix.p, n, &made_total)) return rc;
+            tr_scan = now_ms();
         }
         // list geometry across ranks (see ListGeom): count this rank's products per sub-batch, exchange, derive offsets
         const int W = std::max(1, c->P.world), R = c->P.rank;
@@ -448,6 +460,9 @@ struct Round {
             SCS_CUDA(c, cudaStreamSynchronize(c->st));
         }
         dst.n = old + made_total; dst.batch_end.push_back(dst.n);
+        if (trace) fprintf(stderr, "[scs trace] amplify pass round %d from %s: %llu templates, %llu primers, %llu products | scan+alloc %.1f kernel %.1f scan %.1f geometry+append %.1f ms\n",
+                           round, FROM_FRAG ? "fragments" : "semis", (unsigned long long)n, (unsigned long long)total_slots, (unsigned long long)made_total,
+                           tr_alloc - tr0, tr_kernel - tr_alloc, tr_scan - tr_kernel, now_ms() - tr_scan);
         return SCS_OK;
     }
 };
@@ -458,7 +473,7 @@ int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     if (!c->have_frags) return c->fail(SCS_E_STATE, "scs_amplify: call scs_create_frags first");
     if (c->P.world > 1 && c->replay.on) return c->fail(SCS_E_UNSUPPORTED, "replay runs on one rank only (the reference's logs are sequential)");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
-    Round R; R.c = c; R.g = c->dev_genome();
+    Round R(c); R.g = c->dev_genome();
     R.thr_ber = (uint32_t)std::min<uint64_t>(count_unit_lt(3.4e-4), 0xFFFFFFFFull);
     SCS_CUDA(c, R.dcount.reserve(1)); SCS_CUDA(c, R.ticket.reserve(1)); SCS_CUDA(c, R.flags.reserve(1));
     // createPrimers (Malbac.cpp:36-81): 4^8 primer types, -p copies each

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -18,24 +20,38 @@ namespace scs {
 // short-lived scratch buffers of the stages free of device-wide synchronisation.
 inline cudaStream_t& alloc_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
-// growable device array (host-managed capacity)
+// growable device array (host-managed capacity). Small buffers come from the stream-ordered pool; buffers of kBigAlloc
+// bytes and more use plain cudaMalloc/cudaFree: on this platform a cold cudaMallocAsync of N GB costs ~250 ms per GB (and
+// 0.8 s for 10 GB even from a warm pool) against 3 ms for a 16 GB cudaMalloc (profiles/alloc_probe.cu, r01_alloc_probe.txt)
+// — at default gamma on a human-scale genome that was most of the amplification stage's time.
+constexpr size_t kBigAlloc = 32ull << 20;
 template <class T> struct DevBuf {
-    T* p = nullptr; size_t cap = 0;
+    T* p = nullptr; size_t cap = 0; bool big = false;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, alloc_stream()); p = nullptr; cap = 0; }
+    static void free_one(T* q, bool qbig) { if (!q) return; if (qbig) cudaFree(q); else cudaFreeAsync(q, alloc_stream()); }   // cudaFree waits for the device
+    void release() { free_one(p, big); p = nullptr; cap = 0; big = false; }
     // ensure capacity >= n, keeping the first `keep` elements
     cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t = 0) {
         if (n <= cap) return cudaSuccess;
         size_t ncap = n + n / 8 + 1024;
         T* q = nullptr;
-        cudaError_t e = cudaMallocAsync((void**)&q, ncap * sizeof(T), alloc_stream());
+        const bool qbig = ncap * sizeof(T) >= kBigAlloc;
+        static const bool trace = getenv("SCS_TRACE_ALLOC") != nullptr;
+        auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = trace ? now_ms() : 0;
+        cudaError_t e = qbig ? cudaMalloc((void**)&q, ncap * sizeof(T)) : cudaMallocAsync((void**)&q, ncap * sizeof(T), alloc_stream());
         if (e != cudaSuccess) return e;
-        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, alloc_stream()); if (e != cudaSuccess) { cudaFreeAsync(q, alloc_stream()); return e; } }
-        if (p) cudaFreeAsync(p, alloc_stream());
-        p = q; cap = ncap;
+        const double t1 = trace ? now_ms() : 0;
+        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, alloc_stream()); if (e != cudaSuccess) { free_one(q, qbig); return e; } }
+        if (trace && qbig) cudaStreamSynchronize(alloc_stream());
+        const double t2 = trace ? now_ms() : 0;
+        free_one(p, big);
+        if (trace && qbig) fprintf(stderr, "[scs trace] big alloc %.2f GB: malloc %.2f ms, copy of %.2f GB %.2f ms, free of old (%s, %.2f GB) %.2f ms\n", ncap * sizeof(T) / 1073741824.0, t1 - t0,
+                                   keep * sizeof(T) / 1073741824.0, t2 - t1, big ? "cudaFree" : "pool", cap * sizeof(T) / 1073741824.0, now_ms() - t2);
+        p = q; cap = ncap; big = qbig;
         return cudaSuccess;
     }
 };
@@ -78,7 +94,7 @@ struct AmpList {
     DevBuf<uint32_t> primers;  // semis only
     uint64_t n = 0;
     std::vector<uint64_t> batch_end;
-    void clear() { desc.release(); gc.release(); errref.release(); primers.release(); n = 0; batch_end.clear(); }
+    void clear() { n = 0; batch_end.clear(); }   // capacity is kept: a second run of the stage allocates nothing
 };
 
 struct ReplayDev {
@@ -98,6 +114,12 @@ struct DevProfile {
     DevBuf<uint32_t> qualDiag;   // [4][bins][kDiagW] compact diagonal rows for shared memory
     DevBuf<uint32_t> qualDiagPiv;    // [4][bins][4] pivots (entries 7, 15, 23, 31 of each compact row)
     DevBuf<uint32_t> qualDiagMeta;   // [4][bins]: lo | (n << 8) | (global-only << 16)
+};
+
+// persistent scratch of the amplification stage (per-template slot arrays, reused by every pass and every run)
+struct AmpScratch {
+    DevBuf<unsigned long long> dcount, ticket; DevBuf<int> flags;
+    DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created, gbitmaps;
 };
 
 // persistent scratch of the read stage (no allocation inside the slab loop)
@@ -145,6 +167,9 @@ struct scs_ctx {
     uint64_t reads_requested = 0, n_slots = 0;
 
     scs::ReadScratch rscratch;
+    scs::AmpScratch ascratch;
+    // staging buffers that keep their capacity between calls (cold device allocations are slow and erratic on this platform)
+    scs::DevBuf<uint8_t> genome_stage, sv_stage, sv_ref, sv_text[2];
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
     scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; scs_allreduce_dev_i64_fn ar_dev_i64 = nullptr; void* ar_dev_user = nullptr;

@@ -209,7 +209,9 @@ int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSr
     DevBuf<unsigned int> bad; SCS_CUDA(c, bad.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(bad.p, 0, 4, c->st));
     // stage ASCII through a bounded device buffer
     const uint64_t chunk = 256ull << 20;
-    DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(chunk + (chunk >> 4) + 4096));
+    DevBuf<uint8_t>& stage = c->genome_stage;
+    bool need_stage = false; for (int i = 0; i < n; i++) need_stage |= !src[i].dev;
+    if (need_stage) SCS_CUDA(c, stage.reserve(chunk + (chunk >> 4) + 4096));
     cudaEventRecord(e0, c->st);
     for (int i = 0; i < n; i++) {
         if (src[i].dev) {   // contiguous bases already in device memory (simuvars -> genome without a text round trip)

@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(kSvThreads) sv_scatter_kernel(const uint64_t* 
 }
 
 struct HapJob {
-    DevBuf<uint8_t> text; DevBuf<uint64_t> tables;
+    DevBuf<uint8_t> own_text; DevBuf<uint8_t>* text = &own_text;   // sink mode: one of the context's two persistent buffers
+    DevBuf<uint64_t> tables;
     uint64_t text_len = 0, n_bases = 0; std::string header; size_t hap_index = 0;
     cudaEvent_t done = nullptr;
     ~HapJob() { if (done) cudaEventDestroy(done); }
@@ -236,7 +237,7 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
         const uint64_t n_slabs = (J.text_len + kSlab - 1) / kSlab;
         auto issue = [&](uint64_t k) -> cudaError_t {
             const uint64_t off = k * kSlab, m = std::min(kSlab, J.text_len - off);
-            cudaError_t e = cudaMemcpyAsync(pinned[k & 1], J.text.p + off, m, cudaMemcpyDeviceToHost, c->st_copy);
+            cudaError_t e = cudaMemcpyAsync(pinned[k & 1], J.text->p + off, m, cudaMemcpyDeviceToHost, c->st_copy);
             return e != cudaSuccess ? e : cudaEventRecord(copied[k & 1], c->st_copy);
         };
         if (n_slabs) SCS_CUDA(c, issue(0));
@@ -252,7 +253,8 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
     };
 
     std::vector<std::unique_ptr<HapJob>> jobs;   // sink mode: at most two in flight; genome mode: all of this rank's haplotypes
-    std::unique_ptr<DevBuf<uint8_t>> dref;
+    DevBuf<uint8_t>* dref = &c->sv_ref;   // one buffer: the next chromosome's normalise is stream-ordered behind the kernels that read it
+    size_t n_jobs = 0;
     size_t drained = 0; long cur_chrom = -1;
     const auto t_dev0 = clk::now();
     for (size_t hi = 0; hi < plan.haps.size(); hi++) {
@@ -267,8 +269,8 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
                 if (r.regular && r.llen <= (1u << 20)) { blen = r.blen; llen = r.llen; nbytes = r.len + (r.len - 1) / blen * (llen - blen); }
                 else { ff.gather(H.chrom, gathered); src = gathered.data(); nbytes = gathered.size(); }
             }
-            DevBuf<uint8_t> stage; SCS_CUDA(c, stage.reserve(nbytes + 64));
-            dref.reset(new DevBuf<uint8_t>()); SCS_CUDA(c, dref->reserve(((r.len + 15) & ~15ull) + 64));
+            DevBuf<uint8_t>& stage = c->sv_stage; SCS_CUDA(c, stage.reserve(nbytes + 64));
+            SCS_CUDA(c, dref->reserve(((r.len + 15) & ~15ull) + 64));
             if (nbytes) SCS_CUDA(c, cudaMemcpyAsync(stage.p, src, nbytes, cudaMemcpyHostToDevice, c->st));
             S.h2d_bytes += nbytes;
             if (r.len) {
@@ -278,13 +280,15 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
                 timed_end();
                 S.normalize_bytes += nbytes + r.len;
             }
-            SCS_CUDA(c, cudaStreamSynchronize(c->st));   // `gathered` / `stage` go out of scope
+            SCS_CUDA(c, cudaStreamSynchronize(c->st));   // `gathered` goes out of scope
         }
         std::unique_ptr<HapJob> J(new HapJob());
         J->hap_index = hi; J->n_bases = H.len; J->header = ">" + H.name + "\n";
         J->text_len = W ? H.len + (H.len + W - 1) / W : H.len;
         const uint64_t np = H.piece_hi - H.piece_lo, ns = H.sub_hi - H.sub_lo;
-        SCS_CUDA(c, J->text.reserve(((J->text_len + 15) & ~15ull) + 64));
+        if (!to_genome) J->text = &c->sv_text[n_jobs & 1];   // the job two back has been drained (host-synchronously) by now
+        n_jobs++;
+        SCS_CUDA(c, J->text->reserve(((J->text_len + 15) & ~15ull) + 64));
         SCS_CUDA(c, cudaEventCreateWithFlags(&J->done, cudaEventDisableTiming));
         if (H.len) {
             const uint64_t nblk = (H.len >> kSvBlockShift) + 1;
@@ -306,11 +310,11 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
             SCS_CUDA(c, cudaMemcpyAsync(J->tables.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->st));
             SCS_CUDA(c, cudaStreamSynchronize(c->st));   // `tab` is pageable and goes out of scope
             S.h2d_bytes += tab.size() * 8;
-            SvHapArgs A; A.pout = J->tables.p; A.psrc = J->tables.p + np + 1; A.blk = reinterpret_cast<const uint32_t*>(J->tables.p + 2 * np + 1 + ns); A.n_pieces = (uint32_t)np; A.W = W; A.n_bases = H.len; A.text_len = J->text_len; A.text = J->text.p;
+            SvHapArgs A; A.pout = J->tables.p; A.psrc = J->tables.p + np + 1; A.blk = reinterpret_cast<const uint32_t*>(J->tables.p + 2 * np + 1 + ns); A.n_pieces = (uint32_t)np; A.W = W; A.n_bases = H.len; A.text_len = J->text_len; A.text = J->text->p;
             timed_begin();
             sv_materialize_kernel<<<(unsigned)((J->text_len + 16 * kSvThreads - 1) / (16 * kSvThreads)), kSvThreads, 0, c->st>>>(A);
             SCS_LAUNCHED(c); S.launches++;
-            if (ns) { sv_scatter_kernel<<<(unsigned)((ns + kSvThreads - 1) / kSvThreads), kSvThreads, 0, c->st>>>(J->tables.p + 2 * np + 1, ns, W, J->text.p); SCS_LAUNCHED(c); S.launches++; }
+            if (ns) { sv_scatter_kernel<<<(unsigned)((ns + kSvThreads - 1) / kSvThreads), kSvThreads, 0, c->st>>>(J->tables.p + 2 * np + 1, ns, W, J->text->p); SCS_LAUNCHED(c); S.launches++; }
             timed_end();
             S.materialize_bytes += H.len + J->text_len + 16 * np + 9 * ns + 4 * nblk;
         }
@@ -328,7 +332,7 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
     if (to_genome) {
         std::vector<const char*> names; std::vector<SeqSrc> srcs; std::vector<std::string> keep;
         for (auto& J : jobs) keep.push_back(plan.haps[J->hap_index].name);
-        for (size_t i = 0; i < jobs.size(); i++) { names.push_back(keep[i].c_str()); srcs.push_back({(const char*)jobs[i]->text.p, jobs[i]->n_bases, 0, 0, true}); }
+        for (size_t i = 0; i < jobs.size(); i++) { names.push_back(keep[i].c_str()); srcs.push_back({(const char*)jobs[i]->text->p, jobs[i]->n_bases, 0, 0, true}); }
         if (names.empty()) {
             c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear(); c->ref_len_sum = 0; c->ref_len_half = 0; c->genome_bases = 0;
             SCS_CUDA(c, c->genome_words.reserve(2)); SCS_CUDA(c, c->genome_nmask.reserve(2));
