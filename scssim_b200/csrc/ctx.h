@@ -31,7 +31,8 @@ template <class T> struct DevBuf {
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    static void free_one(T* q, bool qbig) { if (!q) return; if (qbig) cudaFree(q); else cudaFreeAsync(q, alloc_stream()); }   // cudaFree waits for the device
+    // cudaFree waits for the device by itself, but measurably slower (100s of ms at times) than when the stream is drained first
+    static void free_one(T* q, bool qbig) { if (!q) return; if (qbig) { cudaStreamSynchronize(alloc_stream()); cudaFree(q); } else cudaFreeAsync(q, alloc_stream()); }
     void release() { free_one(p, big); p = nullptr; cap = 0; big = false; }
     // ensure capacity >= n, keeping the first `keep` elements
     cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t = 0) {
