@@ -12,6 +12,7 @@
 #include "../../include/scssim_b200.h"
 #include "device_common.cuh"
 #include "profile_host.h"
+#include "vmm.h"
 
 namespace scs {
 
@@ -20,39 +21,61 @@ namespace scs {
 // short-lived scratch buffers of the stages free of device-wide synchronisation.
 inline cudaStream_t& alloc_stream() { static thread_local cudaStream_t s = nullptr; return s; }
 
-// growable device array (host-managed capacity). Small buffers come from the stream-ordered pool; buffers of kBigAlloc
-// bytes and more use plain cudaMalloc/cudaFree: on this platform a cold cudaMallocAsync of N GB costs ~250 ms per GB (and
-// 0.8 s for 10 GB even from a warm pool) against 3 ms for a 16 GB cudaMalloc (profiles/alloc_probe.cu, r01_alloc_probe.txt)
-// — at default gamma on a human-scale genome that was most of the amplification stage's time.
-constexpr size_t kBigAlloc = 32ull << 20;
+// growable device array (host-managed capacity). Small buffers come from the stream-ordered pool. Buffers of big_alloc_bytes()
+// and more live on a reserved virtual range that is extended in place (vmm.h): growth neither reallocates nor copies. On
+// this platform a cold cudaMallocAsync costs ~250 ms per GB (0.8 s for 10 GB even from a warm pool) and cudaMalloc/cudaFree
+// of GB-sized blocks in a live context 10s-100s of ms, erratically (profiles/alloc_probe.cu, r01_alloc_probe.txt) — at the
+// default gamma on a human-scale genome that was most of the amplification stage's time. Without the VMM entry points the
+// big buffers fall back to cudaMalloc + copy.
+inline size_t big_alloc_bytes() {
+    static const size_t v = [] { const char* e = getenv("SCS_BIG_ALLOC_BYTES"); return e ? (size_t)strtoull(e, nullptr, 0) : (size_t)(32ull << 20); }();
+    return v;
+}
+constexpr size_t kVmmReserve = 192ull << 30;   // address space per big buffer (more than one B200's HBM)
 template <class T> struct DevBuf {
-    T* p = nullptr; size_t cap = 0; bool big = false;
+    T* p = nullptr; size_t cap = 0; bool big = false; VmmRange* vmm = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     // cudaFree waits for the device by itself, but measurably slower (100s of ms at times) than when the stream is drained first
     static void free_one(T* q, bool qbig) { if (!q) return; if (qbig) { cudaStreamSynchronize(alloc_stream()); cudaFree(q); } else cudaFreeAsync(q, alloc_stream()); }
-    void release() { free_one(p, big); p = nullptr; cap = 0; big = false; }
+    void release() {
+        if (vmm) { cudaDeviceSynchronize(); vmm->release(); delete vmm; vmm = nullptr; }
+        else free_one(p, big);
+        p = nullptr; cap = 0; big = false;
+    }
     // ensure capacity >= n, keeping the first `keep` elements
     cudaError_t reserve(size_t n, size_t keep = 0, cudaStream_t = 0) {
         if (n <= cap) return cudaSuccess;
         size_t ncap = n + n / 8 + 1024;
+        if (vmm) {   // extend in place: contents stay where they are
+            cudaError_t e = vmm->grow(ncap * sizeof(T));
+            if (e != cudaSuccess) return e;
+            cap = vmm->mapped / sizeof(T);
+            return cudaSuccess;
+        }
         T* q = nullptr;
-        const bool qbig = ncap * sizeof(T) >= kBigAlloc;
-        static const bool trace = getenv("SCS_TRACE_ALLOC") != nullptr;
-        auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        const double t0 = trace ? now_ms() : 0;
-        cudaError_t e = qbig ? cudaMalloc((void**)&q, ncap * sizeof(T)) : cudaMallocAsync((void**)&q, ncap * sizeof(T), alloc_stream());
-        if (e != cudaSuccess) return e;
-        const double t1 = trace ? now_ms() : 0;
-        if (p && keep) { e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, alloc_stream()); if (e != cudaSuccess) { free_one(q, qbig); return e; } }
-        if (trace && qbig) cudaStreamSynchronize(alloc_stream());
-        const double t2 = trace ? now_ms() : 0;
+        const bool qbig = ncap * sizeof(T) >= big_alloc_bytes();
+        VmmRange* v = nullptr;
+        cudaError_t e;
+        if (qbig && VmmRange::available()) {
+            v = new VmmRange();
+            e = v->init(kVmmReserve);
+            if (e == cudaSuccess) e = v->grow(ncap * sizeof(T));
+            if (e != cudaSuccess) { v->release(); delete v; v = nullptr; }
+            else { q = reinterpret_cast<T*>(v->base); ncap = v->mapped / sizeof(T); }
+        }
+        if (!v) {
+            e = qbig ? cudaMalloc((void**)&q, ncap * sizeof(T)) : cudaMallocAsync((void**)&q, ncap * sizeof(T), alloc_stream());
+            if (e != cudaSuccess) return e;
+        }
+        if (p && keep) {
+            e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, alloc_stream());
+            if (e != cudaSuccess) { if (v) { v->release(); delete v; } else free_one(q, qbig); return e; }
+        }
         free_one(p, big);
-        if (trace && qbig) fprintf(stderr, "[scs trace] big alloc %.2f GB: malloc %.2f ms, copy of %.2f GB %.2f ms, free of old (%s, %.2f GB) %.2f ms\n", ncap * sizeof(T) / 1073741824.0, t1 - t0,
-                                   keep * sizeof(T) / 1073741824.0, t2 - t1, big ? "cudaFree" : "pool", cap * sizeof(T) / 1073741824.0, now_ms() - t2);
-        p = q; cap = ncap; big = qbig;
+        p = q; cap = ncap; big = qbig && !v; vmm = v;
         return cudaSuccess;
     }
 };

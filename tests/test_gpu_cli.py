@@ -104,3 +104,23 @@ def test_fasta_layouts_load_identically(tmp_path):
     assert len(outs[0][0]) > 0
     for o in outs[1:]:
         assert o == outs[0]
+
+
+def test_cli_with_every_buffer_on_virtual_memory(tmp_path):
+    """SCS_BIG_ALLOC_BYTES=64 KiB pushes practically every device buffer onto the grow-in-place VMM path that human-scale runs
+    use for their multi-GB arrays (vmm.h): same FASTQ as the oracle, simuvars included."""
+    tmp = str(tmp_path)
+    env = dict(os.environ, SCS_BIG_ALLOC_BYTES="65536")
+    ref, snp, var = H.make_simuvars_case(tmp, 41, chrom_lens=(150_000, 60_000), n_cnv=3)
+    H.run_oracle_simuvars(ref, snp, var, os.path.join(tmp, "orc_cell.fa"))
+    r = subprocess.run([EXE, "simuvars", "-r", ref, "-s", snp, "-v", var, "-o", os.path.join(tmp, "cell.fa")], capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    assert H.read_bytes(os.path.join(tmp, "cell.fa")) == H.read_bytes(os.path.join(tmp, "orc_cell.fa"))
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, "PE", 1e-9, 5.0, 260)          # default gamma: the lists grow over several passes
+    fa = os.path.join(tmp, "cell.fa")
+    H.run_oracle(fa, os.path.join(tmp, "orc"), args, seed=808)
+    r = subprocess.run([EXE, "genreads", "-i", fa, "-o", os.path.join(tmp, "gpu"), "--seed", "808"] + args, capture_output=True, env=env)
+    assert r.returncode == 0, r.stderr.decode()
+    for a, b in zip(H.fastq_names(os.path.join(tmp, "gpu"), "PE"), H.fastq_names(os.path.join(tmp, "orc"), "PE")):
+        assert len(H.read_bytes(a)) > 100_000 and H.read_bytes(a) == H.read_bytes(b)
