@@ -214,6 +214,11 @@ int scs_profile_thresholds(const scs_ctx* ctx, int which, int idx, int row, uint
 /* Host-side shard arithmetic (no GPU needed): contiguous range [*lo, *hi) of `n` units for `rank`. */
 void scs_shard_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi);
 
+/* Which contiguous run [*lo, *hi) of the cell's n sequences rank keeps when a FASTA (scs_load_genome) or a simulated cell
+ * (scs_simuvars_to_genome) is sharded: cut where the cumulative length crosses rank/world of the total, sequence midpoints
+ * decide, so every rank holds about the same number of bases. Host-only. */
+void scs_shard_sequences(const uint64_t* lens, size_t n, int rank, int world, size_t* lo, size_t* hi);
+
 const char* scs_version(void);
 
 #ifdef __cplusplus

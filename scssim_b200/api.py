@@ -88,7 +88,7 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
-           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand"]
+           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences"]
 
 _lib = None
 
@@ -144,6 +144,8 @@ def lib():
         L.scs_svplan_dump.restype = C.c_int64
         L.scs_svplan_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.scs_test_libc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+        L.scs_shard_sequences.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.scs_shard_sequences.restype = None
         _lib = L
     return _lib
 
@@ -151,6 +153,14 @@ def lib():
 def shard_range(n: int, rank: int, world: int):
     lo, hi = C.c_uint64(), C.c_uint64()
     lib().scs_shard_range(n, rank, world, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def shard_sequences(lens, rank: int, world: int):
+    """[lo, hi) of the sequences `rank` keeps when a cell of these sequence lengths is sharded over `world` GPUs."""
+    a = np.ascontiguousarray(lens, dtype=np.uint64)
+    lo, hi = C.c_size_t(), C.c_size_t()
+    lib().scs_shard_sequences(a.ctypes.data, len(a), rank, world, C.byref(lo), C.byref(hi))
     return lo.value, hi.value
 
 

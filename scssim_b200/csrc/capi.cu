@@ -192,6 +192,10 @@ int64_t scs_svplan_dump(const scs_svplan* h, int what, void* buf, uint64_t cap) 
     if (need) memcpy(buf, src, need);
     return (int64_t)need;
 }
+void scs_shard_sequences(const uint64_t* lens, size_t n, int rank, int world, size_t* lo, size_t* hi) {
+    std::vector<uint64_t> v(lens, lens + n);
+    shard_by_midpoint(v, rank, world < 1 ? 1 : world, lo, hi);
+}
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out) {
     if (!out || n < 0) return SCS_E_ARG;
     sv::LibcRand r(seed);

@@ -68,3 +68,44 @@ def test_collectives_and_list_geometry_world2():
     all_idx = sorted(res[0][3] + res[1][3])
     assert all_idx == list(range(res[0][4]))
     assert res[0][3][:3] == [2 + 0, 2 + 1, 2 + 2] and res[1][3][:2] == [0, 1]   # batch 0: rank 1's 2 products precede rank 0's 3
+
+
+def _shard_worker(rank, world, port, q):
+    """Every rank works out its own share of the cell's haplotypes (as scs_simuvars_to_genome / scs_load_genome do) and
+    the shares are gathered over gloo: together they must cover every sequence exactly once, in rank order."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scssim_b200 import api
+    lens = [248_956_422, 248_956_422, 242_193_529, 242_193_529, 198_295_559, 198_295_559, 1000, 0, 57_227_415]
+    lo, hi = api.shard_sequences(lens, rank, world)
+    mine = torch.tensor([lo, hi, sum(lens[lo:hi])], dtype=torch.int64)
+    out = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine)
+    q.put((rank, [o.tolist() for o in out], len(lens), sum(lens)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sequence_sharding_partitions_the_cell(world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    _, shares, n, total = res[0]
+    assert all(r[1] == shares for r in res)                      # every rank sees the same picture
+    assert shares[0][0] == 0 and shares[-1][1] == n
+    for a, b in zip(shares, shares[1:]):
+        assert a[1] == b[0]                                       # contiguous, in rank order, no gaps or overlaps
+    assert sum(s[2] for s in shares) == total
+    assert max(s[2] for s in shares) < 1.6 * total / world        # about balanced by bases
+
+
+def test_sequence_sharding_more_ranks_than_sequences():
+    from scssim_b200 import api
+    got = [api.shard_sequences([100, 100], r, 5) for r in range(5)]
+    owned = [g for g in got if g[1] > g[0]]
+    assert sorted(owned) == [(0, 1), (1, 2)] and all(g == (0, 0) for g in got if g[1] == g[0])
