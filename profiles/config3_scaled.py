@@ -14,7 +14,7 @@ nseq = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 t_s = time.time()
 named = [(f"chrS{i + 1}_1_{glen}", synth_sequence(glen, 4242 + i)) for i in range(nseq)]
 t_synth = time.time() - t_s
-with api.GenReads(gamma=1e-9, coverage=10.0, layout="SE", seed=3, slab_bytes=64 << 20) as g:
+with api.GenReads(gamma=1e-9, coverage=10.0, layout="SE", seed=3, slab_bytes=int(os.environ.get("SLAB_MB", "64")) << 20) as g:
     g.load_profile(H.profile_path("Illumina_HiSeq2000"))
     t0 = time.time(); g.set_genome(named).create_frags(); t1 = time.time()
     g.amplify(); t2 = time.time()
@@ -25,5 +25,5 @@ out = {"genome_len": glen * nseq, "n_sequences": nseq, "host_synth_s": t_synth, 
         "gamma": 1e-9, "frags": st["n_frags"], "semis": st["n_semis"], "fulls": st["n_fulls"], "records": st["records"],
        "ms": {"pack+frags": (t1 - t0) * 1e3, "amplify": st["ms_amplify"], "alloc": st["ms_alloc"], "reads": st["ms_reads"]},
        "amplicons_per_s": (st["n_semis"] + st["n_fulls"]) / (st["ms_amplify"] / 1e3),
-       "reads_per_s": st["records"] / (st["ms_reads"] / 1e3), "fastq_bytes": st["fastq_bytes"], "primers_left": st["total_primers_left"]}
+       "reads_per_s": st["records"] / (st["ms_reads"] / 1e3), "ms_reads_kernels": st["ms_reads_kernels"], "ms_emit_kernel": st["ms_emit_kernel"], "emit_launches": st["emit_launches"], "fastq_bytes": st["fastq_bytes"], "primers_left": st["total_primers_left"]}
 print(json.dumps(out))

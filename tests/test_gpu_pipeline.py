@@ -82,3 +82,42 @@ def test_genome_with_n_iupac_and_lowercase(tmp_path, layout):
     # never bind, countGC() = 0 for windows with N, reads over N emit 'N' with Q in [33,53) and consume draws differently
     st = _run_case(str(tmp_path), "withn" + layout, 1, 300_000, 77, "Illumina_HiSeq2500", layout, 3e-10, 6.0, 260, seed=9, with_n=True)
     assert st["records"] > 0
+
+
+def test_degenerate_inputs_match_the_oracle(tmp_path):
+    """Edge cases: (1) only sequences shorter than the 1027-base amplification minimum -> no amplicons, empty FASTQ (the
+    reference itself crashes on an empty amplicon list; oracle and library write empty files); (2) a coverage that rounds to
+    zero reads; (3) an empty record between two sequences and a last line without a terminator."""
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_sequence, write_fasta
+    d = str(tmp_path)
+    prof = H.profile_path("Illumina_HiSeq2500")
+
+    def both(fa, tag, layout, gamma, cov):
+        args = H.genreads_args(prof, layout, gamma, cov, 260)
+        H.run_oracle(fa, os.path.join(d, tag), args, seed=5)
+        with api.GenReads(gamma=gamma, coverage=cov, layout=layout, seed=5) as g:
+            g.load_profile(prof).load_genome(fa).create_frags().amplify()
+            got = g.yield_reads_bytes()
+            st = g.stats()
+        exp = [H.read_bytes(p) for p in H.fastq_names(os.path.join(d, tag), layout)]
+        assert list(got[:len(exp)]) == exp, tag
+        return st, exp
+
+    fa1 = os.path.join(d, "short.fa")
+    write_fasta(fa1, [("chrA_1_900", synth_sequence(900, 1)), ("chrB_1_500", synth_sequence(500, 2))])
+    st, exp = both(fa1, "short", "PE", 1e-8, 5.0)
+    assert st["n_fulls"] == 0 and exp == [b"", b""]
+
+    fa2 = os.path.join(d, "g.fa")
+    write_fasta(fa2, [("chrA_1_60000", synth_sequence(60000, 3))])
+    st, exp = both(fa2, "nocov", "SE", 2e-10, 0.001)
+    assert st["reads_requested"] == 0 and exp == [b""]
+
+    fa3 = os.path.join(d, "gap.fa")
+    a, b = synth_sequence(40_000, 4), synth_sequence(30_011, 5)
+    with open(fa3, "wb") as f:
+        f.write(b">chrA_1_40000\n" + b"\n".join(a[i:i + 80].tobytes() for i in range(0, len(a), 80)) + b"\n>chrE_1_0\n>chrB_1_30011\n" +
+                b"\n".join(b[i:i + 80].tobytes() for i in range(0, len(b), 80)))       # no newline at the end of the file
+    st, exp = both(fa3, "gap", "PE", 5e-10, 6.0)
+    assert st["n_fulls"] > 0 and len(exp[0]) > 10_000
