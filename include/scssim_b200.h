@@ -164,7 +164,8 @@ enum scs_svplan_dump { SCS_SVP_HAPS = 0,      /* u64 x7 per haplotype: chrom, ha
                        SCS_SVP_PIECES = 1,    /* u64 x3 per piece: out offset, source (bit 63: literal pool), length */
                        SCS_SVP_SUBS = 2,      /* u64 x2 per substitution: out offset, base */
                        SCS_SVP_LITERALS = 3,  /* bytes */
-                       SCS_SVP_NAMES = 4      /* record names, '\n' separated */ };
+                       SCS_SVP_NAMES = 4,     /* record names, '\n' separated */
+                       SCS_SVP_WARNINGS = 5   /* what the reference prints while loading (malformed SNP lines) */ };
 int64_t scs_svplan_dump(const scs_svplan* plan, int what, void* buf, uint64_t cap);
 /* The first n values of libc rand() after srand(seed), as reproduced by the library. */
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out);

@@ -437,7 +437,7 @@ class GenReads:
 
 
 # --- simuvars edit plan, host only (test hook) ---------------------------------------------------------
-SVP_HAPS, SVP_PIECES, SVP_SUBS, SVP_LITERALS, SVP_NAMES = range(5)
+SVP_HAPS, SVP_PIECES, SVP_SUBS, SVP_LITERALS, SVP_NAMES, SVP_WARNINGS = range(6)
 SV_LITERAL = 1 << 63
 
 
@@ -480,6 +480,10 @@ class SimuVarsPlan:
     @property
     def names(self):
         return self._dump(SVP_NAMES).tobytes().decode().split("\n")[:-1]
+
+    @property
+    def warnings(self):
+        return self._dump(SVP_WARNINGS).tobytes().decode()
 
     def close(self):
         if getattr(self, "_h", None):

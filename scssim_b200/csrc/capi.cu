@@ -184,9 +184,10 @@ int64_t scs_svplan_dump(const scs_svplan* h, int what, void* buf, uint64_t cap) 
         case SCS_SVP_SUBS: for (auto& x : P.subs) { v.insert(v.end(), {x.out, (uint64_t)x.ch}); } break;
         case SCS_SVP_LITERALS: s = P.literals; break;
         case SCS_SVP_NAMES: for (auto& x : P.haps) { s += x.name; s += '\n'; } break;
+        case SCS_SVP_WARNINGS: s = P.warnings; break;
         default: return SCS_E_ARG;
     }
-    if (what == SCS_SVP_LITERALS || what == SCS_SVP_NAMES) { src = s.data(); need = s.size(); } else { src = v.data(); need = v.size() * 8; }
+    if (what == SCS_SVP_LITERALS || what == SCS_SVP_NAMES || what == SCS_SVP_WARNINGS) { src = s.data(); need = s.size(); } else { src = v.data(); need = v.size() * 8; }
     if (!buf) return (int64_t)need;
     if (cap < need) return SCS_E_ARG;
     if (need) memcpy(buf, src, need);

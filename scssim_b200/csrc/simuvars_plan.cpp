@@ -2,7 +2,9 @@
 #include "simuvars_plan.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -143,32 +145,89 @@ uint8_t snp_complement(uint8_t c) {   // SNP::getComplement, snp.cpp:96-110
     }
 }
 
-// SNPOnChr::readSNPs + SNP::SNP, snp.cpp:13-36,147-203: id, chromosome, position, observed "X/Y", strand, reference base
+// SNPOnChr::readSNPs + SNP::SNP, snp.cpp:13-36,147-203: id, chromosome, position, observed "X/Y", strand, reference base.
+// One line [s, e) of the file (e points at the '\n' or at the end of the file); tabs are overwritten with NULs in place.
+// Returns false for a line the reference warns about and skips.
+struct SnpRec { const char* chrom; size_t chrom_len; PointVar v; };
+bool parse_snp_line(char* s, char* e, SnpRec& out) {
+    char* col[8]; int nc = 0; col[nc++] = s;
+    bool too_many = false;
+    for (char* p = s; p < e; p++) if (*p == '\t') { *p = 0; if (nc < 8) col[nc++] = p + 1; else too_many = true; }
+    if (nc != 6 || too_many) return false;
+    const char* slash = (const char*)memchr(col[3], '/', strlen(col[3]));
+    if (!slash || slash == col[3] || slash[1] == 0) return false;
+    const uint8_t first = (uint8_t)col[3][0], second = (uint8_t)slash[1];
+    const uint8_t strand = (uint8_t)*col[4];
+    uint8_t ref = (uint8_t)*col[5];   // an empty last field reads the line terminator, as the reference's fgets buffer does
+    if (strand == '-') ref = snp_complement(ref);
+    uint8_t nuc = (first == ref) ? second : first;
+    if (strand == '-') nuc = snp_complement(nuc);
+    char save = *e; *e = 0; const long pos = (long)atoll(col[2]); *e = save;
+    out.chrom = col[1]; out.chrom_len = strlen(col[1]);
+    out.v = {pos, (uint8_t)toupper(nuc), false};
+    return true;
+}
+
 bool load_snps(Plan& P, const char* path, std::map<std::string, ChromVars>& by_chr) {
     if (!path || !*path) return true;
-    FILE* fp = fopen(path, "r");
+    FILE* fp = fopen(path, "rb");
     if (!fp) { P.err = std::string("can not open SNP file ") + path; return false; }
-    char buf[1000]; long ln = 0;
-    ChromLookup chrom(by_chr);
-    while (fgets(buf, sizeof buf, fp)) {
-        ln++;
-        char* col[8]; int nc = 0; col[nc++] = buf;
-        bool too_many = false;
-        for (char* p = buf; *p; p++) if (*p == '\t') { *p = 0; if (nc < 8) col[nc++] = p + 1; else too_many = true; }
-        const char* slash = (nc == 6 && !too_many) ? strchr(col[3], '/') : nullptr;
-        if (nc != 6 || too_many || !slash || slash == col[3] || slash[1] == 0) {
-            if (P.warnings.size() < 4096) P.warnings += std::string("Warning: malformed snp file ") + path + ", there should be 6 fields @line " + std::to_string(ln) + "\n";
-            continue;
-        }
-        uint8_t first = (uint8_t)col[3][0], second = (uint8_t)slash[1];
-        uint8_t strand = (uint8_t)*col[4], ref = (uint8_t)*col[5];
-        if (strand == '-') ref = snp_complement(ref);
-        uint8_t nuc = (first == ref) ? second : first;
-        if (strand == '-') nuc = snp_complement(nuc);
-        chrom(col[1], strlen(col[1])).snp.v.push_back({(long)atoll(col[2]), (uint8_t)toupper(nuc), false});
-        P.n_snp++;
-    }
+    fseek(fp, 0, SEEK_END); const long long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+    std::vector<char> buf((size_t)std::max<long long>(sz, 0) + 2, 0);
+    const size_t got = sz > 0 ? fread(buf.data(), 1, (size_t)sz, fp) : 0;
     fclose(fp);
+    buf[got] = 0;
+    // chunks of whole lines, one per thread; every chunk keeps its records per chromosome in file order
+    unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("SCS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    const size_t nchunk = got >= (4u << 20) ? hw : 1;
+    std::vector<size_t> cut(nchunk + 1, got); cut[0] = 0;
+    for (size_t k = 1; k < nchunk; k++) {
+        size_t p = std::max(cut[k - 1], got * k / nchunk);
+        const char* nl = p < got ? (const char*)memchr(buf.data() + p, '\n', got - p) : nullptr;
+        cut[k] = nl ? (size_t)(nl - buf.data()) + 1 : got;
+    }
+    struct ChunkOut { std::vector<std::pair<std::string, std::vector<PointVar>>> by; std::vector<long> bad_lines; long n_lines = 0; bool long_line = false; };
+    std::vector<ChunkOut> outs(nchunk);
+    auto work = [&](size_t k) {
+        ChunkOut& o = outs[k];
+        char* s = buf.data() + cut[k]; char* const end = buf.data() + cut[k + 1];
+        size_t last = (size_t)-1;
+        while (s < end) {
+            char* e = (char*)memchr(s, '\n', (size_t)(end - s));
+            if (!e) e = end;
+            o.n_lines++;
+            if (e - s >= 999) o.long_line = true;   // the reference's fgets(buf, 1000) would split this line
+            SnpRec r;
+            if (!parse_snp_line(s, e, r)) o.bad_lines.push_back(o.n_lines);
+            else {
+                if (last == (size_t)-1 || o.by[last].first.size() != r.chrom_len || memcmp(o.by[last].first.data(), r.chrom, r.chrom_len) != 0) {
+                    last = (size_t)-1;
+                    for (size_t i = 0; i < o.by.size(); i++) if (o.by[i].first.size() == r.chrom_len && memcmp(o.by[i].first.data(), r.chrom, r.chrom_len) == 0) { last = i; break; }
+                    if (last == (size_t)-1) { o.by.emplace_back(std::string(r.chrom, r.chrom_len), std::vector<PointVar>()); last = o.by.size() - 1; }
+                }
+                o.by[last].second.push_back(r.v);
+            }
+            s = e + 1;
+        }
+    };
+    if (nchunk == 1) work(0);
+    else {
+        std::vector<std::thread> ts;
+        for (size_t k = 0; k < nchunk; k++) ts.emplace_back(work, k);
+        for (auto& t : ts) t.join();
+    }
+    long line0 = 0;
+    for (ChunkOut& o : outs) {
+        if (o.long_line) { P.err = std::string("ERROR: line longer than 999 characters in SNP file ") + path; return false; }
+        for (long b : o.bad_lines) if (P.warnings.size() < 4096) P.warnings += std::string("Warning: malformed snp file ") + path + ", there should be 6 fields @line " + std::to_string(line0 + b) + "\n";
+        for (auto& kv : o.by) {
+            std::vector<PointVar>& dst = by_chr[strip_chr_prefix(kv.first)].snp.v;
+            dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+            P.n_snp += (long)kv.second.size();
+        }
+        line0 += o.n_lines;
+    }
     return true;
 }
 
@@ -278,46 +337,58 @@ void hap_append(HapBuild& h, uint64_t src, uint32_t len) {
     h.pieces.push_back({h.len, src, len}); h.len += len;
 }
 
-struct Planner {
-    Plan& P; LibcRand rng; int ploidy;
-    std::vector<uint32_t> hits;
-    Planner(Plan& p, uint32_t seed, int pl) : P(p), rng(seed), ploidy(pl) {}
+// what the random draws decide for one segment: how many copies each haplotype carries and which haplotypes are "major"
+struct SegSpec { long s, e; std::vector<int> copies; std::vector<char> in_major; };
 
-    // Genome::generateSegment, Genome.cpp:388-691, for the 1-based inclusive chromosome range [s, e]
-    bool segment(std::vector<HapBuild>& hap, ChromVars* cv, const std::string& chr, long chrLen, long s, long e, int CN, int mCN) {
-        if (CN == 0) return true;
-        if (s - 1 < 0 || e - s + 1 < 1) { P.err = "Error: cannot construct subsequence with negative offset or length < 1"; return false; }
-        if (e > chrLen) { P.err = "ERROR: segment " + std::to_string(s) + "-" + std::to_string(e) + " lies past the end of chromosome " + chr; return false; }
-        const unsigned int refSize = (unsigned int)(e - s + 1);
-        P.n_segments++;
-        int i, j, k, n;
-        std::vector<int> major, reps;
-        auto has = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
-        std::vector<int> copies(ploidy, 0);   // how many copies of the segment each haplotype carries
-
-        if (CN < ploidy) {   // :411-425: CN distinct haplotypes keep one copy, the first mCN drawn are the major ones
-            for (i = 0; i < CN; i++) for (;;) { j = (int)rng.integer(0, ploidy); if (!has(reps, j)) { reps.push_back(j); break; } }
-            for (i = 0; i < mCN; i++) major.push_back(reps[i]);
-            for (int h : reps) copies[h] = 1;
-        } else {             // :426-467
-            reps.assign(ploidy, 1);
-            n = CN - ploidy;
-            k = (int)rng.integer(0, ploidy);
-            for (i = n; i >= 0; i--) {
-                if (reps[k] + i == mCN) { reps[k] += i; major.push_back(k); break; }
-                else if (reps[k] + i == CN - mCN) { reps[k] += i; for (j = 0; j < ploidy; j++) if (j != k) major.push_back(j); break; }
-            }
-            if (i >= 0) {
-                n -= i;
-                if (n > 0 && ploidy < 2) { P.err = "ERROR: copy number cannot be distributed over one haplotype"; return false; }   // reference: endless loop
-                while (n > 0) { j = (int)rng.integer(0, ploidy); if (j != k) { reps[j]++; n--; } }
-            } else {
-                while (n > 0) { j = (int)rng.integer(0, ploidy); reps[j]++; n--; }
-                for (i = 0; i < ploidy; i++) major.push_back(i);
-            }
-            copies = reps;
+// The draws of Genome::generateSegment (Genome.cpp:404-467) for the 1-based inclusive range [s, e]. Sequential: libc rand()
+// is one stream over all segments of all chromosomes. Returns false with err set; *skip = true for CN == 0 (nothing emitted).
+bool assign_copies(LibcRand& rng, int ploidy, const std::string& chr, long chrLen, long s, long e, int CN, int mCN, SegSpec& out, bool* skip, std::string& err) {
+    *skip = false;
+    if (CN == 0) { *skip = true; return true; }
+    if (s - 1 < 0 || e - s + 1 < 1) { err = "Error: cannot construct subsequence with negative offset or length < 1"; return false; }
+    if (e > chrLen) { err = "ERROR: segment " + std::to_string(s) + "-" + std::to_string(e) + " lies past the end of chromosome " + chr; return false; }
+    int i, j, k, n;
+    std::vector<int> major, reps;
+    auto has = [](const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    std::vector<int> copies(ploidy, 0);   // how many copies of the segment each haplotype carries
+    if (CN < ploidy) {   // :411-425: CN distinct haplotypes keep one copy, the first mCN drawn are the major ones
+        for (i = 0; i < CN; i++) for (;;) { j = (int)rng.integer(0, ploidy); if (!has(reps, j)) { reps.push_back(j); break; } }
+        for (i = 0; i < mCN; i++) major.push_back(reps[i]);
+        for (int h : reps) copies[h] = 1;
+    } else {             // :426-467
+        reps.assign(ploidy, 1);
+        n = CN - ploidy;
+        k = (int)rng.integer(0, ploidy);
+        for (i = n; i >= 0; i--) {
+            if (reps[k] + i == mCN) { reps[k] += i; major.push_back(k); break; }
+            else if (reps[k] + i == CN - mCN) { reps[k] += i; for (j = 0; j < ploidy; j++) if (j != k) major.push_back(j); break; }
         }
-        std::vector<char> in_major(ploidy, 0); for (int h : major) if (h >= 0 && h < ploidy) in_major[h] = 1;
+        if (i >= 0) {
+            n -= i;
+            if (n > 0 && ploidy < 2) { err = "ERROR: copy number cannot be distributed over one haplotype"; return false; }   // reference: endless loop
+            while (n > 0) { j = (int)rng.integer(0, ploidy); if (j != k) { reps[j]++; n--; } }
+        } else {
+            while (n > 0) { j = (int)rng.integer(0, ploidy); reps[j]++; n--; }
+            for (i = 0; i < ploidy; i++) major.push_back(i);
+        }
+        copies = reps;
+    }
+    out.s = s; out.e = e; out.copies = copies;
+    out.in_major.assign(ploidy, 0); for (int h : major) if (h >= 0 && h < ploidy) out.in_major[h] = 1;
+    return true;
+}
+
+// The deterministic rest of generateSegment (Genome.cpp:469-691) for one chromosome; one instance per worker thread.
+struct Planner {
+    int ploidy; std::string err;
+    std::vector<uint32_t> hits;
+    explicit Planner(int pl) : ploidy(pl) {}
+
+    bool segment(std::vector<HapBuild>& hap, ChromVars* cv, const std::string& chr, const SegSpec& spec) {
+        const long s = spec.s, e = spec.e;
+        const unsigned int refSize = (unsigned int)(e - s + 1);
+        const std::vector<int>& copies = spec.copies; const std::vector<char>& in_major = spec.in_major;
+        int j, k, n;
         // a het variant goes to the major haplotypes when k == 0 and to the others when k == 1 (:496-499 and alike)
         auto skipped = [&](int kk, int jj) { return (kk == 0 && !in_major[jj]) || (kk == 1 && in_major[jj]); };
 
@@ -359,13 +430,13 @@ struct Planner {
                     if (v.het && skipped(k, j)) continue;
                     const int offset = (int)insAt[j].upto(sindx);
                     Rope& q = rope[j];
-                    if (refSize + insLen[j] == 0) { P.err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
+                    if (refSize + insLen[j] == 0) { err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
                     n = (int)(q.size() / (refSize + insLen[j]));
                     const int len = (int)v.len;
                     for (int t = 0; t < n; t++) {
                         const unsigned int at = sindx + offset + t * (refSize + insLen[j] + len);   // the reference's 32-bit arithmetic, :567-569
                         if (!q.insert(at, {kLiteral | v.lit_off, 0, v.len})) {
-                            P.err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
+                            err = "ERROR: insertion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
                             return false;
                         }
                     }
@@ -384,13 +455,13 @@ struct Planner {
                     const int offset = (int)(insAt[j].upto(sindx) - delAt[j].upto(sindx));
                     if (sindx + offset < 0) continue;
                     Rope& q = rope[j];
-                    if (refSize + insLen[j] - delLen[j] == 0) { P.err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
+                    if (refSize + insLen[j] - delLen[j] == 0) { err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + ": empty segment"; return false; }
                     n = (int)(q.size() / (refSize + insLen[j] - delLen[j]));
                     for (int t = 0; t < n; t++) {
                         const unsigned int at = sindx + offset + t * (refSize + insLen[j] - delLen[j] - dl);   // :637-639
                         // std::string::erase(pos, n) takes n as size_t: a negative length becomes "to the end"
                         if (!q.erase(at, (uint64_t)(size_t)(long)dl)) {
-                            P.err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
+                            err = "ERROR: deletion at " + std::to_string(v.pos) + " on chromosome " + chr + " falls outside its haplotype (the reference aborts with std::out_of_range here)";
                             return false;
                         }
                     }
@@ -444,24 +515,65 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
     if (!load_snps(P, snp_file, by_chr)) return false;
     P.ms_parse_snp = ms_since(t0); t0 = clk::now();
     if (chroms.empty()) { P.err = "ERROR: reference sequence cannot be empty!"; return false; }
-    Planner pl(P, libc_seed, ploidy);
     const int mCN = (int)ceilf((float)ploidy / 2);
-    // Genome::saveSequence, Genome.cpp:329-386
-    for (size_t c = 0; c < chroms.size(); c++) {
+    // Genome::saveSequence, Genome.cpp:329-386. Pass 1, sequential: the segment list of every chromosome with its random draws.
+    LibcRand rng(libc_seed);
+    const size_t nc = chroms.size();
+    std::vector<std::vector<SegSpec>> specs(nc);
+    std::vector<ChromVars*> cvs(nc, nullptr);
+    size_t draw_err_chrom = nc; std::string draw_err;
+    for (size_t c = 0; c < nc && draw_err_chrom == nc; c++) {
         const std::string& chr = chroms[c].name;
         const long chrLen = (long)chroms[c].len;
         auto it = by_chr.find(chr);
-        ChromVars* cv = it == by_chr.end() ? nullptr : &it->second;
-        std::vector<HapBuild> hap(ploidy);
-        long segStart = 1;
+        ChromVars* cv = cvs[c] = (it == by_chr.end() ? nullptr : &it->second);
+        auto add = [&](long s, long e, int CN, int mcn) {
+            SegSpec sp; bool skip = false;
+            if (!assign_copies(rng, ploidy, chr, chrLen, s, e, CN, mcn, sp, &skip, draw_err)) { draw_err_chrom = c; return false; }
+            if (!skip) { specs[c].push_back(std::move(sp)); P.n_segments++; }
+            return true;
+        };
+        long segStart = 1; bool ok = true;
         if (cv) for (Cnv cnv : cv->cnv) {
             if (segStart > chrLen) break;
             cnv.epos = std::min(cnv.epos, chrLen);
-            if (segStart < cnv.spos && !pl.segment(hap, cv, chr, chrLen, segStart, cnv.spos - 1, ploidy, mCN)) return false;
-            if (!pl.segment(hap, cv, chr, chrLen, cnv.spos, cnv.epos, (int)cnv.cn, (int)cnv.mcn)) return false;
+            if (segStart < cnv.spos && !(ok = add(segStart, cnv.spos - 1, ploidy, mCN))) break;
+            if (!(ok = add(cnv.spos, cnv.epos, (int)cnv.cn, (int)cnv.mcn))) break;
             segStart = cnv.epos + 1;
         }
-        if (segStart <= chrLen && !pl.segment(hap, cv, chr, chrLen, segStart, chrLen, ploidy, mCN)) return false;
+        if (ok && segStart <= chrLen) add(segStart, chrLen, ploidy, mCN);
+    }
+    // Pass 2, one task per chromosome on a few threads: variants -> piece tables -> runs and substitutions. A chromosome whose
+    // draws failed in pass 1 still gets its earlier segments applied: the reference would have died at the first problem in
+    // file order, and that may be an indel of an earlier segment.
+    const size_t n_apply = std::min(nc, draw_err_chrom + 1);
+    std::vector<std::vector<HapBuild>> built(n_apply);
+    std::vector<std::string> apply_err(n_apply);
+    auto apply_chrom = [&](size_t c) {
+        Planner pl(ploidy);
+        built[c].assign(ploidy, HapBuild());
+        for (const SegSpec& sp : specs[c]) if (!pl.segment(built[c], cvs[c], chroms[c].name, sp)) { apply_err[c] = pl.err; return; }
+    };
+    {
+        unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("SCS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+        size_t nt = std::min<size_t>(hw, n_apply);
+        // two records with the same (stripped) name share their variant lists, whose position index is built lazily: serial then
+        { std::vector<ChromVars*> u; for (ChromVars* v : cvs) if (v) u.push_back(v); std::sort(u.begin(), u.end()); if (std::adjacent_find(u.begin(), u.end()) != u.end()) nt = 1; }
+        if (nt <= 1) for (size_t c = 0; c < n_apply; c++) apply_chrom(c);
+        else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> ts;
+            for (size_t t = 0; t < nt; t++) ts.emplace_back([&] { for (size_t c; (c = next.fetch_add(1)) < n_apply;) apply_chrom(c); });
+            for (auto& t : ts) t.join();
+        }
+    }
+    for (size_t c = 0; c < n_apply; c++) if (!apply_err[c].empty()) { P.err = apply_err[c]; return false; }
+    if (draw_err_chrom < nc) { P.err = draw_err; return false; }
+    for (size_t c = 0; c < nc; c++) {
+        const std::string& chr = chroms[c].name;
+        const long chrLen = (long)chroms[c].len;
+        std::vector<HapBuild>& hap = built[c];
         for (int j = 0; j < ploidy; j++) {
             if (hap[j].len >= (1ull << 32)) { P.err = "ERROR: haplotype longer than 2^32-1 bases (Genome.cpp:370 uses unsigned int)"; return false; }
             Hap h; h.chrom = (uint32_t)c; h.hap = (uint32_t)j; h.len = hap[j].len;
@@ -470,6 +582,7 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
             h.name = chr + "_" + std::to_string(j + 1) + "_" + std::to_string(chrLen);
             P.haps.push_back(h);
         }
+        std::vector<HapBuild>().swap(hap);
     }
     P.ms_segments = ms_since(t0);
     if (getenv("SCS_TRACE")) fprintf(stderr, "[scs trace] simuvars plan: parse var %.1f ms, parse snp %.1f ms, segments %.1f ms\n", P.ms_parse_var, P.ms_parse_snp, P.ms_segments);
