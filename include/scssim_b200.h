@@ -1,4 +1,4 @@
-/* scssim_b200 — C ABI of the B200-native `scssim genreads` hot path.
+/* scssim_b200 — C ABI of the B200-native `scssim genreads` hot path (and of `scssim simuvars`, the producer of its input).
  *
  * Drop-in boundary. Each entry point replaces one stage call that the reference's
  * main() makes on its global singletons (/root/reference/src/scssim.cpp:46-66):
@@ -12,7 +12,9 @@
  *   malbac.createFrags() (src/scssim.cpp:59, lib/malbac/Malbac.cpp:143)    scs_create_frags
  *   malbac.amplify() (src/scssim.cpp:62, lib/malbac/Malbac.cpp:173)        scs_amplify
  *   malbac.yieldReads() (src/scssim.cpp:65, lib/malbac/Malbac.cpp:410)     scs_yield_reads[_sink]
- *   SeqWriter::write (lib/seqwriter/SeqWriter.cpp:41-54)                   scs_sink_fn
+ *   SeqWriter::write (lib/seqwriter/SeqWriter.cpp:41-54)                   scs_sink_fn / io_threads
+ *   simuvars: genome.loadData(); genome.saveSequence() (src/scssim.cpp:33-38,
+ *     lib/genome/Genome.cpp:35-198,329-691, lib/snp/snp.cpp:147-203)       scs_simuvars / _sink / _to_genome
  *
  * Plain pointers and sizes only; no exceptions and no exit() cross this boundary. Every function
  * returns 0 on success or a negative SCS_E_* code; scs_last_error(ctx) gives the message the

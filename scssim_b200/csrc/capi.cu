@@ -59,6 +59,7 @@ void scs_destroy(scs_ctx* c) {
         cudaDeviceSynchronize();
         for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) if (c->slab_host[b][f]) cudaFreeHost(c->slab_host[b][f]);
         if (c->rscratch.htotals) cudaFreeHost(c->rscratch.htotals);
+        for (int b = 0; b < 2; b++) if (c->sv_pinned[b]) cudaFreeHost(c->sv_pinned[b]);
     }
     delete c;   // device buffers are returned to the pool in stream order
     if (dev) {

@@ -194,6 +194,7 @@ struct scs_ctx {
     scs::AmpScratch ascratch;
     // staging buffers that keep their capacity between calls (cold device allocations are slow and erratic on this platform)
     scs::DevBuf<uint8_t> genome_stage, sv_stage, sv_ref, sv_text[2];
+    char* sv_pinned[2] = {nullptr, nullptr};   // simuvars output slabs (pinned), kept between calls
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
     scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; scs_allreduce_dev_i64_fn ar_dev_i64 = nullptr; void* ar_dev_user = nullptr;

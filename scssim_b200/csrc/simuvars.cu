@@ -221,9 +221,12 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
     if (!plan.literals.empty()) SCS_CUDA(c, cudaMemcpyAsync(lit.p, plan.literals.data(), plan.literals.size(), cudaMemcpyHostToDevice, c->st));
 
     constexpr uint64_t kSlab = 32ull << 20;
-    char* pinned[2] = {nullptr, nullptr}; cudaEvent_t copied[2] = {nullptr, nullptr};
-    struct Cleanup { char** p; cudaEvent_t* e; ~Cleanup() { for (int i = 0; i < 2; i++) { if (p[i]) cudaFreeHost(p[i]); if (e[i]) cudaEventDestroy(e[i]); } } } cleanup{pinned, copied};
-    if (!to_genome) for (int i = 0; i < 2; i++) { SCS_CUDA(c, cudaHostAlloc((void**)&pinned[i], kSlab, cudaHostAllocDefault)); SCS_CUDA(c, cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)); }
+    char** pinned = c->sv_pinned; cudaEvent_t copied[2] = {nullptr, nullptr};
+    struct Cleanup { cudaEvent_t* e; ~Cleanup() { for (int i = 0; i < 2; i++) if (e[i]) cudaEventDestroy(e[i]); } } cleanup{copied};
+    if (!to_genome) for (int i = 0; i < 2; i++) {
+        if (!pinned[i]) SCS_CUDA(c, cudaHostAlloc((void**)&pinned[i], kSlab, cudaHostAllocDefault));
+        SCS_CUDA(c, cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    }
 
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;   // kernel groups on the compute stream
     struct EvFree { std::vector<std::pair<cudaEvent_t, cudaEvent_t>>* v; ~EvFree() { for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } } } evfree{&timed};
