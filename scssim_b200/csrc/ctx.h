@@ -151,6 +151,7 @@ struct ReadScratch {
     DevBuf<uint32_t> plan, size1, size2, nfail, hdrno;
     DevBuf<uint64_t> off1, off2, scan, totals;
     DevBuf<int> flags; DevBuf<unsigned long long> records;
+    DevBuf<char> stage[2];         // fixed-stride records of one slab per file (staged emit), packed by compact_records_kernel
     uint64_t* htotals = nullptr;   // pinned + mapped
     uint64_t* dtotals_mapped = nullptr;   // device view of htotals
 };

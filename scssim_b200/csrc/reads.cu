@@ -285,6 +285,7 @@ struct SlabArgs {
     const uint32_t* nfail;             // slow path: failed insert-size attempts before the slot's success
     uint64_t fail_base;                // hdr_no / nfail are indexed by (slot - fail_base)
     uint64_t slab_cap;                 // bytes available in each output slab (emit bounds check)
+    uint64_t stage_stride;             // staged emit: record of slot ls goes to stage + ls * stage_stride (a multiple of 16)
 };
 
 // count_le on a long row, evaluated by the whole warp: 32 pivots, then the segment between two pivots (2 ballots)
@@ -319,7 +320,7 @@ __device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ s
 }
 
 // Shared body of the plan and emit kernels for one slot.
-template <bool EMIT>
+template <bool EMIT, bool STAGED = false>
 __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
                                         WarpScratch* ws, uint32_t* __restrict__ plan, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
                                         const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, char* __restrict__ out1,
@@ -382,10 +383,10 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
             lens |= (uint32_t)np << (mate == 1 ? 0 : 16);
         } else {
             const uint8_t* src = build_source(S, np, nev, lane, ws);
-            const uint64_t o = (mate == 1) ? off1[ls] : off2[ls];
+            const uint64_t o = STAGED ? ls * A.stage_stride : ((mate == 1) ? off1[ls] : off2[ls]);
             const int hl = header_len(ampIdx, fragNo, T.paired);
             const int total = hl + 2 * np + 4;
-            if (o + (uint64_t)total > A.slab_cap) { if (lane == 0) atomicOr(flags, 16); return; }
+            if (STAGED ? ((uint64_t)total > A.stage_stride) : (o + (uint64_t)total > A.slab_cap)) { if (lane == 0) atomicOr(flags, 16); return; }
             char* dst = ((mate == 1) ? out1 : out2) + o;
             char* rec = ws->rec + (reinterpret_cast<uintptr_t>(dst) & 15);
             if (lane == 0) {
@@ -396,8 +397,10 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
             else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
             __syncwarp();
             copy_out(dst, rec, total, lane);
+            if (STAGED && lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;   // sizes were zeroed before the launch
         }
     }
+    if (EMIT && STAGED && lane == 0) atomicAdd(records, T.paired ? 2ull : 1ull);
     if (!EMIT && lane == 0) {
         const int hl = header_len(ampIdx, fragNo, T.paired);
         plan[ls] = lens;
@@ -418,9 +421,13 @@ __global__ void __launch_bounds__(kReadWarps * 32) plan_kernel(Genome g, DrawSrc
 }
 
 // emit: persistent CTAs (one per SM); the diagonal quality tables are staged in shared memory once per CTA
+// STAGED: no plan / offsets — every record goes to its slot's fixed-stride place in a staging buffer and its size is recorded;
+// compact_records_kernel packs them afterwards (the indel pass then runs once per read instead of twice).
+template <bool STAGED>
 __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, const uint32_t* __restrict__ plan,
                                                                   const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
-                                                                  char* __restrict__ out1, char* __restrict__ out2, int* flags) {
+                                                                  char* __restrict__ out1, char* __restrict__ out2, int* flags,
+                                                                  uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, unsigned long long* __restrict__ records) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrows = 4 * T.RL;
@@ -436,8 +443,31 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, Draw
     __syncthreads();
     QualSmem Q; Q.rows = srows; Q.piv = spiv; Q.meta = smeta;
     for (uint64_t ls = (uint64_t)blockIdx.x * kEmitWarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * kEmitWarps) {
-        if (plan[ls] == 0) continue;
-        do_slot<true>(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], nullptr, nullptr, nullptr, off1, off2, out1, out2, flags, nullptr);
+        if (!STAGED && plan[ls] == 0) continue;
+        do_slot<true, STAGED>(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], nullptr, size1, size2, off1, off2, out1, out2, flags, records);
+    }
+}
+
+// pack the staged records of one file: warp per record, 16-byte stores at the destination's alignment, the source realigned by
+// the two-load funnel shifter (load16). HBM-bound: reads and writes every FASTQ byte once (~0.05 ms per 64 MiB slab).
+__global__ void __launch_bounds__(256) compact_records_kernel(const char* __restrict__ stage, uint64_t stride, const uint32_t* __restrict__ sizes,
+                                                              const uint64_t* __restrict__ offs, uint64_t n, char* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    for (uint64_t ls = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); ls < n; ls += (uint64_t)gridDim.x * 8) {
+        const int sz = (int)sizes[ls];
+        if (!sz) continue;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(stage) + ls * stride;
+        char* dst = out + offs[ls];
+        const int head = min(sz, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
+        if (lane < head) dst[lane] = (char)src[lane];
+        const int nvec = (sz - head) >> 4;
+        for (int k = lane; k < nvec; k += 32) {
+            uint32_t X[4]; load16(src + head + 16 * k, X);
+            uint4 v; v.x = X[0]; v.y = X[1]; v.z = X[2]; v.w = X[3];
+            *reinterpret_cast<uint4*>(dst + head + 16 * k) = v;
+        }
+        const int done = head + (nvec << 4);
+        if (done + lane < sz) dst[done + lane] = (char)src[done + lane];
     }
 }
 
@@ -575,11 +605,14 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     }
     int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t emit_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4 + sizeof(WarpScratch) * kEmitWarps;
-    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
     cudaEvent_t e0, e1, etot, ecopy[2], ekern[2];
     cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreateWithFlags(&etot, cudaEventDisableTiming);
     for (int b = 0; b < 2; b++) { cudaEventCreateWithFlags(&ecopy[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ekern[b], cudaEventDisableTiming); }
     std::vector<cudaEvent_t> tev;   // per batch: plan start, emit start, emit end
+    const bool no_d2h_env = getenv("SCS_NO_D2H") != nullptr;
+    cudaEvent_t etotb[2]; for (int b = 0; b < 2; b++) cudaEventCreateWithFlags(&etotb[b], cudaEventDisableTiming);
     cudaEventRecord(e0, c->st);
     // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
     if (c->P.paired && P.maxInsert > 1000) {
@@ -600,6 +633,69 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         fail_scan_kernel<<<(unsigned)((F.nslots + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
         A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p; A.fail_base = ext_lo;
     }
+    // ---- staged path (default): emit -> scan of the recorded sizes -> compaction. One indel pass per read instead of two. -----
+    std::vector<cudaEvent_t> tev4;   // per slab: start, emit start, emit end, end
+    const bool staged = getenv("SCS_TWO_PASS") == nullptr;
+    if (staged) {
+        const uint64_t stride = ((uint64_t)kRecCap + 15) & ~15ull;
+        A.stage_stride = stride;
+        for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
+        struct Slab { bool launched = false, copying = false; uint64_t bytes[2] = {0, 0}; } sl[2];
+        // the kernels of buffer b have been launched: wait for the byte totals, start the copy (it waits for the compaction on the device)
+        auto finalize = [&](int b) -> int {
+            if (!sl[b].launched) return SCS_OK;
+            SCS_CUDA(c, cudaEventSynchronize(etotb[b]));
+            sl[b].launched = false;
+            const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};
+            if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
+            SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
+            if (!no_d2h_env) for (int f = 0; f < nfiles; f++) if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(c->slab_host[b][f], c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
+            SCS_CUDA(c, cudaEventRecord(ecopy[b], c->st_copy));
+            sl[b].copying = true; sl[b].bytes[0] = tot[0]; sl[b].bytes[1] = tot[1];
+            c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
+            return SCS_OK;
+        };
+        auto drain_s = [&](int b) -> int {
+            if (!sl[b].copying) return SCS_OK;
+            SCS_CUDA(c, cudaEventSynchronize(ecopy[b]));
+            sl[b].copying = false;
+            if (sink) for (int f = 0; f < nfiles; f++) if (sl[b].bytes[f]) if (sink(user, f, c->slab_host[b][f], sl[b].bytes[f])) return c->fail(SCS_E_IO, "FASTQ sink failed");
+            return SCS_OK;
+        };
+        int b = 0;
+        for (uint64_t s0 = slot_lo; s0 < slot_hi; s0 += batch, b ^= 1) {
+            const uint64_t m = std::min(batch, slot_hi - s0);
+            A.slot0 = s0; A.nslots = m;
+            cudaEvent_t q0, q1, q2, q3; cudaEventCreate(&q0); cudaEventCreate(&q1); cudaEventCreate(&q2); cudaEventCreate(&q3);
+            tev4.push_back(q0); tev4.push_back(q1); tev4.push_back(q2); tev4.push_back(q3);
+            cudaEventRecord(q0, c->st);
+            SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
+            if (nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
+            cudaEventRecord(q1, c->st);
+            emit_kernel<true><<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, nullptr, nullptr, nullptr, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr,
+                                                                         W.flags.p, W.size1.p, W.size2.p, W.records.p);
+            SCS_LAUNCHED(c); c->stats.emit_launches++;
+            cudaEventRecord(q2, c->st);
+            if (int rc = scan_sizes(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;
+            if (nfiles == 2) { if (int rc = scan_sizes(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 2 * b + 1)) return rc; }
+            SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
+            cudaEventRecord(q3, c->st);   // kernel time of the slab without the compaction (~0.05 ms), which may wait for a copy
+            // the packed device slab b is free once the copy of the slab two back is done
+            SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));
+            const unsigned cgrid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)sms * 16);
+            compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[0].p, stride, W.size1.p, W.off1.p, m, c->slab_dev[b][0].p); SCS_LAUNCHED(c);
+            if (nfiles == 2) { compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[1].p, stride, W.size2.p, W.off2.p, m, c->slab_dev[b][1].p); SCS_LAUNCHED(c); }
+            SCS_CUDA(c, cudaEventRecord(ekern[b], c->st));
+            sl[b].launched = true;
+            if (int rc = finalize(b ^ 1)) return rc;   // slab k-1: totals known -> copy queued behind its compaction
+            if (int rc = drain_s(b)) return rc;        // slab k-2: copied -> sink; its pinned buffer is free for slab k
+        }
+        // the last two slabs, in slab order (b now names the older of the two buffers)
+        if (int rc = finalize(b)) return rc;
+        if (int rc = drain_s(b)) return rc;
+        if (int rc = finalize(b ^ 1)) return rc;
+        if (int rc = drain_s(b ^ 1)) return rc;
+    } else {
     struct Pending { bool live = false; uint64_t bytes[2] = {0, 0}; } pend[2];
     auto drain = [&](int b) -> int {
         if (!pend[b].live) return SCS_OK;
@@ -628,8 +724,8 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         if (nfiles == 2) { if (int rc = scan_sizes(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 1)) return rc; }
         cudaEventRecord(etot, c->st);
         cudaEventRecord(t1, c->st);
-        emit_kernel<<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.plan.p, W.off1.p, W.off2.p, c->slab_dev[bi][0].p,
-                                                               nfiles == 2 ? c->slab_dev[bi][1].p : nullptr, W.flags.p);
+        emit_kernel<false><<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.plan.p, W.off1.p, W.off2.p, c->slab_dev[bi][0].p,
+                                                                      nfiles == 2 ? c->slab_dev[bi][1].p : nullptr, W.flags.p, nullptr, nullptr, nullptr);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         cudaEventRecord(t2, c->st);
         cudaEventRecord(ekern[bi], c->st);
@@ -650,6 +746,7 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     }
     if (int rc = drain(0)) return rc;
     if (int rc = drain(1)) return rc;
+    }   // two-kernel path
     SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[0], 0)); SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[1], 0));
     cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
@@ -657,7 +754,12 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     for (size_t i = 0; i + 2 < tev.size(); i += 3) {
         float a = 0, b2 = 0; cudaEventElapsedTime(&a, tev[i], tev[i + 2]); cudaEventElapsedTime(&b2, tev[i + 1], tev[i + 2]); msk += a; mse += b2;
     }
+    for (size_t i = 0; i + 3 < tev4.size(); i += 4) {
+        float a = 0, b2 = 0; cudaEventElapsedTime(&a, tev4[i], tev4[i + 3]); cudaEventElapsedTime(&b2, tev4[i + 1], tev4[i + 2]); msk += a; mse += b2;
+    }
     for (auto ev : tev) cudaEventDestroy(ev);
+    for (auto ev : tev4) cudaEventDestroy(ev);
+    for (int b = 0; b < 2; b++) cudaEventDestroy(etotb[b]);
     c->stats.ms_reads = ms; c->stats.ms_reads_kernels = msk; c->stats.ms_emit_kernel = mse;
     int hflags = 0; SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
     unsigned long long hrec = 0; SCS_CUDA(c, memcpy_sync(c, &hrec, W.records.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;

@@ -35,28 +35,6 @@ __device__ __forceinline__ uint32_t upper4(uint32_t w) {
     return w - (lower >> 2);
 }
 
-// 16 bytes starting at an arbitrary address: two aligned 16-byte loads (the second one is the neighbour thread's first,
-// an L1 hit) and a word/byte shifter. The caller guarantees 31 readable bytes past p (buffers are padded).
-__device__ __forceinline__ void load16(const uint8_t* p, uint32_t X[4]) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint4* q = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    const uint4 v0 = __ldg(q), v1 = __ldg(q + 1);
-    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-    const uint32_t sh = (uint32_t)(a & 15), s8 = (sh & 3) * 8;
-    uint32_t t[6], u[5];
-#pragma unroll
-    for (int i = 0; i < 6; i++) t[i] = (sh & 8) ? w[i + 2] : w[i];
-#pragma unroll
-    for (int i = 0; i < 5; i++) u[i] = (sh & 4) ? t[i + 1] : t[i];
-#pragma unroll
-    for (int m = 0; m < 4; m++) X[m] = __funnelshift_r(u[m], u[m + 1], s8);
-}
-// word m of a 16-byte vector: mask of the bytes whose index in the vector is below k (k may be <= 0 or >= 16)
-__device__ __forceinline__ uint32_t below_mask(int k, int m) {
-    const int km = k - 4 * m;
-    return km <= 0 ? 0u : (km >= 4 ? 0xffffffffu : (1u << (8 * km)) - 1u);
-}
-
 constexpr int kSvTile = kSvThreads * 16;   // bytes (bases) one CTA produces
 
 // One thread = 16 output bases. FASTA text with a fixed line geometry: the bases sit at text[line * llen + col]; a vector
