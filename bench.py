@@ -287,10 +287,10 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        # algorithmic HBM bytes of one emit launch (DESIGN.md "emit_kernel"): FASTQ bytes stored + 2-bit genome windows read
-        # (ceil(L/4) B per read) + 16 B descriptor per amplicon touched + 20 B of plan/offsets per slot
+        # algorithmic HBM bytes of one emit launch (DESIGN.md "emit_kernel"): FASTQ bytes stored (into the staging buffer) + 2-bit
+        # genome windows read (ceil(L/4) B per read) + 16 B descriptor per amplicon touched + 8 B of record sizes per slot
         slots = reads_per_step / 2
-        alg_step = fastq_bytes + reads_per_step * ((READ_LEN + 3) // 4) + 16 * n_fulls + 20 * slots
+        alg_step = fastq_bytes + reads_per_step * ((READ_LEN + 3) // 4) + 16 * n_fulls + 8 * slots
         traffic = None
         try:   # dram__bytes_read+write of one emit launch from the committed ncu --set full capture of this same command
             with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
