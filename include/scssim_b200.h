@@ -169,6 +169,12 @@ enum scs_svplan_dump { SCS_SVP_HAPS = 0,      /* u64 x7 per haplotype: chrom, ha
                        SCS_SVP_NAMES = 4,     /* record names, '\n' separated */
                        SCS_SVP_WARNINGS = 5   /* what the reference prints while loading (malformed SNP lines) */ };
 int64_t scs_svplan_dump(const scs_svplan* plan, int what, void* buf, uint64_t cap);
+/* Host-only test hooks for the file side. scs_test_fasta_index: the .fai model the loaders build (lib/fastahack/Fasta.cpp:103-191);
+ * writes up to cap records of 5 u64 (length, offset, bases per line, bytes per line, regular geometry 0/1) and the '\n'-joined
+ * names; returns the record count or a negative code. scs_test_file_writer: writes n bytes to path through the parallel pwrite
+ * sink in slabs of slab_bytes with the given thread count; returns 0 on success. */
+int64_t scs_test_fasta_index(const char* path, uint64_t* recs, uint64_t cap, char* names, uint64_t names_cap);
+int scs_test_file_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads);
 /* The first n values of libc rand() after srand(seed), as reproduced by the library. */
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out);
 

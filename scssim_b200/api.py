@@ -88,7 +88,7 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
-           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences"]
+           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer"]
 
 _lib = None
 
@@ -146,6 +146,9 @@ def lib():
         L.scs_test_libc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
         L.scs_shard_sequences.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.scs_shard_sequences.restype = None
+        L.scs_test_fasta_index.restype = C.c_int64
+        L.scs_test_fasta_index.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
+        L.scs_test_file_writer.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
         _lib = L
     return _lib
 
@@ -154,6 +157,24 @@ def shard_range(n: int, rank: int, world: int):
     lo, hi = C.c_uint64(), C.c_uint64()
     lib().scs_shard_range(n, rank, world, C.byref(lo), C.byref(hi))
     return lo.value, hi.value
+
+
+def fasta_index(path: str):
+    """[(name, length, offset, bases per line, bytes per line, regular)] as the loaders index a FASTA file (host only)."""
+    n = lib().scs_test_fasta_index(path.encode(), None, 0, None, 0)
+    if n < 0:
+        raise ScsError(int(n), f"could not open {path}")
+    recs = np.zeros((max(int(n), 1), 5), dtype=np.uint64)
+    names = C.create_string_buffer(1 << 20)
+    lib().scs_test_fasta_index(path.encode(), recs.ctypes.data, n, names, len(names))
+    nm = names.value.decode().split("\n")[:-1]
+    return [(nm[i],) + tuple(int(x) for x in recs[i]) for i in range(int(n))]
+
+
+def write_file_parallel(path: str, data: bytes, slab_bytes: int, threads: int) -> None:
+    rc = lib().scs_test_file_writer(path.encode(), data, len(data), slab_bytes, threads)
+    if rc != SCS_OK:
+        raise ScsError(rc, f"can not write {path}")
 
 
 def shard_sequences(lens, rank: int, world: int):

@@ -4,6 +4,7 @@
 #include <cstring>
 
 #include "ctx.h"
+#include "fasta_host.h"
 #include "file_sink.h"
 #include "simuvars_plan.h"
 
@@ -197,6 +198,26 @@ int64_t scs_svplan_dump(const scs_svplan* h, int what, void* buf, uint64_t cap) 
 void scs_shard_sequences(const uint64_t* lens, size_t n, int rank, int world, size_t* lo, size_t* hi) {
     std::vector<uint64_t> v(lens, lens + n);
     shard_by_midpoint(v, rank, world < 1 ? 1 : world, lo, hi);
+}
+int64_t scs_test_fasta_index(const char* path, uint64_t* recs, uint64_t cap, char* names, uint64_t names_cap) {
+    if (!path) return SCS_E_ARG;
+    FastaFile ff; std::string err;
+    if (!ff.open(path, &err)) return SCS_E_IO;
+    std::string nm;
+    for (size_t i = 0; i < ff.fai.size(); i++) {
+        const FaiRec& r = ff.fai[i];
+        if (recs && i < cap) { recs[5 * i] = r.len; recs[5 * i + 1] = r.off; recs[5 * i + 2] = r.blen; recs[5 * i + 3] = r.llen; recs[5 * i + 4] = r.regular ? 1 : 0; }
+        nm += r.name; nm += '\n';
+    }
+    if (names && names_cap) { strncpy(names, nm.c_str(), names_cap - 1); names[names_cap - 1] = 0; }
+    return (int64_t)ff.fai.size();
+}
+int scs_test_file_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads) {
+    if (!path || (!data && n) || slab_bytes == 0) return SCS_E_ARG;
+    ParallelFileWriter w(threads);
+    if (!w.open(0, path)) return SCS_E_IO;
+    for (uint64_t o = 0; o < n; o += slab_bytes) if (w.write(0, data + o, (size_t)std::min(slab_bytes, n - o))) return SCS_E_IO;
+    return w.close() ? SCS_E_IO : SCS_OK;
 }
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out) {
     if (!out || n < 0) return SCS_E_ARG;

@@ -143,3 +143,53 @@ def test_resampled_profile_is_a_valid_profile(tmp_path):
     L.orc_profile_info(op, info)
     assert info[0] == 150 and info[1] == 150
     L.orc_profile_free(op)
+
+
+def test_fasta_index_matches_samtools_fai_model(tmp_path):
+    """The host FASTA reader (mmap + record-parallel indexing): names, lengths, offsets and line geometry as in a .fai
+    (lib/fastahack/Fasta.cpp:103-191), for fixed-width, single-line, CRLF, ragged and unterminated records and a file big
+    enough (> 64 MB) to take the threaded path."""
+    import numpy as np
+    from scssim_b200.synth import synth_sequence
+    d = str(tmp_path)
+    a, b, c, e = synth_sequence(1000, 1), synth_sequence(77, 2), synth_sequence(250, 3), synth_sequence(130, 4)
+    path = os.path.join(d, "mix.fa")
+    with open(path, "wb") as f:
+        f.write(b">chr1 some description\n" + b"".join(a[i:i + 60].tobytes() + b"\n" for i in range(0, 1000, 60)))
+        f.write(b">single\n" + b.tobytes() + b"\n")
+        f.write(b">crlf\r\n" + b"".join(c[i:i + 50].tobytes() + b"\r\n" for i in range(0, 250, 50)))
+        f.write(b">ragged\n" + e[:40].tobytes() + b"\n" + e[40:100].tobytes() + b"\n" + e[100:].tobytes() + b"\n")
+        f.write(b">empty\n>last_no_newline\nACGTACGTAC\nACG")
+    idx = api.fasta_index(path)
+    assert [r[0] for r in idx] == ["chr1", "single", "crlf", "ragged", "empty", "last_no_newline"]
+    assert [r[1] for r in idx] == [1000, 77, 250, 130, 0, 13]
+    raw = open(path, "rb").read()
+    for name, length, off, blen, llen, regular in idx:
+        if length:
+            assert raw[off - 1:off] == b"\n" and raw[off:off + 1] in b"ACGT"
+    assert idx[0][3:] == (60, 61, 1) and idx[1][3:] == (77, 78, 1) and idx[2][3:] == (50, 52, 1)
+    assert idx[3][5] == 0                      # a longer line after a shorter one: not a uniform geometry
+    assert idx[5][3:] == (10, 11, 1)
+    big = os.path.join(d, "big.fa")
+    s = synth_sequence(12_000_000, 9)
+    from scssim_b200.synth import write_fasta
+    write_fasta(big, [(f"chrB{i}_1_{len(s) - 1000 * i}", s[:len(s) - 1000 * i]) for i in range(7)], 100)
+    assert os.path.getsize(big) > 64 << 20
+    idx = api.fasta_index(big)
+    assert [r[1] for r in idx] == [len(s) - 1000 * i for i in range(7)] and all(r[3:] == (100, 101, 1) for r in idx)
+    raw = np.fromfile(big, dtype=np.uint8)
+    for i, r in enumerate(idx):
+        assert bytes(raw[r[2] - len(r[0]) - 2:r[2]]) == b">" + r[0].encode() + b"\n"
+        assert bytes(raw[r[2]:r[2] + 100]) == s[:100].tobytes()
+
+
+def test_parallel_file_writer_round_trip(tmp_path):
+    """The pwrite pool behind scs_yield_reads / scs_simuvars: slabs of odd sizes, 1..8 threads, bytes land in order."""
+    import numpy as np
+    data = np.random.default_rng(3).integers(0, 256, size=9_000_001, dtype=np.uint8).tobytes()
+    for threads, slab in [(1, 1 << 20), (3, 4_194_303), (8, 5_000_000), (4, 64 << 20)]:
+        p = os.path.join(str(tmp_path), f"w{threads}.bin")
+        api.write_file_parallel(p, data, slab, threads)
+        assert open(p, "rb").read() == data
+    with pytest.raises(api.ScsError):
+        api.write_file_parallel(os.path.join(str(tmp_path), "no_such_dir", "x"), b"abc", 16, 2)
