@@ -91,48 +91,111 @@ std::vector<std::string> split_fields(const std::string& s, char d) {
 
 bool parse_zygosity(const std::string& t, bool& het) { if (t == "het") { het = true; return true; } if (t == "homo") { het = false; return true; } return false; }
 
-// Genome::loadAbers, Genome.cpp:35-165
+// Genome::loadAbers, Genome.cpp:35-165. The file is cut into chunks of whole lines that are parsed on threads; the records are
+// merged in file order, and the first bad line in file order is the one reported (the reference stops there).
+struct VarRec { char kind; std::string chrom; long a = 0, b = 0; float cn = 0, mcn = 0; uint8_t ch = 0; bool het = false; std::string seq; int dlen = 0; };
+enum VarErr { VE_NONE = 0, VE_FIELDS, VE_CN, VE_SAME, VE_SNV_TYPE, VE_INS_TYPE, VE_DEL_TYPE, VE_KIND };
+
+// one line; returns VE_NONE and fills r (r.kind = 0 for a blank / comment line)
+VarErr parse_var_line(const std::string& line, VarRec& r) {
+    r.kind = 0;
+    if (line.empty() || line[0] == '#') return VE_NONE;
+    std::vector<std::string> f = split_fields(line, '\t');
+    const std::string kind = f.empty() ? std::string() : f[0];
+    if (kind == "c") {
+        if (f.size() != 6) return VE_FIELDS;
+        float cn = (float)atof(f[4].c_str()), mcn = (float)atof(f[5].c_str());
+        if (cn < mcn) return VE_CN;
+        if (cn - mcn > mcn) mcn = cn - mcn;
+        r.kind = 'c'; r.chrom = f[1]; r.a = atol(f[2].c_str()); r.b = atol(f[3].c_str()); r.cn = cn; r.mcn = mcn;
+    } else if (kind == "s") {
+        if (f.size() != 6) return VE_FIELDS;
+        if (f[3].empty() || f[4].empty()) return VE_FIELDS;   // reference: std::out_of_range from at(0)
+        if (f[3][0] == f[4][0]) return VE_SAME;
+        if (!parse_zygosity(f[5], r.het)) return VE_SNV_TYPE;
+        r.kind = 's'; r.chrom = f[1]; r.a = atol(f[2].c_str()); r.ch = (uint8_t)toupper((unsigned char)f[4][0]);
+    } else if (kind == "i") {
+        if (f.size() != 5) return VE_FIELDS;
+        if (!parse_zygosity(f[4], r.het)) return VE_INS_TYPE;
+        r.kind = 'i'; r.chrom = f[1]; r.a = atol(f[2].c_str()); r.seq = f[3];
+        for (char& ch : r.seq) ch = (char)toupper((unsigned char)ch);   // the segment is upper-cased as a whole at the end, Genome.cpp:683-687
+    } else if (kind == "d") {
+        if (f.size() != 5) return VE_FIELDS;
+        if (!parse_zygosity(f[4], r.het)) return VE_DEL_TYPE;
+        r.kind = 'd'; r.chrom = f[1]; r.a = atol(f[2].c_str()); r.dlen = atoi(f[3].c_str());
+    } else return VE_KIND;
+    return VE_NONE;
+}
+
 bool load_variations(Plan& P, const char* path, std::map<std::string, ChromVars>& by_chr) {
     if (!path || !*path) return true;
-    std::ifstream ifs(path);
-    if (!ifs.is_open()) { P.err = std::string("can not open file ") + path; return false; }
-    std::string line; int ln = 0;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) { P.err = std::string("can not open file ") + path; return false; }
+    fseek(fp, 0, SEEK_END); const long long sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+    std::string buf((size_t)std::max<long long>(sz, 0), '\0');
+    const size_t got = sz > 0 ? fread(&buf[0], 1, (size_t)sz, fp) : 0;
+    fclose(fp);
+    buf.resize(got);
+    unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("SCS_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    const size_t nchunk = got >= (2u << 20) ? hw : 1;
+    std::vector<size_t> cut(nchunk + 1, got); cut[0] = 0;
+    for (size_t k = 1; k < nchunk; k++) {
+        size_t p = std::max(cut[k - 1], got * k / nchunk);
+        const size_t nl = p < got ? buf.find('\n', p) : std::string::npos;
+        cut[k] = nl == std::string::npos ? got : nl + 1;
+    }
+    struct ChunkOut { std::vector<VarRec> recs; long n_lines = 0; VarErr err = VE_NONE; long err_line = 0; std::string err_text; };
+    std::vector<ChunkOut> outs(nchunk);
+    auto work = [&](size_t k) {
+        ChunkOut& o = outs[k];
+        size_t s = cut[k]; const size_t end = cut[k + 1];
+        std::string line; VarRec r;
+        while (s < end) {
+            size_t e = buf.find('\n', s);
+            if (e == std::string::npos || e > end) e = end;
+            line.assign(buf, s, e - s);
+            o.n_lines++;
+            const VarErr ve = parse_var_line(line, r);
+            if (ve != VE_NONE) { o.err = ve; o.err_line = o.n_lines; o.err_text = line; return; }   // later lines of this chunk do not matter
+            if (r.kind) o.recs.push_back(r);
+            s = e + 1;
+        }
+    };
+    if (nchunk == 1) work(0);
+    else {
+        std::vector<std::thread> ts;
+        for (size_t k = 0; k < nchunk; k++) ts.emplace_back(work, k);
+        for (auto& t : ts) t.join();
+    }
     ChromLookup chrom(by_chr);
-    auto fail = [&](const std::string& head) { P.err = head + "\n" + line; return false; };
-    auto fields_err = [&]() { return fail("ERROR: line " + std::to_string(ln) + " has wrong number of fields in file " + path); };
-    while (std::getline(ifs, line)) {
-        ln++;
-        if (line.empty() || line[0] == '#') continue;
-        std::vector<std::string> f = split_fields(line, '\t');
-        const std::string kind = f.empty() ? std::string() : f[0];
-        if (kind == "c") {
-            if (f.size() != 6) return fields_err();
-            float cn = (float)atof(f[4].c_str()), mcn = (float)atof(f[5].c_str());
-            if (cn < mcn) return fail("ERROR: total copy number should be not lower than major copy number at line " + std::to_string(ln) + " in file " + path);
-            if (cn - mcn > mcn) mcn = cn - mcn;
-            chrom(f[1]).cnv.push_back({atol(f[2].c_str()), atol(f[3].c_str()), cn, mcn});
-            P.n_cnv++;
-        } else if (kind == "s") {
-            if (f.size() != 6) return fields_err();
-            if (f[3].empty() || f[4].empty()) return fields_err();   // reference: std::out_of_range from at(0)
-            if (f[3][0] == f[4][0]) return fail("ERROR: the mutated allele should be not same as the reference allele at line " + std::to_string(ln) + " in file " + path);
-            bool het; if (!parse_zygosity(f[5], het)) return fail("ERROR: unrecognized SNV type at line " + std::to_string(ln) + " in file " + path);
-            chrom(f[1]).snv.v.push_back({atol(f[2].c_str()), (uint8_t)toupper((unsigned char)f[4][0]), het});
-            P.n_snv++;
-        } else if (kind == "i") {
-            if (f.size() != 5) return fields_err();
-            bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized insert type at line " + std::to_string(ln) + " in file " + path);
-            std::string seq = f[3];
-            for (char& ch : seq) ch = (char)toupper((unsigned char)ch);   // the segment is upper-cased as a whole at the end, Genome.cpp:683-687
-            chrom(f[1]).ins.v.push_back({atol(f[2].c_str()), (uint64_t)P.literals.size(), (uint32_t)seq.size(), het});
-            P.literals += seq;
-            P.n_ins++;
-        } else if (kind == "d") {
-            if (f.size() != 5) return fields_err();
-            bool het; if (!parse_zygosity(f[4], het)) return fail("ERROR: unrecognized deletion type at line " + std::to_string(ln) + " in file " + path);
-            chrom(f[1]).del.v.push_back({atol(f[2].c_str()), atoi(f[3].c_str()), het});
-            P.n_del++;
-        } else return fail("ERROR: unrecognized aberraton type at line " + std::to_string(ln) + " in file " + path);
+    long line0 = 0;
+    for (ChunkOut& o : outs) {
+        for (VarRec& r : o.recs) {
+            ChromVars& cv = chrom(r.chrom);
+            switch (r.kind) {
+                case 'c': cv.cnv.push_back({r.a, r.b, r.cn, r.mcn}); P.n_cnv++; break;
+                case 's': cv.snv.v.push_back({r.a, r.ch, r.het}); P.n_snv++; break;
+                case 'i': cv.ins.v.push_back({r.a, (uint64_t)P.literals.size(), (uint32_t)r.seq.size(), r.het}); P.literals += r.seq; P.n_ins++; break;
+                default: cv.del.v.push_back({r.a, r.dlen, r.het}); P.n_del++; break;
+            }
+        }
+        if (o.err != VE_NONE) {
+            const std::string ln = std::to_string(line0 + o.err_line), in_file = std::string(" in file ") + path;
+            std::string head;
+            switch (o.err) {
+                case VE_FIELDS: head = "ERROR: line " + ln + " has wrong number of fields" + in_file; break;
+                case VE_CN: head = "ERROR: total copy number should be not lower than major copy number at line " + ln + in_file; break;
+                case VE_SAME: head = "ERROR: the mutated allele should be not same as the reference allele at line " + ln + in_file; break;
+                case VE_SNV_TYPE: head = "ERROR: unrecognized SNV type at line " + ln + in_file; break;
+                case VE_INS_TYPE: head = "ERROR: unrecognized insert type at line " + ln + in_file; break;
+                case VE_DEL_TYPE: head = "ERROR: unrecognized deletion type at line " + ln + in_file; break;
+                default: head = "ERROR: unrecognized aberraton type at line " + ln + in_file; break;
+            }
+            P.err = head + "\n" + o.err_text;
+            return false;
+        }
+        line0 += o.n_lines;
     }
     return true;
 }
