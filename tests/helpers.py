@@ -320,3 +320,21 @@ def materialize_plan(ref, snp, var, ploidy=2, seed=1, width=100) -> bytes:
         out.extend(t[i:i + width] + b"\n" for i in range(0, L, width))
     P.close()
     return b"".join(out)
+
+
+def config0_inputs(d: str):
+    """BASELINE configs[0] inputs in directory d: synthetic 63,025,520-base chr20 (the reference's ref.fa.gz is not shipped with
+    it) + the reference's own testData SNP and variation files (tests/golden/testdata). Returns (ref, snp, var) paths."""
+    from scssim_b200.synth import synth_sequence, write_fasta
+    os.makedirs(d, exist_ok=True)
+    ref = os.path.join(d, "ref.fa")
+    write_fasta(ref, [("chr20", synth_sequence(63_025_520, 20))], 100)
+    if os.path.exists(ref + ".fai"):
+        os.remove(ref + ".fai")
+    out = [ref]
+    for f in ("snp.txt", "vars.txt"):
+        p = os.path.join(d, f)
+        with lzma.open(os.path.join(GOLDEN, "testdata", f + ".xz")) as i, open(p, "wb") as o:
+            o.write(i.read())
+        out.append(p)
+    return tuple(out)

@@ -179,3 +179,18 @@ def test_to_genome_two_ranks_equal_one_rank(tmp_path):
     assert out[0][1]["n_sequences"] + out[1][1]["n_sequences"] == 4 and out[0][1]["n_sequences"] in (1, 2, 3)
     rec = lambda fq: sorted(b"\n".join(l) for l in zip(*[iter(fq.split(b"\n")[:-1])] * 4))
     assert len(one) > 50_000 and rec(out[0][0] + out[1][0]) == rec(one)
+
+
+def test_config0_testdata_case(tmp_path, ctx):
+    """BASELINE configs[0], simuvars half, on the GPU: the reference's own testData SNP / variation files on a synthetic chr20;
+    the FASTA must hash to what the reference binary wrote (tests/golden/testdata/config0.json)."""
+    d = str(tmp_path)
+    meta = json.load(open(os.path.join(H.GOLDEN, "testdata", "config0.json")))
+    ref, snp, var = H.config0_inputs(d)
+    ctx.simuvars(ref, snp, var, os.path.join(d, "cell.fa"))
+    data = H.read_bytes(os.path.join(d, "cell.fa"))
+    assert len(data) == meta["bytes"] and hashlib.sha256(data).hexdigest() == meta["sha256"]
+    st = ctx.simuvars_stats()
+    assert st["n_snp"] == 38603 and (st["n_cnv"], st["n_snv"], st["n_ins"], st["n_del"]) == (6, 11, 6, 6)
+    recs = H.read_fasta_records(os.path.join(d, "cell.fa"))
+    assert [(n, len(s)) for n, s in recs] == [tuple(r) for r in meta["records"]]
