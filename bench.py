@@ -101,13 +101,13 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference_cpu(tmp, profile, steps, warmup):
+def run_reference_cpu(tmp, profile, steps, warmup, genome_len=GENOME_LEN):
     """Reference genreads on the host cores, bounded sample. Returns (M reads/s, cores, sample text, s/step)."""
     import helpers as H
     from scssim_b200.synth import synth_sequence, write_fasta
     exe = os.path.join(ROOT, "oracle", "_ref", "bin", "scssim")
     cores = os.cpu_count() or 1
-    n = GENOME_LEN // SAMPLE_DIV
+    n = genome_len // SAMPLE_DIV
     fa = os.path.join(tmp, "sample.fa")
     write_fasta(fa, [(f"chrS1_1_{n}", synth_sequence(n, 7001))])
     reads = int((n // 2) * COVERAGE / READ_LEN)
@@ -160,10 +160,10 @@ def main():
             return 0
         with tempfile.TemporaryDirectory() as tmp:
             profile = bench_profile(tmp)
-            v, cores, sample, sec, kind, reads = run_reference_cpu(tmp, profile, max(1, min(a.steps, 3)), min(warmup, 1))
+            v, cores, sample, sec, kind, reads = run_reference_cpu(tmp, profile, max(1, min(a.steps, 3)), min(warmup, 1), a.genome_len)
         emit({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": workload_name(), "sample": sample},
+                          "config": {"workload": workload_name() if a.genome_len == GENOME_LEN else f"DEBUG {a.genome_len} bp", "sample": sample},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
@@ -281,7 +281,7 @@ def main():
 
         cpu = None
         if rank == 0 and not a.no_cpu_baseline:
-            v, cores, sample, sec, kind, _ = run_reference_cpu(tmp, profile, 1, 0)
+            v, cores, sample, sec, kind, _ = run_reference_cpu(tmp, profile, 1, 0, glen)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "s_per_sample": sec}
         g.close()
 

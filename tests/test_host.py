@@ -193,3 +193,23 @@ def test_parallel_file_writer_round_trip(tmp_path):
         assert open(p, "rb").read() == data
     with pytest.raises(api.ScsError):
         api.write_file_parallel(os.path.join(str(tmp_path), "no_such_dir", "x"), b"abc", 16, 2)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours): one JSON line with the contract's keys, produced by
+    the compiled reference when it exists, else by the CPU oracle — on a tiny debug genome here."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--genome-len", "2000000"], capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    lines = [l for l in r.stdout.decode().splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "impl", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "M reads/s" and d["dtype"] == "u8"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
