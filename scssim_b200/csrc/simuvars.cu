@@ -81,7 +81,7 @@ struct SvHapArgs {
     uint64_t n_bases, text_len;
     uint8_t* text;
 };
-constexpr uint32_t kSvBlockShift = 11, kSvBlock = 1u << kSvBlockShift;
+constexpr uint32_t kSvBlockShift = 11;   // one coarse-index entry per 2048 output bases
 
 __global__ void __launch_bounds__(kSvThreads) sv_materialize_kernel(const SvHapArgs A) {
     __shared__ uint64_t s_line0; __shared__ uint32_t s_col0;
