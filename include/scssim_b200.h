@@ -229,6 +229,8 @@ void scs_shard_range(uint64_t n, int rank, int world, uint64_t* lo, uint64_t* hi
 void scs_shard_sequences(const uint64_t* lens, size_t n, int rank, int world, size_t* lo, size_t* hi);
 
 const char* scs_version(void);
+/* Number of CUDA devices visible to the library (0 when there is no usable driver). */
+int scs_device_count(void);
 
 #ifdef __cplusplus
 }

@@ -86,7 +86,7 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_set_shard_weight", "scs_create_frags", "scs_amplify",
            "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
-           "scs_version",
+           "scs_version", "scs_device_count",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
            "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer"]
 

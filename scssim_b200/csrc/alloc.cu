@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) parity_slots_kernel(uint32_t* __restrict_
 int set_read_counts(scs_ctx* c) {
     if (!c->amplified) return c->fail(SCS_E_STATE, "scs_set_read_counts: call scs_amplify first");
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_set_read_counts: no profile loaded");
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
+    StageTimer timer(c);
     const uint64_t n = c->fulls.n;   // local
     const ListGeom G = c->full_geom;
     uint64_t N = 0; for (int b = 0; b < G.nb; b++) N += G.gtot[b];   // all ranks
@@ -313,8 +313,7 @@ int set_read_counts(scs_ctx* c) {
         c->global_view = true;
         SCS_CUDA(c, cudaStreamSynchronize(c->st));
     }
-    cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_alloc = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SCS_CUDA(c, timer.stop(&c->stats.ms_alloc));
     c->have_counts = true;
     return SCS_OK;
 }

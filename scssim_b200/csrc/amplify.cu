@@ -472,7 +472,7 @@ struct Round {
 int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
     if (!c->have_frags) return c->fail(SCS_E_STATE, "scs_amplify: call scs_create_frags first");
     if (c->P.world > 1 && c->replay.on) return c->fail(SCS_E_UNSUPPORTED, "replay runs on one rank only (the reference's logs are sequential)");
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st);
+    StageTimer timer(c);
     Round R(c); R.g = c->dev_genome();
     R.thr_ber = (uint32_t)std::min<uint64_t>(count_unit_lt(3.4e-4), 0xFFFFFFFFull);
     SCS_CUDA(c, R.dcount.reserve(1)); SCS_CUDA(c, R.ticket.reserve(1)); SCS_CUDA(c, R.flags.reserve(1));
@@ -495,8 +495,7 @@ int amplify(scs_ctx* c) {   // Malbac::amplify, Malbac.cpp:173-201
         if ((rc = R.pass<false>(i + 1, c->semis.n, c->semis.desc.p, c->semis.primers.p, c->semis.errref.p, c->fulls, c->full_geom))) return rc;
         if (i < 4) if ((rc = R.pass<true>(i + 1, nF, c->frag_desc.p, c->frag_primers.p, nullptr, c->semis, c->semi_geom))) return rc;
     }
-    cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_amplify = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SCS_CUDA(c, timer.stop(&c->stats.ms_amplify));
     c->stats.n_semis = c->semis.n; c->stats.n_fulls = c->fulls.n;
     c->stats.n_semis_global = 0; for (int b = 0; b < c->semi_geom.nb; b++) c->stats.n_semis_global += c->semi_geom.gtot[b];
     c->stats.n_fulls_global = 0; for (int b = 0; b < c->full_geom.nb; b++) c->stats.n_fulls_global += c->full_geom.gtot[b];

@@ -6,6 +6,7 @@
 #include "ctx.h"
 #include "fasta_host.h"
 #include "file_sink.h"
+#include "slab_sink.h"
 #include "simuvars_plan.h"
 
 using namespace scs;
@@ -15,6 +16,8 @@ static std::string g_create_error;
 extern "C" {
 
 const char* scs_version(void) { return "scssim_b200 0.1 (sm_100a)"; }
+
+int scs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; } return n; }
 
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
@@ -58,7 +61,7 @@ void scs_destroy(scs_ctx* c) {
     if (dev) {
         cudaSetDevice(c->P.device); alloc_stream() = c->st;
         cudaDeviceSynchronize();
-        for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) if (c->slab_host[b][f]) cudaFreeHost(c->slab_host[b][f]);
+        for (int f = 0; f < 2; f++) for (char* q : c->ring_host[f]) cudaFreeHost(q);
         if (c->rscratch.htotals) cudaFreeHost(c->rscratch.htotals);
         for (int b = 0; b < 2; b++) if (c->sv_pinned[b]) cudaFreeHost(c->sv_pinned[b]);
     }
@@ -74,6 +77,7 @@ const char* scs_last_error(const scs_ctx* c) { return c ? c->err.c_str() : g_cre
 
 int scs_load_profile(scs_ctx* c, const char* path) {
     if (!c || !path) return SCS_E_ARG;
+    if (c->have_device) { cudaSetDevice(c->P.device); alloc_stream() = c->st; }   // upload_profile allocates on this context's device / stream
     if (!c->prof.load(path, c->P.paired != 0, c->P.isize)) return c->fail(SCS_E_IO, c->prof.error);
     c->have_profile = true; c->have_counts = false;
     return upload_profile(c);
@@ -117,7 +121,8 @@ int scs_yield_reads_sink(scs_ctx* c, scs_sink_fn sink, void* user) {
     if (!c) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
     cudaSetDevice(c->P.device); alloc_stream() = c->st;
-    return yield_reads(c, sink, user);
+    CallbackConsumer cb(sink, user);
+    return yield_reads(c, cb);
 }
 
 int scs_yield_reads(scs_ctx* c, const char* prefix) {   // Malbac.cpp:426-435: <prefix>_1.fq/_2.fq or <prefix>.fq
@@ -326,7 +331,7 @@ int64_t scs_dump(scs_ctx* c, int what, void* buf, uint64_t cap) {
 int scs_test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
                      uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len) {
     if (!c) return SCS_E_ARG;
-    if (c->have_device) cudaSetDevice(c->P.device); alloc_stream() = c->st;
+    if (c->have_device) { cudaSetDevice(c->P.device); alloc_stream() = c->st; }
     return test_predict(c, src, n_reads, is_read1, real, stride_real, ints, stride_int, out_seq, out_qual, out_stride, out_len);
 }
 

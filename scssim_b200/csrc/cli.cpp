@@ -2,7 +2,12 @@
 // output files as the reference's CLI (/root/reference/src/scssim.cpp:23-76,109-172,285-404,421-485), driving
 // the CUDA path through the C ABI. `-t` (the reference's worker-thread count) sets the number of host
 // threads that write the FASTQ slabs to the files: the compute runs on the GPU. Extra long-only flags: --seed <u64>, --device <n>.
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <cerrno>
 
 #include <condition_variable>
 #include <cstdio>
@@ -18,6 +23,26 @@
 #include "scssim_b200.h"
 
 using namespace std;
+
+// .gz input is expanded beside the input like the reference does (lib/genome/Genome.cpp:183-187), but without a shell:
+// gzip runs through fork/execvp with its stdout redirected, so paths with spaces or shell metacharacters are just paths.
+static bool gunzip_beside(const string& gz, string* out) {
+    *out = gz.substr(0, gz.size() - 3);
+    int fd = open(out->c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return false;
+    pid_t pid = fork();
+    if (pid < 0) { close(fd); return false; }
+    if (pid == 0) {
+        dup2(fd, 1); close(fd);
+        execlp("gzip", "gzip", "-cd", "--", gz.c_str(), (char*)NULL);
+        _exit(127);
+    }
+    close(fd);
+    int st = 0;
+    while (waitpid(pid, &st, 0) < 0) if (errno != EINTR) return false;
+    return WIFEXITED(st) && WEXITSTATUS(st) == 0;
+}
+static bool is_gz(const string& p) { return p.size() > 3 && p.compare(p.size() - 3, 3, ".gz") == 0; }
 
 static void usage(const char* app) {
     cerr << "\nSCSsim version: 1.0 (B200-native genreads)" << endl;
@@ -72,10 +97,10 @@ static int main_simuvars(int argc, char* argv[], time_t start_t) {
     int rc = scs_create(&P, &ctx);
     if (rc) return die(nullptr, rc);
     string fa = refFile;   // .gz input: gunzipped beside the input (lib/genome/Genome.cpp:183-187)
-    if (fa.size() > 3 && fa.substr(fa.size() - 3) == ".gz") {
-        string cmd = "gzip -cd " + fa + " > " + fa.substr(0, fa.size() - 3);
-        if (system(cmd.c_str()) != 0) { cerr << "could not open " << fa << endl; scs_destroy(ctx); return 1; }
-        fa = fa.substr(0, fa.size() - 3);
+    if (is_gz(fa)) {
+        string plain;
+        if (!gunzip_beside(fa, &plain)) { cerr << "could not open " << fa << endl; scs_destroy(ctx); return 1; }
+        fa = plain;
     }
     scs_simuvars_params sp; scs_simuvars_default_params(&sp);
     rc = scs_simuvars(ctx, &sp, fa.c_str(), snpFile.c_str(), varFile.c_str(), outFile.c_str());
@@ -118,22 +143,26 @@ static void usage_genReads(const char* app) {
 // --gpus N: one host thread per GPU in this process; the library's collectives (a few words per amplification pass, once
 // the weight vector) are plain sums through shared memory behind a barrier. (bench.py runs one process per GPU with NCCL.)
 struct ThreadSum {
-    int world; std::mutex mu; std::condition_variable cv; int arrived = 0; long gen = 0;
+    int world; std::mutex mu; std::condition_variable cv; int arrived = 0; long gen = 0; bool aborted = false;
     std::vector<uint64_t> au; std::vector<double> ad;
     explicit ThreadSum(int w) : world(w) {}
+    // a worker that fails calls this before it returns: everybody waiting in (or arriving at) a sum gets a non-zero result
+    void abort() { std::lock_guard<std::mutex> lk(mu); aborted = true; cv.notify_all(); }
     template <class T> int sum(std::vector<T>& acc, T* buf, size_t n) {
         std::unique_lock<std::mutex> lk(mu);
+        if (aborted) return 1;
         if (arrived == 0) acc.assign(n, T(0));
         for (size_t i = 0; i < n; i++) acc[i] += buf[i];
         long g = gen;
         if (++arrived == world) { arrived = 0; gen++; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g; });
+        else cv.wait(lk, [&] { return gen != g || aborted; });
+        if (aborted) return 1;
         for (size_t i = 0; i < n; i++) buf[i] = acc[i];
         // second phase: nobody may start the next sum (and clear acc) before everyone has copied the result out
         long g2 = gen;
         if (++arrived == world) { arrived = 0; gen++; cv.notify_all(); }
-        else cv.wait(lk, [&] { return gen != g2; });
-        return 0;
+        else cv.wait(lk, [&] { return gen != g2 || aborted; });
+        return aborted ? 1 : 0;
     }
 };
 static int sum_u64(void* u, uint64_t* b, size_t n) { ThreadSum* t = (ThreadSum*)u; return t->sum(t->au, b, n); }
@@ -213,10 +242,14 @@ int main(int argc, char* argv[]) {
 
     if (gpus > 1) {
         string fa = inputFile;
-        if (fa.size() > 3 && fa.substr(fa.size() - 3) == ".gz") {
-            string cmd = "gzip -cd " + fa + " > " + fa.substr(0, fa.size() - 3);
-            if (system(cmd.c_str()) != 0) { cerr << "could not open " << fa << endl; return 1; }
-            fa = fa.substr(0, fa.size() - 3);
+        if (is_gz(fa)) {
+            string plain;
+            if (!gunzip_beside(fa, &plain)) { cerr << "could not open " << fa << endl; return 1; }
+            fa = plain;
+        }
+        if (!getenv("SCS_CLI_SAME_DEVICE") && P.device + gpus > scs_device_count()) {
+            cerr << "Error: --gpus " << gpus << " from device " << P.device << " needs " << P.device + gpus << " CUDA devices, found " << scs_device_count() << endl;
+            return 1;
         }
         ThreadSum coll(gpus);
         std::vector<int> rcs(gpus, 0); std::vector<string> errs(gpus);
@@ -227,13 +260,11 @@ int main(int argc, char* argv[]) {
             Q.device = getenv("SCS_CLI_SAME_DEVICE") ? P.device : P.device + r;   // test hook: all workers on one GPU
             scs_ctx* c = nullptr;
             int rc = scs_create(&Q, &c);
-            if (rc) { errs[r] = scs_last_error(nullptr); rcs[r] = rc; return; }
+            if (rc) { errs[r] = scs_last_error(nullptr); rcs[r] = rc; coll.abort(); return; }
             scs_set_collectives(c, sum_u64, sum_f64, &coll);
-            // a failure before the first collective would leave the other workers waiting: inputs are checked by every
-            // worker identically (same files), so they fail together
             if ((rc = scs_load_genome(c, fa.c_str())) || (rc = scs_load_profile(c, modelFile.c_str())) || (rc = scs_create_frags(c)) ||
                 (rc = scs_amplify(c)) || (rc = scs_set_read_counts(c)) || (rc = scs_yield_reads(c, outputPrefix.c_str()))) {
-                errs[r] = scs_last_error(c); rcs[r] = rc;
+                errs[r] = scs_last_error(c); rcs[r] = rc; coll.abort();   // the other workers leave their collectives with an error
             }
             scs_stats st; scs_get_stats(c, &st); reads[r] = st.reads_requested;
             scs_destroy(c);
@@ -241,7 +272,10 @@ int main(int argc, char* argv[]) {
         std::vector<std::thread> ts;
         for (int r = 0; r < gpus; r++) ts.emplace_back(worker, r);
         for (auto& t : ts) t.join();
-        for (int r = 0; r < gpus; r++) if (rcs[r]) { cerr << errs[r] << endl; return rcs[r] == SCS_E_IO ? -1 : 1; }
+        // report the worker that failed first-hand, not the ones that were released from a collective by its failure
+        int bad = -1;
+        for (int r = 0; r < gpus; r++) if (rcs[r] && (bad < 0 || errs[bad].find("callback failed") != string::npos)) bad = r;
+        if (bad >= 0) { cerr << errs[bad] << endl; return rcs[bad] == SCS_E_IO ? -1 : 1; }
         cerr << "\nNumber of reads to generate: " << reads[0] << endl << "\n*****Producing reads*****" << endl;
         // shards <prefix>.rank<r>... are concatenated in rank order into the reference's file names
         for (int r = 0; r < gpus; r++) {
@@ -261,10 +295,10 @@ int main(int argc, char* argv[]) {
     if (rc) return die(nullptr, rc);
     // .gz input: the reference gunzips beside the input (lib/genome/Genome.cpp:183-187)
     string fa = inputFile;
-    if (fa.size() > 3 && fa.substr(fa.size() - 3) == ".gz") {
-        string cmd = "gzip -cd " + fa + " > " + fa.substr(0, fa.size() - 3);
-        if (system(cmd.c_str()) != 0) { cerr << "could not open " << fa << endl; scs_destroy(ctx); return 1; }
-        fa = fa.substr(0, fa.size() - 3);
+    if (is_gz(fa)) {
+        string plain;
+        if (!gunzip_beside(fa, &plain)) { cerr << "could not open " << fa << endl; scs_destroy(ctx); return 1; }
+        fa = plain;
     }
     if ((rc = scs_load_genome(ctx, fa.c_str()))) return die(ctx, rc);
     cerr << "\nReference sequence was loaded from file " << inputFile << endl;

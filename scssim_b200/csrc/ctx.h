@@ -148,7 +148,7 @@ struct AmpScratch {
 
 // persistent scratch of the read stage (no allocation inside the slab loop)
 struct ReadScratch {
-    DevBuf<uint32_t> plan, size1, size2, nfail, hdrno;
+    DevBuf<uint32_t> size1, size2, nfail, hdrno;
     DevBuf<uint64_t> off1, off2, scan, totals;
     DevBuf<int> flags; DevBuf<unsigned long long> records;
     DevBuf<char> stage[2];         // fixed-stride records of one slab per file (staged emit), packed by compact_records_kernel
@@ -207,8 +207,8 @@ struct scs_ctx {
     scs_simuvars_stats sv_stats{}; std::string sv_warnings;
 
     // FASTQ slabs
-    scs::DevBuf<char> slab_dev[2][2];   // [buffer][file]
-    char* slab_host[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    scs::DevBuf<char> slab_dev[2][2];   // [buffer][file] packed device slabs
+    std::vector<char*> ring_host[2];    // [file] ring of pinned host slots the slabs are copied into (slab_sink.h)
     uint64_t slab_cap = 0;
 
     int fail(int code, const std::string& msg) { err = msg; return code; }
@@ -224,6 +224,23 @@ struct scs_ctx {
 #define SCS_LAUNCHED(ctx) ((ctx)->stats.kernel_launches++)
 
 namespace scs {
+// CUDA-event timer of one stage on the compute stream. Every exit path of the stage (errors included) drains the stream and
+// frees the events, so a caller that retries on the same context never races with work left over from the failed call.
+struct StageTimer {
+    scs_ctx* c; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    explicit StageTimer(scs_ctx* ctx) : c(ctx) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->st); }
+    StageTimer(const StageTimer&) = delete;
+    StageTimer& operator=(const StageTimer&) = delete;
+    cudaError_t stop(double* ms) {
+        cudaEventRecord(e1, c->st);
+        cudaError_t e = cudaStreamSynchronize(c->st);
+        float f = 0; if (e == cudaSuccess) cudaEventElapsedTime(&f, e0, e1);
+        *ms = f;
+        return e;
+    }
+    ~StageTimer() { cudaStreamSynchronize(c->st); cudaEventDestroy(e0); cudaEventDestroy(e1); }
+};
+
 // blocking copy ordered on the context's compute stream (device buffers are stream-ordered allocations)
 inline cudaError_t memcpy_sync(scs_ctx* c, void* dst, const void* src, size_t n, cudaMemcpyKind kind) {
     cudaError_t e = cudaMemcpyAsync(dst, src, n, kind, c->st);
@@ -251,7 +268,8 @@ int upload_profile(scs_ctx* c);
 int create_frags(scs_ctx* c);
 int amplify(scs_ctx* c);
 int set_read_counts(scs_ctx* c);
-int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user);
+struct SlabConsumer;
+int yield_reads(scs_ctx* c, SlabConsumer& sink);
 int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
                  uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len);
 int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written);

@@ -4,6 +4,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 
 namespace scs {
 
@@ -42,6 +43,7 @@ void ParallelFileWriter::worker() {
         bool ok = true;
         while (t.n) {
             ssize_t w = ::pwrite(t.fd, t.p, t.n, (off_t)t.off);
+            if (w < 0 && errno == EINTR) continue;
             if (w <= 0) { ok = false; break; }
             t.p += w; t.n -= (size_t)w; t.off += (uint64_t)w;
         }

@@ -204,7 +204,6 @@ int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSr
     if (goff >= (1ull << 40)) return c->fail(SCS_E_ARG, "genome too large");
     c->ref_len_sum = refLen; c->ref_len_half = refLen / 2;
     c->genome_bases = goff;
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     SCS_CUDA(c, c->genome_words.reserve(goff / 32 + 2)); SCS_CUDA(c, c->genome_nmask.reserve(goff / 32 + 2));
     DevBuf<unsigned int> bad; SCS_CUDA(c, bad.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(bad.p, 0, 4, c->st));
     // stage ASCII through a bounded device buffer
@@ -212,7 +211,7 @@ int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSr
     DevBuf<uint8_t>& stage = c->genome_stage;
     bool need_stage = false; for (int i = 0; i < n; i++) need_stage |= !src[i].dev;
     if (need_stage) SCS_CUDA(c, stage.reserve(chunk + (chunk >> 4) + 4096));
-    cudaEventRecord(e0, c->st);
+    StageTimer timer(c);
     for (int i = 0; i < n; i++) {
         if (src[i].dev) {   // contiguous bases already in device memory (simuvars -> genome without a text round trip)
             uint64_t nw = (lens[i] + 31) >> 5;
@@ -245,11 +244,9 @@ int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSr
             }
         }
     }
-    cudaEventRecord(e1, c->st);
+    SCS_CUDA(c, timer.stop(&c->stats.ms_pack));
     unsigned int hbad = 0;
-    SCS_CUDA(c, cudaMemcpyAsync(&hbad, bad.p, 4, cudaMemcpyDeviceToHost, c->st));
-    SCS_CUDA(c, cudaStreamSynchronize(c->st));
-    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); c->stats.ms_pack = ms; cudaEventDestroy(e0); cudaEventDestroy(e1);
+    SCS_CUDA(c, memcpy_sync(c, &hbad, bad.p, 4, cudaMemcpyDeviceToHost));
     c->genome_has_n = hbad ? 1 : 0;
     c->stats.n_sequences = n; c->stats.genome_bases = 0; for (auto l : c->seq_len) c->stats.genome_bases += l;
     c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;

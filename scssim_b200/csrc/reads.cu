@@ -6,10 +6,11 @@
 // (lib/profile/Profile.cpp:1482-1697), the sprintf/strncpy record formatting (Amplicon.cpp:459-541)
 // and SeqWriter::write (lib/seqwriter/SeqWriter.cpp:41-54).
 //
-// Per slab of consecutive slots:  plan (lengths)  ->  exclusive scan (byte offsets)  ->  emit.
-// Both kernels walk the slot's draw stream with the same cursors the reference's sequential code
-// would have, but evaluate 64 positions per step (2 per lane, one Philox4x32 block per lane) and
-// resolve the rare indel events with a ballot, so a read costs ~RL/32 steps instead of RL.
+// Per slab of consecutive slots:  emit (fixed-stride staging + record sizes)  ->  exclusive scan (byte
+// offsets)  ->  compaction into the packed slab  ->  D2H into the pinned host ring.
+// The emit kernel walks the slot's draw stream with the same cursors the reference's sequential code
+// would have, but evaluates 64 positions per step (2 per lane, one Philox4x32 block per lane) and
+// resolves the rare indel events with a ballot, so a read costs ~RL/32 steps instead of RL.
 // All sampling is integer compares against the threshold tables built on the host. Records are
 // assembled in shared memory at the destination's 16-byte phase and stored with 128-bit stores.
 #include <algorithm>
@@ -19,6 +20,7 @@
 
 #define SCS_PHILOX_OUTLINE 1
 #include "ctx.h"
+#include "slab_sink.h"
 
 namespace scs {
 
@@ -319,11 +321,10 @@ __device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ s
     return lo;
 }
 
-// Shared body of the plan and emit kernels for one slot.
-template <bool EMIT, bool STAGED = false>
+// One slot (SE read / PE pair): every record goes to its slot's fixed-stride place in the staging buffer and its size is recorded;
+// compact_records_kernel packs them afterwards.
 __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
-                                        WarpScratch* ws, uint32_t* __restrict__ plan, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
-                                        const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2, char* __restrict__ out1,
+                                        WarpScratch* ws, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, char* __restrict__ out1,
                                         char* __restrict__ out2, int* flags, unsigned long long* records) {
     const uint64_t slot = A.slot0 + ls;
     const uint64_t a = find_amplicon(A.slot_base, A.n_amp, slot, lane);
@@ -333,10 +334,7 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot - A.fail_base] : (uint32_t)(slot - sb) + 1u;
     const uint32_t ampIdx = A.amp_gidx ? (uint32_t)__ldg(A.amp_gidx + a) : (uint32_t)a;
     const uint64_t entity = __ldg(A.slot_gbase + a) + (slot - sb);
-    if (fragNo == 0 || ampLen < RL) {   // dropped slot / Amplicon.cpp:442
-        if (!EMIT && lane == 0) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; }
-        return;
-    }
+    if (fragNo == 0 || ampLen < RL) return;   // dropped slot / Amplicon.cpp:442 (sizes were zeroed before the launch)
     Stream S; S.init(dsrc, D_READ, entity, entity);
     uint32_t cr = 0, ci = 0;
     int pos = 0, isz = RL;
@@ -348,86 +346,50 @@ __device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, co
     } else {
         pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
     }
-    // the plan kernel needs the bases only when the genome holds N (draw consumption then depends on the sequence)
-    const bool fetch = EMIT || g.has_n;
-    uint32_t nerr = 0; const uint32_t* __restrict__ errs = nullptr;
-    if (fetch) { const uint64_t er = __ldg(A.errref + a); nerr = (uint32_t)(er & 0xFFFF); errs = A.err_pool + (er >> 16); }
-    uint32_t lens = 0;
+    const uint64_t er = __ldg(A.errref + a);
+    const uint32_t nerr = (uint32_t)(er & 0xFFFF); const uint32_t* __restrict__ errs = A.err_pool + (er >> 16);
 #pragma unroll 1
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
-        bool hasN = false;
-        if (fetch) {
-            // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
-            __syncwarp();
-            bool myN = false;
-            for (int i = lane; i < RL; i += 32) {
-                const uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
-                uint32_t b = window_base(g, F.gstart, F.rc, fi);
-                for (uint32_t e = 0; e < nerr; e++) { const uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
-                b = (mate == 1) ? b : comp_code(b);
-                myN |= (b == 4u);
-                ws->ref[i] = (uint8_t)b;
-            }
-            hasN = g.has_n && __any_sync(0xffffffffu, myN);
-            __syncwarp();
+        // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
+        __syncwarp();
+        bool myN = false;
+        for (int i = lane; i < RL; i += 32) {
+            const uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
+            uint32_t b = window_base(g, F.gstart, F.rc, fi);
+            for (uint32_t e = 0; e < nerr; e++) { const uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
+            b = (mate == 1) ? b : comp_code(b);
+            myN |= (b == 4u);
+            ws->ref[i] = (uint8_t)b;
         }
+        const bool hasN = g.has_n && __any_sync(0xffffffffu, myN);
+        __syncwarp();
         int nev = 0;
         const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
-        if (np > kSrcCap) { if (lane == 0) { atomicOr(flags, 8); if (!EMIT) { plan[ls] = 0; size1[ls] = 0; size2[ls] = 0; } } return; }
+        if (np > kSrcCap) { if (lane == 0) atomicOr(flags, 8); return; }
         __syncwarp();
-        if (!EMIT) {
-            if (hasN) {
-                const uint8_t* src = build_source(S, np, nev, lane, ws);
-                subst_quality_pass_n<false>(S, T, nullptr, src, np, mate == 1, cr, ci, lane, nullptr, nullptr);
-            } else cr += 2u * (uint32_t)np;   // the substitution/quality pass draws twice per output base
-            lens |= (uint32_t)np << (mate == 1 ? 0 : 16);
-        } else {
-            const uint8_t* src = build_source(S, np, nev, lane, ws);
-            const uint64_t o = STAGED ? ls * A.stage_stride : ((mate == 1) ? off1[ls] : off2[ls]);
-            const int hl = header_len(ampIdx, fragNo, T.paired);
-            const int total = hl + 2 * np + 4;
-            if (STAGED ? ((uint64_t)total > A.stage_stride) : (o + (uint64_t)total > A.slab_cap)) { if (lane == 0) atomicOr(flags, 16); return; }
-            char* dst = ((mate == 1) ? out1 : out2) + o;
-            char* rec = ws->rec + (reinterpret_cast<uintptr_t>(dst) & 15);
-            if (lane == 0) {
-                write_header(rec, ampIdx, fragNo, T.paired ? mate : 0);
-                rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; rec[hl + 2 * np + 3] = '\n';
-            }
-            if (hasN) subst_quality_pass_n<true>(S, T, Q, src, np, mate == 1, cr, ci, lane, rec + hl, rec + hl + np + 3);
-            else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
-            __syncwarp();
-            copy_out(dst, rec, total, lane);
-            if (STAGED && lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;   // sizes were zeroed before the launch
-        }
-    }
-    if (EMIT && STAGED && lane == 0) atomicAdd(records, T.paired ? 2ull : 1ull);
-    if (!EMIT && lane == 0) {
+        const uint8_t* src = build_source(S, np, nev, lane, ws);
         const int hl = header_len(ampIdx, fragNo, T.paired);
-        plan[ls] = lens;
-        size1[ls] = (uint32_t)(hl + 2 * (int)(lens & 0xFFFF) + 4);
-        size2[ls] = T.paired ? (uint32_t)(hl + 2 * (int)(lens >> 16) + 4) : 0u;
-        atomicAdd(records, T.paired ? 2ull : 1ull);
+        const int total = hl + 2 * np + 4;
+        if ((uint64_t)total > A.stage_stride) { if (lane == 0) atomicOr(flags, 16); return; }
+        char* dst = ((mate == 1) ? out1 : out2) + ls * A.stage_stride;
+        char* rec = ws->rec + (reinterpret_cast<uintptr_t>(dst) & 15);
+        if (lane == 0) {
+            write_header(rec, ampIdx, fragNo, T.paired ? mate : 0);
+            rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; rec[hl + 2 * np + 3] = '\n';
+        }
+        if (hasN) subst_quality_pass_n<true>(S, T, Q, src, np, mate == 1, cr, ci, lane, rec + hl, rec + hl + np + 3);
+        else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
+        __syncwarp();
+        copy_out(dst, rec, total, lane);
+        if (lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;
     }
-}
-
-// plan: output lengths of both mates -> record sizes for the scan (no sequence access: the indel pass only needs draws)
-__global__ void __launch_bounds__(kReadWarps * 32) plan_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, uint32_t* __restrict__ plan,
-                                                               uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, int* flags,
-                                                               unsigned long long* __restrict__ records) {
-    __shared__ WarpScratch scratch[kReadWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t ls = (uint64_t)blockIdx.x * kReadWarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * kReadWarps)
-        do_slot<false>(g, dsrc, T, nullptr, A, ls, lane, &scratch[warp], plan, size1, size2, nullptr, nullptr, nullptr, nullptr, flags, records);
+    if (lane == 0) atomicAdd(records, T.paired ? 2ull : 1ull);
 }
 
 // emit: persistent CTAs (one per SM); the diagonal quality tables are staged in shared memory once per CTA
-// STAGED: no plan / offsets — every record goes to its slot's fixed-stride place in a staging buffer and its size is recorded;
-// compact_records_kernel packs them afterwards (the indel pass then runs once per read instead of twice).
-template <bool STAGED>
-__global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, const uint32_t* __restrict__ plan,
-                                                                  const uint64_t* __restrict__ off1, const uint64_t* __restrict__ off2,
-                                                                  char* __restrict__ out1, char* __restrict__ out2, int* flags,
-                                                                  uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, unsigned long long* __restrict__ records) {
+__global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, char* __restrict__ out1, char* __restrict__ out2,
+                                                                  int* flags, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
+                                                                  unsigned long long* __restrict__ records) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nrows = 4 * T.RL;
@@ -442,22 +404,25 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, Draw
     }
     __syncthreads();
     QualSmem Q; Q.rows = srows; Q.piv = spiv; Q.meta = smeta;
-    for (uint64_t ls = (uint64_t)blockIdx.x * kEmitWarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * kEmitWarps) {
-        if (!STAGED && plan[ls] == 0) continue;
-        do_slot<true, STAGED>(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], nullptr, size1, size2, off1, off2, out1, out2, flags, records);
-    }
+    const int nwarps = (int)(blockDim.x >> 5);   // <= kEmitWarps: long-read profiles leave room for fewer warp scratch areas
+    for (uint64_t ls = (uint64_t)blockIdx.x * nwarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * nwarps)
+        do_slot(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], size1, size2, out1, out2, flags, records);
 }
 
 // pack the staged records of one file: warp per record, 16-byte stores at the destination's alignment, the source realigned by
 // the two-load funnel shifter (load16). HBM-bound: reads and writes every FASTQ byte once (~0.05 ms per 64 MiB slab).
+// A record that would end past `cap` (the slab) is skipped and flagged: the host reports the overflow, nothing is written outside.
 __global__ void __launch_bounds__(256) compact_records_kernel(const char* __restrict__ stage, uint64_t stride, const uint32_t* __restrict__ sizes,
-                                                              const uint64_t* __restrict__ offs, uint64_t n, char* __restrict__ out) {
+                                                              const uint64_t* __restrict__ offs, uint64_t n, char* __restrict__ out, uint64_t cap,
+                                                              int* __restrict__ flags) {
     const int lane = threadIdx.x & 31;
     for (uint64_t ls = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); ls < n; ls += (uint64_t)gridDim.x * 8) {
         const int sz = (int)sizes[ls];
         if (!sz) continue;
+        const uint64_t o = offs[ls];
+        if (o + (uint64_t)sz > cap) { if (lane == 0) atomicOr(flags, 16); continue; }
         const uint8_t* src = reinterpret_cast<const uint8_t*>(stage) + ls * stride;
-        char* dst = out + offs[ls];
+        char* dst = out + o;
         const int head = min(sz, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
         if (lane < head) dst[lane] = (char)src[lane];
         const int nvec = (sz - head) >> 4;
@@ -546,12 +511,54 @@ static ReadTables make_tables(const scs_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------- slab pipeline
-// allocation-free exclusive scan of up to 2048*2048 u32 sizes (one slab batch); total left in *total_dev
-static int scan_sizes(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev) {
-    return scan_u32_noalloc(c, in, out, n, scratch, total_dev);
+namespace {
+
+// events of one run of the stage; every exit path (errors included) first drains both streams, so nothing that was queued
+// can still touch the context's buffers when the caller retries
+struct StageGuard {
+    scs_ctx* c; std::vector<cudaEvent_t> evs;
+    explicit StageGuard(scs_ctx* ctx) : c(ctx) {}
+    cudaEvent_t make(unsigned flags) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, flags); evs.push_back(e); return e; }
+    ~StageGuard() {
+        cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
+        for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    }
+};
+
+}  // namespace
+
+// scs_sink_fn adapter: two ring slots, the user's function runs on the launching thread in slab order
+CallbackConsumer::CallbackConsumer(scs_sink_fn f, void* u) : fn(f), user(u) {}
+int CallbackConsumer::consume_front(bool wait) {
+    if (count == 0) return 0;
+    Pending& q = pend[head];
+    if (wait) { if (cudaEventSynchronize(q.ev) != cudaSuccess) return 1; }
+    else if (cudaEventQuery(q.ev) != cudaSuccess) { (void)cudaGetLastError(); return -1; }   // not landed yet
+    int rc = 0;
+    if (fn) for (int f = 0; f < 2 && !rc; f++) if (q.n[f]) rc = fn(user, f, q.p[f], q.n[f]) ? 1 : 0;
+    q.live = false; head ^= 1; count--;
+    return rc;
+}
+int CallbackConsumer::acquire(int slot) {
+    while (pend[slot].live) { int rc = consume_front(true); if (rc) return rc; }
+    return 0;
+}
+int CallbackConsumer::submit(int slot, cudaEvent_t copied, char* const p[2], const uint64_t bytes[2]) {
+    Pending& q = pend[slot];
+    q.live = true; q.ev = copied; q.p[0] = p[0]; q.p[1] = p[1]; q.n[0] = bytes[0]; q.n[1] = bytes[1];
+    if (count == 0) head = slot;
+    count++;
+    return 0;
+}
+int CallbackConsumer::service() {
+    for (;;) { int rc = consume_front(false); if (rc < 0 || count == 0) return 0; if (rc) return rc; }
+}
+int CallbackConsumer::finish() {
+    while (count) { int rc = consume_front(true); if (rc) return rc; }
+    return 0;
 }
 
-int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
+int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
     if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
     const HostProfile& P = c->prof;
@@ -563,30 +570,35 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     const bool gv = c->global_view;
     const uint64_t slot_lo = gv ? c->g_slot_lo : 0, slot_hi = gv ? c->g_slot_hi : c->n_slots;
     const uint64_t nslots = slot_hi - slot_lo;
-    if (nslots == 0) return SCS_OK;
     const int nfiles = c->P.paired ? 2 : 1;
     const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
-    // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4; the emit kernel bounds-checks every store
+    const uint64_t stride = ((uint64_t)kRecCap + 15) & ~15ull;
+    if (slab < 64 * stride) return c->fail(SCS_E_ARG, "slab_bytes is too small (needs room for 64 records of the largest size, 53 KiB)");
+    if (nslots == 0) return sink.finish() ? c->fail(SCS_E_IO, "FASTQ sink failed") : SCS_OK;
+    // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4. A batch whose records are longer than
+    // that on average (heavy insertion profiles) can exceed the slab: the compaction kernel then skips the records that do not
+    // fit, and the run ends with SCS_E_NOMEM ("raise slab_bytes") — nothing is ever written outside the slab.
     const uint64_t typical = 30 + 2ull * (P.readLength + 8) + 4;
-    const uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(1024, slab / typical), 2048ull * 2048ull);
-    // device + pinned slabs, double buffered
+    const uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(64, slab / typical), 2048ull * 2048ull);
+    const int R = std::max(2, sink.ring_slots());
+    // device slabs (double buffered) + ring of pinned host slots; both keep their capacity between calls
     if (c->slab_cap != slab) {
-        for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) {
-            c->slab_dev[b][f].release();
-            if (c->slab_host[b][f]) { cudaFreeHost(c->slab_host[b][f]); c->slab_host[b][f] = nullptr; }
-        }
+        for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) c->slab_dev[b][f].release();
+        for (int f = 0; f < 2; f++) { for (char* q : c->ring_host[f]) cudaFreeHost(q); c->ring_host[f].clear(); }
         c->slab_cap = slab;
     }
-    for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) if (!c->slab_host[b][f]) {
-        SCS_CUDA(c, c->slab_dev[b][f].reserve(slab + 64));
-        SCS_CUDA(c, cudaMallocHost((void**)&c->slab_host[b][f], slab + 64));
+    for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) if (!c->slab_dev[b][f].p) SCS_CUDA(c, c->slab_dev[b][f].reserve(slab + 64));
+    for (int f = 0; f < nfiles; f++) while ((int)c->ring_host[f].size() < R) {
+        char* q = nullptr;
+        SCS_CUDA(c, cudaMallocHost((void**)&q, slab + 4096 + 64));   // + one block: file sinks place the slab at its file offset mod 4096
+        c->ring_host[f].push_back(q);
     }
     ReadTables T = make_tables(c);
     Genome g = c->dev_genome();
     DrawSrc dsrc = draw_src(c, D_READ);
     SlabArgs A; A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
     A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
-    A.fail_base = 0;
+    A.fail_base = 0; A.stage_stride = stride;
     if (gv) {
         g.words = c->g_words.p; g.nmask = c->g_nmask.p; g.n_bases = c->g_bases; g.has_n = c->g_has_n;
         A.slot_gbase = c->g_slot_base.p; A.amp_gidx = nullptr; A.n_amp = c->g_n_amp; A.slot_base = c->g_slot_base.p;
@@ -594,9 +606,9 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
     }
     ReadScratch& W = c->rscratch;
     SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));
-    SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
-    SCS_CUDA(c, W.plan.reserve(batch + 1)); SCS_CUDA(c, W.size1.reserve(batch + 1)); SCS_CUDA(c, W.size2.reserve(batch + 1));
+    SCS_CUDA(c, W.size1.reserve(batch + 1)); SCS_CUDA(c, W.size2.reserve(batch + 1));
     SCS_CUDA(c, W.off1.reserve(batch + 1)); SCS_CUDA(c, W.off2.reserve(batch + 1)); SCS_CUDA(c, W.scan.reserve(2 * 2048 + 16));
+    for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
     // slab byte totals are written by the scan kernel straight into mapped pinned memory: a D2H memcpy on the compute
     // stream would queue behind the previous slab's 0.5 GB copy on the same copy engine and stall the emit kernel
     if (!W.htotals) {
@@ -604,16 +616,31 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         SCS_CUDA(c, cudaHostGetDevicePointer((void**)&W.dtotals_mapped, W.htotals, 0));
     }
     int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t emit_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4 + sizeof(WarpScratch) * kEmitWarps;
-    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-    cudaEvent_t e0, e1, etot, ecopy[2], ekern[2];
-    cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreateWithFlags(&etot, cudaEventDisableTiming);
-    for (int b = 0; b < 2; b++) { cudaEventCreateWithFlags(&ecopy[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&ekern[b], cudaEventDisableTiming); }
-    std::vector<cudaEvent_t> tev;   // per batch: plan start, emit start, emit end
-    const bool no_d2h_env = getenv("SCS_NO_D2H") != nullptr;
-    cudaEvent_t etotb[2]; for (int b = 0; b < 2; b++) cudaEventCreateWithFlags(&etotb[b], cudaEventDisableTiming);
-    cudaEventRecord(e0, c->st);
+    // shared memory of a persistent emit CTA: the diagonal quality tables + one scratch area per warp; as many warps (<= 24) as fit
+    const size_t table_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4;
+    int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const int emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(table_smem, (size_t)smem_max)) / sizeof(WarpScratch));
+    if (emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
+    const size_t emit_smem = table_smem + sizeof(WarpScratch) * (size_t)emit_warps;
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+
+    StageGuard G(c);   // from here on every return drains the streams and frees the events
+    SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
+    cudaEvent_t e0 = G.make(cudaEventDefault), e1 = G.make(cudaEventDefault);
+    cudaEvent_t ecopy[2], ekern[2], etotb[2], tq[2][4]; bool timed[2] = {false, false};
+    for (int b = 0; b < 2; b++) {
+        ecopy[b] = G.make(cudaEventDisableTiming); ekern[b] = G.make(cudaEventDisableTiming); etotb[b] = G.make(cudaEventDisableTiming);
+        for (int q = 0; q < 4; q++) tq[b][q] = G.make(cudaEventDefault);
+    }
+    std::vector<cudaEvent_t> eslot(R); for (int i = 0; i < R; i++) eslot[i] = G.make(cudaEventDisableTiming);
+    double msk = 0, mse = 0;
+    auto harvest = [&](int b) {   // kernel times of the slab that used buffer b (its events are complete: a later event was waited for)
+        if (!timed[b]) return;
+        float x = 0, y = 0;
+        if (cudaEventElapsedTime(&x, tq[b][0], tq[b][3]) == cudaSuccess && cudaEventElapsedTime(&y, tq[b][1], tq[b][2]) == cudaSuccess) { msk += x; mse += y; }
+        timed[b] = false;
+    };
+    SCS_CUDA(c, cudaEventRecord(e0, c->st));
     // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
     if (c->P.paired && P.maxInsert > 1000) {
         // the numbering of an amplicon's pairs depends on all of its earlier pairs: cover whole amplicons around the range
@@ -633,138 +660,68 @@ int yield_reads(scs_ctx* c, scs_sink_fn sink, void* user) {
         fail_scan_kernel<<<(unsigned)((F.nslots + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
         A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p; A.fail_base = ext_lo;
     }
-    // ---- staged path (default): emit -> scan of the recorded sizes -> compaction. One indel pass per read instead of two. -----
-    std::vector<cudaEvent_t> tev4;   // per slab: start, emit start, emit end, end
-    const bool staged = getenv("SCS_TWO_PASS") == nullptr;
-    if (staged) {
-        const uint64_t stride = ((uint64_t)kRecCap + 15) & ~15ull;
-        A.stage_stride = stride;
-        for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
-        struct Slab { bool launched = false, copying = false; uint64_t bytes[2] = {0, 0}; } sl[2];
-        // the kernels of buffer b have been launched: wait for the byte totals, start the copy (it waits for the compaction on the device)
-        auto finalize = [&](int b) -> int {
-            if (!sl[b].launched) return SCS_OK;
-            SCS_CUDA(c, cudaEventSynchronize(etotb[b]));
-            sl[b].launched = false;
-            const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};
-            if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
-            SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
-            if (!no_d2h_env) for (int f = 0; f < nfiles; f++) if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(c->slab_host[b][f], c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
-            SCS_CUDA(c, cudaEventRecord(ecopy[b], c->st_copy));
-            sl[b].copying = true; sl[b].bytes[0] = tot[0]; sl[b].bytes[1] = tot[1];
-            c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
-            return SCS_OK;
-        };
-        auto drain_s = [&](int b) -> int {
-            if (!sl[b].copying) return SCS_OK;
-            SCS_CUDA(c, cudaEventSynchronize(ecopy[b]));
-            sl[b].copying = false;
-            if (sink) for (int f = 0; f < nfiles; f++) if (sl[b].bytes[f]) if (sink(user, f, c->slab_host[b][f], sl[b].bytes[f])) return c->fail(SCS_E_IO, "FASTQ sink failed");
-            return SCS_OK;
-        };
-        int b = 0;
-        for (uint64_t s0 = slot_lo; s0 < slot_hi; s0 += batch, b ^= 1) {
-            const uint64_t m = std::min(batch, slot_hi - s0);
-            A.slot0 = s0; A.nslots = m;
-            cudaEvent_t q0, q1, q2, q3; cudaEventCreate(&q0); cudaEventCreate(&q1); cudaEventCreate(&q2); cudaEventCreate(&q3);
-            tev4.push_back(q0); tev4.push_back(q1); tev4.push_back(q2); tev4.push_back(q3);
-            cudaEventRecord(q0, c->st);
-            SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
-            if (nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
-            cudaEventRecord(q1, c->st);
-            emit_kernel<true><<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, nullptr, nullptr, nullptr, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr,
-                                                                         W.flags.p, W.size1.p, W.size2.p, W.records.p);
-            SCS_LAUNCHED(c); c->stats.emit_launches++;
-            cudaEventRecord(q2, c->st);
-            if (int rc = scan_sizes(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;
-            if (nfiles == 2) { if (int rc = scan_sizes(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 2 * b + 1)) return rc; }
-            SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
-            cudaEventRecord(q3, c->st);   // kernel time of the slab without the compaction (~0.05 ms), which may wait for a copy
-            // the packed device slab b is free once the copy of the slab two back is done
-            SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));
-            const unsigned cgrid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)sms * 16);
-            compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[0].p, stride, W.size1.p, W.off1.p, m, c->slab_dev[b][0].p); SCS_LAUNCHED(c);
-            if (nfiles == 2) { compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[1].p, stride, W.size2.p, W.off2.p, m, c->slab_dev[b][1].p); SCS_LAUNCHED(c); }
-            SCS_CUDA(c, cudaEventRecord(ekern[b], c->st));
-            sl[b].launched = true;
-            if (int rc = finalize(b ^ 1)) return rc;   // slab k-1: totals known -> copy queued behind its compaction
-            if (int rc = drain_s(b)) return rc;        // slab k-2: copied -> sink; its pinned buffer is free for slab k
+    // ---- per slab: emit (staging + sizes) -> scans -> compaction into the packed device slab -> D2H into a pinned ring slot.
+    // Software-pipelined on the host: slab k is launched before the host waits for the byte totals of slab k-1, so the kernels
+    // run back to back; the consumer is serviced in between.
+    struct DevSlab { bool launched = false; uint64_t k = 0; } dv[2];
+    auto finalize = [&](int b) -> int {   // the kernels of device buffer b were launched: wait for the byte totals, queue the copy behind the compaction
+        if (!dv[b].launched) return SCS_OK;
+        SCS_CUDA(c, cudaEventSynchronize(etotb[b]));
+        dv[b].launched = false;
+        const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};
+        if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
+        const int slot = (int)(dv[b].k % (uint64_t)R);
+        if (sink.acquire(slot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
+        char* p[2] = {nullptr, nullptr};
+        for (int f = 0; f < nfiles; f++) {
+            p[f] = c->ring_host[f][slot] + (sink.phase(f) & 4095);
+            if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(p[f], c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
         }
-        // the last two slabs, in slab order (b now names the older of the two buffers)
-        if (int rc = finalize(b)) return rc;
-        if (int rc = drain_s(b)) return rc;
-        if (int rc = finalize(b ^ 1)) return rc;
-        if (int rc = drain_s(b ^ 1)) return rc;
-    } else {
-    struct Pending { bool live = false; uint64_t bytes[2] = {0, 0}; } pend[2];
-    auto drain = [&](int b) -> int {
-        if (!pend[b].live) return SCS_OK;
-        cudaError_t e = cudaEventSynchronize(ecopy[b]);
-        if (e != cudaSuccess) return c->fail(SCS_E_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
-        pend[b].live = false;
-        if (sink) for (int f = 0; f < nfiles; f++) if (pend[b].bytes[f]) if (sink(user, f, c->slab_host[b][f], pend[b].bytes[f])) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        SCS_CUDA(c, cudaEventRecord(ecopy[b], c->st_copy));
+        SCS_CUDA(c, cudaEventRecord(eslot[slot], c->st_copy));
+        c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
+        if (sink.submit(slot, eslot[slot], p, tot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
         return SCS_OK;
     };
-    int bi = 0;
-    const bool trace = getenv("SCS_TRACE") != nullptr, no_d2h = getenv("SCS_NO_D2H") != nullptr;
-    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double tr0 = now_ms();
-    for (uint64_t s0 = slot_lo; s0 < slot_hi; s0 += batch, bi ^= 1) {
+    uint64_t k = 0;
+    for (uint64_t s0 = slot_lo; s0 < slot_hi; s0 += batch, k++) {
+        const int b = (int)(k & 1);
         const uint64_t m = std::min(batch, slot_hi - s0);
-        const double ta = now_ms();
-        if (int rc = drain(bi)) return rc;   // buffer bi is free again once its previous copy has been consumed
-        const double tb = now_ms();
         A.slot0 = s0; A.nslots = m;
-        cudaEvent_t t0, t1, t2; cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2); tev.push_back(t0); tev.push_back(t1); tev.push_back(t2);
-        cudaEventRecord(t0, c->st);
-        const unsigned nbp = (unsigned)std::min<uint64_t>((m + kReadWarps - 1) / kReadWarps, (uint64_t)sms * 32);
-        plan_kernel<<<nbp, kReadWarps * 32, 0, c->st>>>(g, dsrc, T, A, W.plan.p, W.size1.p, W.size2.p, W.flags.p, W.records.p); SCS_LAUNCHED(c);
-        W.htotals[0] = W.htotals[1] = 0;
-        if (int rc = scan_sizes(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped)) return rc;
-        if (nfiles == 2) { if (int rc = scan_sizes(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 1)) return rc; }
-        cudaEventRecord(etot, c->st);
-        cudaEventRecord(t1, c->st);
-        emit_kernel<false><<<sms, kEmitWarps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.plan.p, W.off1.p, W.off2.p, c->slab_dev[bi][0].p,
-                                                                      nfiles == 2 ? c->slab_dev[bi][1].p : nullptr, W.flags.p, nullptr, nullptr, nullptr);
+        harvest(b);
+        SCS_CUDA(c, cudaEventRecord(tq[b][0], c->st));
+        SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
+        if (nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
+        SCS_CUDA(c, cudaEventRecord(tq[b][1], c->st));
+        emit_kernel<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p,
+                                                                W.records.p);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
-        cudaEventRecord(t2, c->st);
-        cudaEventRecord(ekern[bi], c->st);
-        SCS_CUDA(c, cudaEventSynchronize(etot));   // byte totals of this slab (the emit kernel is already running)
-        uint64_t tot[2] = {W.htotals[0], W.htotals[1]};
-        if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
-        SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[bi], 0));
-        const double tc = now_ms();
-        if (!no_d2h) for (int f = 0; f < nfiles; f++) if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(c->slab_host[bi][f], c->slab_dev[bi][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
-        cudaEventRecord(ecopy[bi], c->st_copy);
-        pend[bi].live = true; pend[bi].bytes[0] = tot[0]; pend[bi].bytes[1] = tot[1];
-        c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
-        // while this slab is produced and copied, hand the previous one to the sink
-        const double td = now_ms();
-        if (int rc = drain(bi ^ 1)) return rc;
-        if (trace) fprintf(stderr, "[scs trace] batch@%llu: start %.2f drain_own %.2f launch+wait_totals %.2f enqueue_copy %.2f drain_prev %.2f ms\n",
-                           (unsigned long long)s0, ta - tr0, tb - ta, tc - tb, td - tc, now_ms() - td);
+        SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
+        if (int rc = scan_u32_noalloc(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;
+        if (nfiles == 2) { if (int rc = scan_u32_noalloc(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 2 * b + 1)) return rc; }
+        SCS_CUDA(c, cudaEventRecord(tq[b][3], c->st));   // kernel time of the slab without the compaction (~0.05 ms), which may wait for a copy
+        SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
+        timed[b] = true;
+        // the packed device slab b is free once the copy of the slab two back is done
+        SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));
+        const unsigned cgrid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)sms * 16);
+        compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[0].p, stride, W.size1.p, W.off1.p, m, c->slab_dev[b][0].p, slab, W.flags.p); SCS_LAUNCHED(c);
+        if (nfiles == 2) { compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[1].p, stride, W.size2.p, W.off2.p, m, c->slab_dev[b][1].p, slab, W.flags.p); SCS_LAUNCHED(c); }
+        SCS_CUDA(c, cudaEventRecord(ekern[b], c->st));
+        dv[b].launched = true; dv[b].k = k;
+        if (int rc = finalize(b ^ 1)) return rc;   // slab k-1: totals known -> copy queued behind its compaction
+        if (sink.service()) return c->fail(SCS_E_IO, "FASTQ sink failed");
     }
-    if (int rc = drain(0)) return rc;
-    if (int rc = drain(1)) return rc;
-    }   // two-kernel path
+    if (int rc = finalize((int)((k - 1) & 1))) return rc;   // the last slab
+    if (sink.finish()) return c->fail(SCS_E_IO, "FASTQ sink failed");
     SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[0], 0)); SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[1], 0));
-    cudaEventRecord(e1, c->st); SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    SCS_CUDA(c, cudaEventRecord(e1, c->st)); SCS_CUDA(c, cudaStreamSynchronize(c->st));
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-    double msk = 0, mse = 0;
-    for (size_t i = 0; i + 2 < tev.size(); i += 3) {
-        float a = 0, b2 = 0; cudaEventElapsedTime(&a, tev[i], tev[i + 2]); cudaEventElapsedTime(&b2, tev[i + 1], tev[i + 2]); msk += a; mse += b2;
-    }
-    for (size_t i = 0; i + 3 < tev4.size(); i += 4) {
-        float a = 0, b2 = 0; cudaEventElapsedTime(&a, tev4[i], tev4[i + 3]); cudaEventElapsedTime(&b2, tev4[i + 1], tev4[i + 2]); msk += a; mse += b2;
-    }
-    for (auto ev : tev) cudaEventDestroy(ev);
-    for (auto ev : tev4) cudaEventDestroy(ev);
-    for (int b = 0; b < 2; b++) cudaEventDestroy(etotb[b]);
+    harvest(0); harvest(1);
     c->stats.ms_reads = ms; c->stats.ms_reads_kernels = msk; c->stats.ms_emit_kernel = mse;
     int hflags = 0; SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
     unsigned long long hrec = 0; SCS_CUDA(c, memcpy_sync(c, &hrec, W.records.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(etot);
-    for (int b = 0; b < 2; b++) { cudaEventDestroy(ecopy[b]); cudaEventDestroy(ekern[b]); }
     if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
     if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
     if (hflags & 16) return c->fail(SCS_E_NOMEM, "FASTQ slab overflow (raise slab_bytes)");

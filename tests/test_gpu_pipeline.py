@@ -13,16 +13,17 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000, diploid=True, with_n=False):
+def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, coverage, isize, seed, primers=100000, diploid=True, with_n=False,
+              slab_bytes=0, min_slabs=0):
     from scssim_b200 import api
     fa = os.path.join(tmp, f"{name}.fa")
     genome = H.write_genome_with_n(fa, chrom_len, gseed) if with_n else H.write_genome(fa, n_chrom, chrom_len, gseed, diploid=diploid)
-    prof = H.profile_path(profile)
+    prof = profile if os.path.isabs(profile) else H.profile_path(profile)
     args = H.genreads_args(prof, layout, gamma, coverage, isize, primers)
     oprefix, dprefix = os.path.join(tmp, name + "_orc"), os.path.join(tmp, name + "_dump")
     H.run_oracle(fa, oprefix, args, seed=seed, dump_prefix=dprefix)
     od = H.oracle_dump(dprefix)
-    with api.GenReads(primers=primers, gamma=gamma, coverage=coverage, isize=isize, layout=layout, seed=seed) as g:
+    with api.GenReads(primers=primers, gamma=gamma, coverage=coverage, isize=isize, layout=layout, seed=seed, slab_bytes=slab_bytes) as g:
         g.load_profile(prof).load_genome(fa).create_frags()
         fr = g.dump(api.DUMP_FRAGS)
         assert np.array_equal(fr[:, :4], od["frags"][:, :4]), "fragments differ"
@@ -44,6 +45,7 @@ def _run_case(tmp, name, n_chrom, chrom_len, gseed, profile, layout, gamma, cove
     assert f1 == H.read_bytes(names[0]), "FASTQ file 1 differs"
     if layout == "PE":
         assert f2 == H.read_bytes(names[1]), "FASTQ file 2 differs"
+    assert st["emit_launches"] >= min_slabs, f"expected at least {min_slabs} slabs, ran {st['emit_launches']}"
     return st
 
 
@@ -121,3 +123,58 @@ def test_degenerate_inputs_match_the_oracle(tmp_path):
                 b"\n".join(b[i:i + 80].tobytes() for i in range(0, len(b), 80)))       # no newline at the end of the file
     st, exp = both(fa3, "gap", "PE", 5e-10, 6.0)
     assert st["n_fulls"] > 0 and len(exp[0]) > 10_000
+
+
+# ---- the slab pipeline itself against the oracle: many slabs per file, so the double-buffered device slabs, the ring of pinned
+# ---- host slots and the launch-ahead / finalize / consume hand-offs (reads.cu yield_reads) all cycle several times
+@pytest.mark.parametrize("layout,profile,isize,slab", [("PE", "Illumina_HiSeq2500", 260, 1 << 20), ("SE", "Illumina_HiSeq2000", 260, 1 << 20),
+                                                      ("PE", "Illumina_HiSeqXTen", 1200, 1 << 20), ("PE", "Illumina_HiSeq2500", 260, 64 << 10)])
+def test_many_slabs_equal_the_oracle(tmp_path, layout, profile, isize, slab):
+    cov = 40.0 if slab >= (1 << 20) else 4.0
+    st = _run_case(str(tmp_path), f"slabs{layout}{isize}_{slab}", 1, 600_000, 11, profile, layout, 2e-10, cov, isize, seed=31337,
+                   slab_bytes=slab, min_slabs=20)
+    assert st["records"] > 0
+
+
+def test_slabs_with_n_genome_equal_the_oracle(tmp_path):
+    _run_case(str(tmp_path), "slabsN", 1, 300_000, 77, "Illumina_HiSeq2500", "PE", 3e-10, 30.0, 260, seed=9, with_n=True, slab_bytes=1 << 20, min_slabs=10)
+
+
+# ---- the tables bench.py runs on (read length is a property of the .profile: the bench derives 150- / 100-bin profiles by
+# ---- nearest-bin resampling; the oracle reads the same derived file). RL 150 is also the largest shared-memory footprint.
+@pytest.mark.parametrize("src,rl,layout,isize", [("Illumina_HiSeq2500", 150, "PE", 260), ("Illumina_HiSeqXTen", 100, "PE", 260),
+                                                 ("Illumina_HiSeq2500", 150, "SE", 260), ("Illumina_HiSeq2500", 250, "PE", 400)])
+def test_resampled_bench_profiles_equal_the_oracle(tmp_path, src, rl, layout, isize):
+    from scssim_b200.tools.resample_profile import resample
+    prof = os.path.join(str(tmp_path), f"{src}_{rl}.profile")
+    resample(H.profile_path(src), prof, rl)
+    st = _run_case(str(tmp_path), f"res{rl}{layout}", 1, 400_000, 13, prof, layout, 2e-10, 6.0, isize, seed=150 + rl, slab_bytes=4 << 20, min_slabs=2)
+    assert st["records"] > 0
+
+
+def test_slab_limits_are_clean_errors(tmp_path):
+    """A slab that cannot hold 64 of the largest records is refused up front; a batch that outgrows its slab (a profile whose
+    reads are much longer than the typical record the batch was sized for) ends with SCS_E_NOMEM — the compaction kernel skips
+    what does not fit instead of writing past the slab — and the context stays usable with a larger slab."""
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_sequence
+    prof = H.profile_path("Illumina_HiSeq2500")
+    seq = synth_sequence(300_000, 5)
+    with api.GenReads(gamma=2e-10, coverage=8.0, layout="PE", seed=3, slab_bytes=1024) as g:
+        g.load_profile(prof).set_genome([("chrA_1_300000", seq)]).create_frags().amplify()
+        with pytest.raises(api.ScsError) as e:
+            g.yield_reads_bytes()
+        assert e.value.code == api.SCS_E_ARG
+    # insertion rate 0.06: ~7.5 events per read, every read ~18 bases longer than the profile's read length
+    lines = open(prof).read().split("\n")
+    i = lines.index("[Insert Rate]")
+    lines[i + 1] = "0.06"
+    heavy = os.path.join(str(tmp_path), "heavy.profile")
+    open(heavy, "w").write("\n".join(lines))
+    with api.GenReads(gamma=2e-10, coverage=40.0, layout="PE", seed=3, slab_bytes=256 << 10) as g:
+        g.load_profile(heavy).set_genome([("chrA_1_300000", seq)]).create_frags().amplify()
+        with pytest.raises(api.ScsError) as e:
+            g.yield_reads_bytes()
+        assert e.value.code == api.SCS_E_NOMEM, e.value
+    # same profile with a roomy slab: equals the oracle (reads with many indel events)
+    _run_case(str(tmp_path), "heavy", 1, 300_000, 5, heavy, "PE", 2e-10, 8.0, 260, seed=3, slab_bytes=8 << 20)
