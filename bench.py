@@ -1,23 +1,28 @@
 #!/usr/bin/env python
 """bench.py — the `scssim genreads` hot path on B200 (contract: see the task brief; one JSON line on stdout).
 
-Workload at N=1 = BASELINE.json configs[1]: synthetic 250 Mb haploid sequence (GC 35-60 % spectrum), paired-end
-150 bp at 10x with the HiSeq2500 profile (resampled 125 -> 150 bins, scssim_b200/tools/resample_profile.py; read
-length is a property of the .profile in the reference), GC bias on, gamma 2e-10 (README value). The reference's
-`-c` is relative to HALF the summed sequence length and counts individual reads (Malbac.cpp:414-420), so 10x of a
-haploid FASTA is `-c 20`: 16.67 M reads = 8.33 M pairs per step.
+Workload = BASELINE.json configs[3], the configuration the metric is quoted on: ONE synthetic human-scale diploid cell,
+6.2 Gb = 4 chromosomes x 775 Mb x 2 haplotypes (GC 35-60 % per 100 kb block, haplotype 2 = haplotype 1 + 0.1 % SNPs, every
+sequence < 2^31 as the reference's FASTA reader requires), paired-end 150 bp at 30x with the HiSeq2500 profile (resampled
+125 -> 150 bins, scssim_b200/tools/resample_profile.py: read length is a property of the .profile in the reference), GC bias on,
+gamma 2e-10 (README value). The reference's `-c` is relative to HALF the summed sequence length and counts individual reads
+(Malbac.cpp:414-420), so 30x of the 6.2 Gb diploid FASTA = 620 M pairs is `-c 60`: 1.24 G reads, ~394 GB of FASTQ per step.
+The SAME cell is generated at every N (strong scaling): rank r holds its share of the sequences for the amplification, the
+packed genome and the amplicon table are then replicated over NVLink (NCCL) and the cell's read slots are cut into contiguous
+ranges, one per GPU; the rank-ordered shards concatenate to exactly the single-GPU files.
 
-A "step" = one pass of the hot path over that input: MALBAC amplification -> GC-weighted read allocation -> read
-synthesis -> FASTQ packing, FASTQ landing in the library's pinned host ring.
-  value : M reads/s with the packed genome already resident in HBM when the timed region starts (CUDA events).
-  e2e   : the same through the C-ABI calls a user makes with HOST buffers: scs_set_genome (H2D of the ASCII genome
-          from pinned memory + pack) ... scs_yield_reads_sink (D2H of every FASTQ byte) inside the timed region.
-For N > 1 (torchrun) the cell has N such chromosomes, one per rank (weak scaling: per-GPU work fixed). The ranks form ONE
-run: NCCL all-reduces carry the primer budget per amplification round, the per-batch amplicon counts and the cell-wide
-weight vector of the read allocation; every rank then writes its own FASTQ shard.
+A "step" = one pass of the hot path over that cell: MALBAC amplification -> GC-weighted read allocation -> read synthesis ->
+FASTQ packing, FASTQ landing in the library's pinned host ring.
+  value     : M reads/s with the packed genome already resident in HBM when the timed region starts (CUDA events).
+  e2e       : the same through the C-ABI calls a user makes with HOST buffers: scs_set_genome (H2D of the ASCII genome from
+              pinned memory + pack) ... scs_yield_reads_sink (D2H of every FASTQ byte) inside the timed region.
+  e2e_files : through the drop-in call that writes files, scs_yield_reads(prefix) -> <prefix>_1.fq/_2.fq, on the bounded
+              configs[1] cell (5.3 GB of FASTQ per step; the full cell would need 394 GB of scratch disk per step).
+  configs1  : BASELINE configs[1] (250 Mb haploid, PE150 10x) on rank 0's GPU, the round-1 headline, kept for continuity.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref/bin/scssim, built from /root/reference by
-oracle/build_ref.sh) with all host threads on a bounded sample of the same workload.
+oracle/build_ref.sh) with all host threads; every step is one whole `scssim genreads` process on a bounded sample of the same
+workload (a 1/387-scale cell: same GC spectrum, gamma, coverage, profile, layout), and the line says "extrapolated".
 """
 import argparse
 import ctypes as C
@@ -33,13 +38,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-GENOME_LEN = 250_000_000
-COVERAGE = 20.0          # = 10x of a haploid FASTA (see module docstring)
+N_CHROM = 4
+CHROM_LEN = 775_000_000      # x 4 chromosomes x 2 haplotypes = 6.2 Gb
+COVERAGE = 60.0              # = 30x of the diploid FASTA (see module docstring)
 GAMMA = 2e-10
 READ_LEN = 150
-SAMPLE_DIV = 2           # CPU legs run on a 1/2-scale genome (125 Mb, 8.3 M reads), same gamma / coverage / profile: ~20 s of reference work
+ISIZE = 260
+SNP_RATE = 1e-3
+REF_SAMPLE_CHROM = 8_000_000   # the CPU legs run a cell of 1 chromosome x 8 Mb x 2 haplotypes (1/387.5 of the bases and of the reads)
+C1_LEN, C1_COVERAGE = 250_000_000, 20.0   # BASELINE configs[1]
 UNIT = "M reads/s"
-METRIC = "PE150 M reads/s (FASTQ GB/s in config) vs HBM/D2H roofline"
+METRIC = "PE150 M reads/s (FASTQ GB/s in detail) vs HBM/D2H roofline"
 
 
 def bench_profile(tmp):
@@ -50,9 +59,18 @@ def bench_profile(tmp):
     return p
 
 
-def workload_name():
-    return ("synthetic 250 Mb haploid (GC 35-60%), PE150 10x (-c 20, 16.67 M reads/step), HiSeq2500 profile resampled to "
-            "150 bins, GC bias on, gamma 2e-10")
+def bench_config(scale, coverage):
+    """The workload both arms are run on (identical dict in both JSON lines)."""
+    clen = int(CHROM_LEN * scale)
+    reads = int((N_CHROM * 2 * clen // 2) * coverage / READ_LEN)
+    name = (f"BASELINE configs[3]: one synthetic 6.2 Gb diploid cell ({N_CHROM} chromosomes x {CHROM_LEN / 1e6:.0f} Mb x 2 haplotypes, GC 35-60%, "
+            f"haplotype 2 = haplotype 1 + 0.1% SNPs), PE150 30x (-c 60: 1.24 G reads = 620 M pairs per step), HiSeq2500 profile resampled to "
+            f"150 bins, GC bias on, gamma 2e-10, -s 260; the same cell at every N")
+    if scale != 1.0 or coverage != COVERAGE:
+        name = f"DEBUG scale {scale} coverage {coverage} of: " + name
+    return {"workload": name, "layout": "PE", "read_length": READ_LEN, "coverage_flag": coverage, "gamma": GAMMA, "isize": ISIZE,
+            "genome_bases": N_CHROM * 2 * clen, "reads_per_step": reads,
+            "l2": "inputs larger than L2: every step streams the 1.55 GB packed genome and ~394 GB of FASTQ through the 126 MB L2"}
 
 
 class ClockSampler:
@@ -65,7 +83,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -101,50 +119,162 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def run_reference_cpu(tmp, profile, steps, warmup, genome_len=GENOME_LEN):
-    """Reference genreads on the host cores, bounded sample. Returns (M reads/s, cores, sample text, s/step)."""
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def run_reference_cpu(tmp, profile, steps, warmup, coverage, sample_chrom=REF_SAMPLE_CHROM):
+    """The reference's own `scssim genreads -t <cores>` (compiled from /root/reference into oracle/_ref), one whole process per
+    step on the bounded sample cell. Stage times are taken from the moments its own stderr progress lines appear
+    (Malbac.cpp:174,422,437; scssim.cpp:66). Returns a dict."""
     import helpers as H
-    from scssim_b200.synth import synth_sequence, write_fasta
+    from scssim_b200.synth import synth_genome, write_fasta
     exe = os.path.join(ROOT, "oracle", "_ref", "bin", "scssim")
     cores = os.cpu_count() or 1
-    n = genome_len // SAMPLE_DIV
     fa = os.path.join(tmp, "sample.fa")
-    write_fasta(fa, [(f"chrS1_1_{n}", synth_sequence(n, 7001))])
-    reads = int((n // 2) * COVERAGE / READ_LEN)
-    sample = (f"1/{SAMPLE_DIV}-scale genome ({n / 1e6:.1f} Mb haploid, {reads / 1e6:.2f} M reads/step), same gamma/coverage/profile; "
-              f"reference `scssim genreads -t {cores}` whole-process wall time (load+amplify+reads+FASTQ files on local disk)")
-    if not os.path.exists(exe):
-        # no compiled reference on this box: time the CPU oracle (single thread) instead
-        kind, cores = "port", 1
-        cmd = [H.oracle_bin(), "genreads", "-i", fa, "-o", os.path.join(tmp, "cpu"), "--seed", "1"] + H.genreads_args(profile, "PE", GAMMA, COVERAGE, 260)
-        sample = sample.replace(f"reference `scssim genreads -t {os.cpu_count() or 1}`", "CPU oracle (oracle/scs_oracle, 1 thread)")
-    else:
+    write_fasta(fa, synth_genome(1, sample_chrom, 7001, diploid=True, snp_rate=SNP_RATE))
+    reads = int((2 * sample_chrom // 2) * coverage / READ_LEN)
+    frac = sample_chrom / (N_CHROM * CHROM_LEN)
+    if os.path.exists(exe):
         kind = "reference"
-        cmd = [exe, "genreads", "-i", fa, "-t", str(cores), "-o", os.path.join(tmp, "cpu")] + H.genreads_args(profile, "PE", GAMMA, COVERAGE, 260)
-    times = []
+        cmd = [exe, "genreads", "-i", fa, "-t", str(cores), "-o", os.path.join(tmp, "cpu")] + H.genreads_args(profile, "PE", GAMMA, coverage, ISIZE)
+        what = f"reference `scssim genreads -t {cores}` (oracle/_ref, unmodified algorithm)"
+    else:   # no compiled reference on this box: the CPU oracle (single thread)
+        kind, cores = "port", 1
+        cmd = [H.oracle_bin(), "genreads", "-i", fa, "-o", os.path.join(tmp, "cpu"), "--seed", "1"] + H.genreads_args(profile, "PE", GAMMA, coverage, ISIZE)
+        what = "CPU oracle (oracle/scs_oracle, 1 thread)"
+    sample = (f"1/{1 / frac:.1f}-scale cell (1 chromosome x {sample_chrom / 1e6:.0f} Mb x 2 haplotypes, {reads / 1e6:.2f} M reads per step), same GC spectrum / "
+              f"gamma / -c / profile / layout; {what}; one whole process per step (FASTA load + index, amplification, read stage, FASTQ files "
+              f"on local disk); the full-cell figure is EXTRAPOLATED linearly in the number of reads")
+    marks = ["MALBAC amplification", "Number of reads to generate", "Producing reads", "Reads generation done"]
+    walls, stages = [], []
     for i in range(warmup + steps):
         if os.path.exists(fa + ".fai"):
             os.remove(fa + ".fai")
         t0 = time.perf_counter()
-        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        p = subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        seen = {}
+        for line in p.stderr:
+            for m in marks:
+                if m in line and m not in seen:
+                    seen[m] = time.perf_counter() - t0
+        rc = p.wait()
         dt = time.perf_counter() - t0
+        if rc != 0:
+            raise RuntimeError(f"reference arm: {cmd[0]} exited {rc}")
         if i >= warmup:
-            times.append(dt)
-    sec = sum(times) / len(times)
-    return reads / sec / 1e6, cores, sample, sec, kind, reads
+            walls.append(dt)
+            if len(seen) == len(marks):
+                t = [seen[m] for m in marks]
+                stages.append({"load_frags": t[0], "amplify": t[1] - t[0], "alloc": t[2] - t[1], "reads": t[3] - t[2]})
+    sec = sum(walls) / len(walls)
+    st = {k: sum(s[k] for s in stages) / len(stages) for k in stages[0]} if stages else None
+    return {"value": reads / sec / 1e6, "cores": cores, "kind": kind, "sample": sample, "s_per_step": sec, "reads_per_step": reads,
+            "stage_s": st, "reads_stage_value": (reads / st["reads"] / 1e6) if st and st["reads"] > 0 else None,
+            "steps_run": len(walls), "warmup_run": warmup, "extrapolated_full_cell_s": sec / frac}
+
+
+# ------------------------------------------------------------------------------------------------ synthetic cell on the device
+def synth_chromosome_cuda(torch, length, seed, device, out_h1, out_h2):
+    """One chromosome of the synthetic cell, generated on the GPU (plumbing: 6.2 Gb through numpy would take minutes) straight into
+    two pinned host arrays: per-100 kb block GC content ~ U[0.35, 0.60], bases i.i.d. within a block; haplotype 2 = haplotype 1
+    with 0.1 % of its positions substituted (scssim_b200/synth.py is the numpy statement of the same generator)."""
+    gen = torch.Generator(device=device); gen.manual_seed(seed)
+    block, chunk = 100_000, 50_000_000
+    nblk = (length + block - 1) // block
+    gcs = 0.35 + 0.25 * torch.rand(nblk, generator=gen, device=device)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    h1 = torch.from_numpy(out_h1); h2 = torch.from_numpy(out_h2)
+    for lo in range(0, length, chunk):
+        n = min(chunk, length - lo)
+        idx = torch.arange(lo, lo + n, device=device) // block
+        is_gc = torch.rand(n, generator=gen, device=device) < gcs[idx]
+        pick = torch.randint(0, 2, (n,), generator=gen, device=device, dtype=torch.uint8)
+        code = torch.where(is_gc, 1 + pick, 3 * pick)   # A=0 C=1 G=2 T=3 ; GC -> {C,G}, AT -> {A,T}
+        h1[lo:lo + n].copy_(lut[code.long()], non_blocking=False)
+        nsnp = int(n * SNP_RATE)
+        pos = torch.randint(0, n, (nsnp,), generator=gen, device=device)
+        shift = torch.randint(1, 4, (nsnp,), generator=gen, device=device, dtype=torch.uint8)
+        code[pos] = (code[pos] + shift) & 3
+        h2[lo:lo + n].copy_(lut[code.long()], non_blocking=False)
+        del idx, is_gc, pick, code, pos, shift
+    torch.cuda.empty_cache()
+
+
+def probe_host_pipes(torch, ndev):
+    """Which GPUs share a host link? Concurrent pinned D2H from device 0 and device j: if the pair moves clearly more than device
+    0 alone, j sits behind another host pipe. Returns (device order that alternates between the groups, probe record)."""
+    nb = 128 << 20
+    bufs = {}
+    for j in range(ndev):
+        with torch.cuda.device(j):
+            bufs[j] = (torch.empty(nb, dtype=torch.uint8, device=f"cuda:{j}"), torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.cuda.Stream(device=j))
+
+    def run(devs, reps=3):
+        for j in devs:
+            d, h, s = bufs[j]
+            with torch.cuda.stream(s):
+                h.copy_(d, non_blocking=True)
+        for j in devs:
+            bufs[j][2].synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for j in devs:
+                d, h, s = bufs[j]
+                with torch.cuda.stream(s):
+                    h.copy_(d, non_blocking=True)
+        for j in devs:
+            bufs[j][2].synchronize()
+        return reps * nb * len(devs) / (time.perf_counter() - t0) / 1e9
+    single = run([0])
+    pair = {j: run([0, j]) for j in range(1, ndev)}
+    other = [j for j in range(1, ndev) if pair[j] > 1.5 * single]
+    same = [0] + [j for j in range(1, ndev) if j not in other]
+    order = []
+    for i in range(max(len(same), len(other))):
+        if i < len(same):
+            order.append(same[i])
+        if i < len(other):
+            order.append(other[i])
+    rec = {"single_GBps": round(single, 1), "pair_with_gpu0_GBps": {str(j): round(v, 1) for j, v in pair.items()}, "groups": [same, other]}
+    del bufs
+    torch.cuda.empty_cache()
+    return order, rec
+
+
+def device_for_rank(torch, local, world):
+    """Topology-aware device order for N < all GPUs: local ranks alternate between the host pipes that the probe finds, so two or
+    four ranks do not crowd behind one of them. Rank 0 probes and publishes the order; the other ranks read it."""
+    ndev = torch.cuda.device_count()
+    if world <= 1 or world >= ndev or os.environ.get("SCS_BENCH_NO_DEVMAP"):
+        return local, {"order": list(range(ndev)), "probe": None}
+    path = os.path.join(tempfile.gettempdir(), f"scs_devmap_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}.json")
+    if local == 0:
+        order, rec = probe_host_pipes(torch, ndev)
+        with open(path + ".tmp", "w") as f:
+            json.dump({"order": order, "probe": rec}, f)
+        os.replace(path + ".tmp", path)
+    t0 = time.time()
+    while not os.path.exists(path) and time.time() - t0 < 120:
+        time.sleep(0.05)
+    try:
+        with open(path) as f:
+            m = json.load(f)
+    except (OSError, ValueError):
+        m = {"order": list(range(ndev)), "probe": "unavailable"}
+    return m["order"][local], m
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--genome-len", type=int, default=GENOME_LEN, help="(debug) override the workload size; invalidates the number")
+    ap.add_argument("--scale", type=float, default=1.0, help="(debug) fraction of the cell's bases; invalidates the number")
     ap.add_argument("--coverage", type=float, default=COVERAGE, help="(debug) override -c; invalidates the number")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="(debug) skip the CPU leg")
-    ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons (equal shards)")
+    ap.add_argument("--no-extras", action="store_true", help="(debug) skip the configs[1] and e2e_files legs")
+    ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons")
     ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
+    ap.add_argument("--files-dir", default=None, help="directory for the e2e_files leg (default: the system temp dir)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(a.warmup, 0)
@@ -155,74 +285,97 @@ def main():
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
+    config = bench_config(a.scale, a.coverage)
     if a.impl == "reference":
         if rank != 0:
             return 0
         with tempfile.TemporaryDirectory() as tmp:
             profile = bench_profile(tmp)
-            v, cores, sample, sec, kind, reads = run_reference_cpu(tmp, profile, max(1, min(a.steps, 3)), min(warmup, 1), a.genome_len)
-        emit({"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                          "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                          "config": {"workload": workload_name() if a.genome_len == GENOME_LEN else f"DEBUG {a.genome_len} bp", "sample": sample},
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            sample_chrom = REF_SAMPLE_CHROM if a.scale >= 1.0 else max(200_000, int(REF_SAMPLE_CHROM * a.scale))
+            r = run_reference_cpu(tmp, profile, max(1, a.steps), warmup, a.coverage, sample_chrom)
+        emit({"metric": METRIC, "value": r["value"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": r["steps_run"], "warmup": r["warmup_run"],
+              "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+              "config": config,
+              "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                               "stage_s": r["stage_s"], "reads_stage_value": r["reads_stage_value"], "reads_per_step": r["reads_per_step"],
+                               "extrapolated_full_cell_s": r["extrapolated_full_cell_s"]},
+              "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return 0
 
     import numpy as np
     import torch
     import torch.distributed as dist
     from scssim_b200 import api
-    from scssim_b200.synth import synth_sequence
 
-    torch.cuda.set_device(local)
+    device, devmap = device_for_rank(torch, local, world)
+    torch.cuda.set_device(device)
+    dev = f"cuda:{device}"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather_f64(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(t)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(v) for v in out]
+
     with tempfile.TemporaryDirectory() as tmp:
         profile = bench_profile(tmp)
-        glen = a.genome_len
-        # every rank: its own chromosome of the synthetic cell (weak scaling), ASCII in pinned host memory
-        seq = synth_sequence(glen, 7000 + rank)
-        pinned = torch.empty(glen, dtype=torch.uint8, pin_memory=True)
-        pinned.numpy()[:] = seq
-        named = [(f"chrS{rank + 1}_1_{glen}", pinned.numpy())]
-        # pinned D2H copy ceiling of this box, measured live with ALL ranks copying at once (the binding roof of the read
-        # stage; on shared PCIe fabrics the per-GPU rate drops as N grows)
+        clen = int(CHROM_LEN * a.scale)
+        # the cell: 8 sequences in file order chrS1_1, chrS1_2, chrS2_1, ...; this rank keeps a contiguous run of them
+        names = [f"chrS{c + 1}_{h}_{clen}" for c in range(N_CHROM) for h in (1, 2)]
+        lo, hi = api.shard_sequences([clen] * len(names), rank, world)
+        mine = list(range(lo, hi))
+        host = {}
+        for c in sorted({i // 2 for i in mine}):
+            b1 = torch.empty(clen, dtype=torch.uint8, pin_memory=True).numpy(); b2 = torch.empty(clen, dtype=torch.uint8, pin_memory=True).numpy()
+            synth_chromosome_cuda(torch, clen, 7000 + c, dev, b1, b2)
+            host[2 * c], host[2 * c + 1] = b1, b2
+        named = [(names[i], host[i]) for i in mine]
+        h2d_bytes = sum(len(s) for _, s in named)
+        for i in list(host):
+            if i not in mine:
+                del host[i]
+
+        # ---- pinned D2H ceilings of this box, measured live: one GPU alone (rank 0), then ALL ranks copying at once. The second is the
+        # ---- binding roof of the read stage; on shared host fabrics the per-GPU rate drops as N grows
         nb = 256 << 20
-        dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda"); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
-        hbuf.copy_(dbuf, non_blocking=True)
-        barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(6):
-            hbuf.copy_(dbuf, non_blocking=True)
-        c1.record(); torch.cuda.synchronize()
-        mine = torch.tensor([6 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9], dtype=torch.float64, device="cuda")
-        per_rank = [torch.zeros_like(mine) for _ in range(world)]
-        if world > 1:
-            dist.all_gather(per_rank, mine)
-        else:
-            per_rank = [mine]
-        d2h_per_rank = [float(x) for x in per_rank]
-        d2h_peak = sum(d2h_per_rank)            # aggregate over the N GPUs
-        d2h_slowest = min(d2h_per_rank)
+        dbuf = torch.empty(nb, dtype=torch.uint8, device=dev); hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+
+        def d2h_rate(active):
+            hbuf.copy_(dbuf, non_blocking=True); barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            if active:
+                for _ in range(6):
+                    hbuf.copy_(dbuf, non_blocking=True)
+            c1.record(); torch.cuda.synchronize()
+            r = 6 * nb / (c0.elapsed_time(c1) / 1e3) / 1e9 if active else 0.0
+            barrier()
+            return r
+        d2h_single = gather_f64(d2h_rate(rank == 0))[0]
+        d2h_per_rank = gather_f64(d2h_rate(True))
+        d2h_peak = sum(d2h_per_rank)
         del dbuf, hbuf
-        # one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream. With several GPUs the
-        # read slots are cut in proportion to each GPU's measured D2H rate (balance=1), so a GPU behind a slower host link
-        # writes fewer reads; the rank-ordered shards are byte-identical to the single-GPU files
-        g = api.GenReads(gamma=GAMMA, coverage=a.coverage, isize=260, layout="PE", seed=0x5C55, device=local, rank=rank, world=world,
+
+        # ---- one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream. With several GPUs the read
+        # ---- slots are cut in proportion to a per-GPU weight (balance = 1): first its measured D2H rate, then refined after every
+        # ---- warm-up step from the measured read-stage times, so that all GPUs finish together
+        g = api.GenReads(gamma=GAMMA, coverage=a.coverage, isize=ISIZE, layout="PE", seed=0x5C55, device=device, rank=rank, world=world,
                          slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance))
-        if world > 1:
-            g.set_shard_weight(d2h_per_rank[rank])
+        weight = d2h_per_rank[rank]
         if world > 1:
             from scssim_b200.dist import make_collectives, make_device_allreduce
-            g.set_collectives(*make_collectives(dist, device=f"cuda:{local}"))
-            g.set_device_collective(*make_device_allreduce(dist, f"cuda:{local}"))
+            g.set_shard_weight(weight)
+            g.set_collectives(*make_collectives(dist, device=dev))
+            g.set_device_collective(*make_device_allreduce(dist, dev))
         g.load_profile(profile)
         g.set_genome(named).create_frags()
 
@@ -241,10 +394,19 @@ def main():
             g.set_genome(named).create_frags().amplify().set_read_counts()
             g._ck(api.lib().scs_yield_reads_sink(g._h, sink_cb, None))
 
+        weights_hist = []
         for _ in range(warmup):
             step_resident()
+            if world > 1 and not a.no_balance:
+                st = g.stats()
+                t_all = gather_f64(st["ms_reads"]); r_all = gather_f64(st["records"])
+                rate = [r / t if t > 0 else 0.0 for r, t in zip(r_all, t_all)]   # records per ms of this GPU's read stage
+                if min(rate) > 0:
+                    weight = rate[rank]
+                    g.set_shard_weight(weight)
+                    weights_hist.append([round(x / sum(rate), 4) for x in rate])
         l0 = g.stats()["kernel_launches"]
-        clocks = ClockSampler(local); clocks.start()
+        clocks = ClockSampler(device); clocks.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         emit_ms = emit_n = reads_ms = amp_ms = alloc_ms = 0.0
         barrier(); ev0.record(); t0 = time.perf_counter()
@@ -258,39 +420,92 @@ def main():
         clk = clocks.stop()
         st = g.stats()
         launches = st["kernel_launches"] - l0
-        reads_per_step = st["records"]   # FASTQ records actually written (both files)
+        reads_per_step = st["records"]   # FASTQ records actually written by this rank (both files)
         fastq_bytes = st["fastq_bytes"][0] + st["fastq_bytes"][1]
-        n_fulls, n_semis = st["n_fulls"], st["n_semis"]
+        n_fulls, n_semis = st["n_fulls_global"], st["n_semis_global"]
 
-        # e2e leg (host buffers in, host bytes out); two untimed passes first (pool growth, page faults of the host side)
-        step_e2e()
+        # ---- e2e leg (host buffers in, host bytes out); one untimed pass first (page faults of the host side)
         step_e2e()
         barrier(); t0 = time.perf_counter()
         e2e_steps = max(1, min(a.steps, 3))
         for _ in range(e2e_steps):
             step_e2e()
         barrier(); e2e_s = time.perf_counter() - t0
+        g.close()
 
-        tmax = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
-        tot = torch.tensor([float(reads_per_step), float(fastq_bytes)], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([dev_s, e2e_s, reads_ms], dtype=torch.float64, device=dev)
+        tot = torch.tensor([float(reads_per_step), float(fastq_bytes), float(launches)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dev_s, e2e_s = tmax.tolist(); reads_all, bytes_all = tot.tolist()
+        dev_s, e2e_s, reads_ms_max = tmax.tolist(); reads_all, bytes_all, launches_all = tot.tolist()
+        shares = gather_f64(reads_per_step)
         value = reads_all * a.steps / dev_s / 1e6
         e2e_value = reads_all * e2e_steps / e2e_s / 1e6
 
+        # ---- bounded extras on rank 0's GPU: BASELINE configs[1] and the file-writing drop-in call
+        extras = {}
+        if rank == 0 and not a.no_extras:
+            from scssim_b200.synth import synth_sequence
+            c1len = max(1_000_000, int(C1_LEN * a.scale))
+            seq = torch.empty(c1len, dtype=torch.uint8, pin_memory=True).numpy(); dummy = torch.empty(c1len, dtype=torch.uint8, pin_memory=True).numpy()
+            synth_chromosome_cuda(torch, c1len, 7100, dev, seq, dummy)
+            del dummy
+            g1 = api.GenReads(gamma=GAMMA, coverage=C1_COVERAGE, isize=ISIZE, layout="PE", seed=0x5C55, device=device, slab_bytes=a.slab_mb << 20, io_threads=8)
+            g1.load_profile(profile).set_genome([(f"chrS1_1_{c1len}", seq)]).create_frags()
+            for _ in range(2):
+                g1.amplify().set_read_counts().yield_reads_discard()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3):
+                g1.amplify().set_read_counts().yield_reads_discard()
+            c1_s = (time.perf_counter() - t0) / 3
+            s1 = g1.stats()
+            extras["configs1"] = {"workload": "BASELINE configs[1]: synthetic 250 Mb haploid, PE150 10x (-c 20), same profile/gamma" + ("" if a.scale == 1.0 else f" DEBUG scale {a.scale}"),
+                                  "value": s1["records"] / c1_s / 1e6, "unit": UNIT, "ms_per_step": c1_s * 1e3,
+                                  "fastq_GBps": (s1["fastq_bytes"][0] + s1["fastq_bytes"][1]) / c1_s / 1e9, "steps": 3, "warmup": 2}
+            # files: <prefix>_1.fq / <prefix>_2.fq through scs_yield_reads (asynchronous sink, O_DIRECT where the file system has it)
+            fdir = a.files_dir or tmp
+            files = {}
+            for label, d in (("tmp", fdir), ("shm", "/dev/shm")):
+                if not os.path.isdir(d) or (label == "shm" and a.files_dir):
+                    continue
+                need = (s1["fastq_bytes"][0] + s1["fastq_bytes"][1]) * 1.05
+                try:
+                    sv = os.statvfs(d)
+                    if sv.f_bavail * sv.f_frsize < need:
+                        files[label] = {"skipped": f"needs {need / 1e9:.1f} GB free in {d}"}
+                        continue
+                except OSError:
+                    continue
+                prefix = os.path.join(d, f"scs_bench_{os.getpid()}")
+                try:
+                    g1.set_genome([(f"chrS1_1_{c1len}", seq)]).create_frags().amplify().set_read_counts().yield_reads(prefix)   # untimed pass
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    g1.set_genome([(f"chrS1_1_{c1len}", seq)]).create_frags().amplify().set_read_counts().yield_reads(prefix)
+                    fs = time.perf_counter() - t0
+                    sz = sum(os.path.getsize(prefix + sfx) for sfx in ("_1.fq", "_2.fq"))
+                    files[label] = {"value": g1.stats()["records"] / fs / 1e6, "unit": UNIT, "file_GBps": sz / fs / 1e9, "file_bytes": sz, "dir": d, "s": fs}
+                finally:
+                    for sfx in ("_1.fq", "_2.fq"):
+                        if os.path.exists(prefix + sfx):
+                            os.remove(prefix + sfx)
+            extras["e2e_files"] = {"workload": extras["configs1"]["workload"], "through": "scs_yield_reads(prefix): host ASCII genome in, <prefix>_1.fq/_2.fq out",
+                                   **files}
+            g1.close()
+
         cpu = None
         if rank == 0 and not a.no_cpu_baseline:
-            v, cores, sample, sec, kind, _ = run_reference_cpu(tmp, profile, 1, 0, glen)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "s_per_sample": sec}
-        g.close()
+            r = run_reference_cpu(tmp, profile, 2, 0, a.coverage, REF_SAMPLE_CHROM if a.scale >= 1.0 else max(200_000, int(REF_SAMPLE_CHROM * a.scale)))
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "s_per_sample": r["s_per_step"],
+                   "stage_s": r["stage_s"], "reads_stage_value": r["reads_stage_value"], "reads_per_sample": r["reads_per_step"],
+                   "extrapolated_full_cell_s": r["extrapolated_full_cell_s"]}
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         # algorithmic HBM bytes of one emit launch (DESIGN.md "emit_kernel"): FASTQ bytes stored (into the staging buffer) + 2-bit
-        # genome windows read (ceil(L/4) B per read) + 16 B descriptor per amplicon touched + 8 B of record sizes per slot
+        # genome windows read (ceil(L/4) B per read) + 16 B descriptor per amplicon touched + 8 B of record sizes per slot;
+        # rank 0's launches (all ranks run the same kernel on their slot range)
         slots = reads_per_step / 2
-        alg_step = fastq_bytes + reads_per_step * ((READ_LEN + 3) // 4) + 16 * n_fulls + 8 * slots
+        alg_step = fastq_bytes + reads_per_step * ((READ_LEN + 3) // 4) + 16 * n_fulls * (reads_per_step / max(reads_all, 1)) + 8 * slots
         traffic = None
         try:   # dram__bytes_read+write of one emit launch from the committed ncu --set full capture of this same command
             with open(os.path.join(ROOT, "profiles", "emit_traffic.json")) as f:
@@ -300,28 +515,35 @@ def main():
         emit_launches_per_step = emit_n / a.steps if a.steps else 0
         emit_ms_avg = emit_ms / emit_n if emit_n else None
         achieved = (alg_step / emit_launches_per_step) / (emit_ms_avg / 1e3) / 1e9 if emit_ms_avg else None
+        gbps = bytes_all * a.steps / dev_s / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_name() if (glen == GENOME_LEN and a.coverage == COVERAGE) else f"DEBUG {glen} bp per rank, -c {a.coverage}", "per_gpu": "one 250 Mb chromosome per rank; ranks form one cell (global read allocation over NCCL)", "layout": "PE", "read_length": READ_LEN,
-                       "reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": bytes_all * a.steps / dev_s / 1e9,
-                       "full_amplicons": n_fulls, "semi_amplicons": n_semis,
-                       "l2": "every step streams ~5 GB of FASTQ through L2 (>> 126 MB), evicting the 62 MB packed genome between steps",
-                       "stage_ms_per_step": {"amplify": amp_ms / a.steps, "alloc": alloc_ms / a.steps, "reads": reads_ms / a.steps}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": glen * world, "d2h_bytes_per_step": bytes_all, "steps": e2e_steps,
-                    "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9},
-            "gpu_launches": int(launches),
+            "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config,
+            "detail": {"reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": gbps, "full_amplicons": n_fulls, "semi_amplicons": n_semis,
+                       "stage_ms_per_step_rank0": {"amplify": amp_ms / a.steps, "alloc": alloc_ms / a.steps, "reads": reads_ms / a.steps},
+                       "reads_stage_ms_max_rank": reads_ms_max / a.steps,
+                       "parallelism": (f"one cell over {world} GPUs: sequences sharded for the amplification, packed genome + amplicon table replicated "
+                                       f"over NCCL, read slots cut into {world} contiguous ranges") if world > 1 else "one GPU",
+                       "device_map": devmap, "share_of_reads_per_rank": [round(s / max(reads_all, 1), 4) for s in shares],
+                       "shard_weight_history": weights_hist[-3:]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": config["genome_bases"], "d2h_bytes_per_step": bytes_all, "steps": e2e_steps,
+                    "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9, "this_rank_h2d_bytes": h2d_bytes},
+            "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": (alg_step / emit_launches_per_step) if emit_launches_per_step else None, "peak_source": peak_src, "launches_per_step": emit_launches_per_step, "avg_launch_ms": emit_ms_avg,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": (alg_step / emit_launches_per_step) if emit_launches_per_step else None, "peak_source": peak_src,
+                         "launches_per_step": emit_launches_per_step, "avg_launch_ms": emit_ms_avg,
                          "kernel_share_of_step": (emit_ms / a.steps) / (dev_s / a.steps * 1e3) if dev_s else None,
-                         "d2h": {"bound": "pcie", "achieved": bytes_all * a.steps / dev_s / 1e9, "peak": d2h_peak, "unit": "GB/s (all GPUs)",
-                                 "frac": (bytes_all * a.steps / dev_s / 1e9 / d2h_peak) if d2h_peak else None,
-                                 "frac_read_stage_rank0": (bytes_all / world / (reads_ms / a.steps / 1e3) / 1e9 / d2h_per_rank[0]) if reads_ms else None,
-                                 "per_gpu_peak": [round(x, 1) for x in d2h_per_rank],
-                                 "equal_shard_ceiling": world * d2h_slowest, "balanced": bool(world > 1 and not a.no_balance),
-                                 "note": "FASTQ bytes landing in pinned host memory over the whole step, against the pinned D2H copy rate measured in this run with all ranks copying at once; this, not HBM, is the binding roof of the path. With equal shards the slowest GPU's link would set the pace (N x slowest); for N > 1 the read slots are cut in proportion to the measured per-GPU rates"}},
+                         "d2h": {"bound": "pcie", "achieved": gbps, "unit": "GB/s (all GPUs)",
+                                 "peak": d2h_peak, "frac": (gbps / d2h_peak) if d2h_peak else None,
+                                 "peak_n_x_single_link": world * d2h_single, "frac_of_n_x_single_link": gbps / (world * d2h_single) if d2h_single else None,
+                                 "single_gpu_link": d2h_single, "per_gpu_concurrent": [round(x, 1) for x in d2h_per_rank],
+                                 "note": "FASTQ bytes landing in pinned host memory over the whole step. `peak` = pinned D2H copy rate measured in this run with all "
+                                         "ranks copying at once (what this box's host side can absorb); `peak_n_x_single_link` = N x the rate of one GPU copying "
+                                         "alone. This, not HBM, is the binding roof of the path"}},
             "cpu_baseline": cpu, "clocks": clk,
         }
+        out.update(extras)
         emit(out)
     if world > 1:
         dist.destroy_process_group()

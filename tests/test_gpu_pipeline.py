@@ -148,7 +148,7 @@ def test_resampled_bench_profiles_equal_the_oracle(tmp_path, src, rl, layout, is
     from scssim_b200.tools.resample_profile import resample
     prof = os.path.join(str(tmp_path), f"{src}_{rl}.profile")
     resample(H.profile_path(src), prof, rl)
-    st = _run_case(str(tmp_path), f"res{rl}{layout}", 1, 400_000, 13, prof, layout, 2e-10, 6.0, isize, seed=150 + rl, slab_bytes=4 << 20, min_slabs=2)
+    st = _run_case(str(tmp_path), f"res{rl}{layout}", 1, 400_000, 13, prof, layout, 2e-10, 6.0, isize, seed=150 + rl, slab_bytes=256 << 10, min_slabs=3)
     assert st["records"] > 0
 
 

@@ -201,8 +201,8 @@ def test_bench_reference_arm_contract():
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--genome-len", "2000000"], capture_output=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--scale", "0.05", "--coverage", "10"], capture_output=True, timeout=600)
     assert r.returncode == 0, r.stderr.decode()[-2000:]
     lines = [l for l in r.stdout.decode().splitlines() if l.strip()]
     assert len(lines) == 1
@@ -211,5 +211,10 @@ def test_bench_reference_arm_contract():
               "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "M reads/s" and d["dtype"] == "u8"
+    # the line states the steps it really ran (one whole reference process each), and its timed region fits its own run
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["scaling"] == "strong"
+    assert d["config"]["workload"].startswith("DEBUG") and "EXTRAPOLATED" in d["cpu_baseline"]["sample"]
+    if d["cpu_baseline"]["kind"] == "reference":
+        assert set(d["cpu_baseline"]["stage_s"]) == {"load_frags", "amplify", "alloc", "reads"} and d["cpu_baseline"]["reads_stage_value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
