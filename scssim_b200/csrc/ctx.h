@@ -148,7 +148,7 @@ struct AmpScratch {
 
 // persistent scratch of the read stage (no allocation inside the slab loop)
 struct ReadScratch {
-    DevBuf<uint32_t> size1, size2, nfail, hdrno;
+    DevBuf<uint32_t> size1, size2, nfail, hdrno, coarse;
     DevBuf<uint64_t> off1, off2, scan, totals;
     DevBuf<int> flags; DevBuf<unsigned long long> records;
     DevBuf<char> stage[2];         // fixed-stride records of one slab per file (staged emit), packed by compact_records_kernel

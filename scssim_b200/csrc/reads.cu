@@ -28,7 +28,7 @@ __device__ __noinline__ void philox4x32_10_call(uint32_t c0, uint32_t c1, uint32
     philox4x32_10(c0, c1, c2, c3, k0, k1, out);
 }
 
-constexpr int kReadWarps = 8;         // warps per CTA (plan / test kernels)
+constexpr int kReadWarps = 8;         // warps per CTA (test kernels)
 constexpr int kEmitWarps = 24;        // warps per persistent CTA of the emit kernel (one CTA per SM)
 constexpr int kDiagW = 40;            // entries per compact quality row kept in shared memory (shipped profiles need <= 39)
 constexpr int kDiagStride = 44;       // words per row: 40 + 4 pad; 44*r mod 32 is a distinct multiple of 4 for 8 neighbouring rows,
@@ -37,6 +37,10 @@ constexpr int kRLCap = 256;           // max profile read length handled by the 
 constexpr int kSrcCap = 384;          // max read length after insertions (overflow -> error flag)
 constexpr int kMaxEvents = 32;        // indel events per read kept in shared memory
 constexpr int kRecCap = 16 + 40 + 2 * kSrcCap + 8;
+constexpr int kWinBytes = 96;         // staged 2-bit window of one mate: kRLCap bases (64 B) + 16-byte alignment skirts on both sides
+constexpr int kWinNBytes = 64;        // staged N-mask window of one mate: kRLCap bits (32 B) + skirts
+constexpr int kCoarseShift = 10;      // coarse slot -> amplicon index: one entry per 1024 slots
+constexpr int kISizeSmemCap = 4096;   // insert-size thresholds kept in shared memory (longer tables stay in global memory)
 
 struct ReadTables {
     const uint32_t* subs1; const uint32_t* subs2;   // [84][bins][4]  (3 thresholds + eff)
@@ -51,30 +55,77 @@ struct ReadTables {
 
 struct QualSmem { const uint32_t* rows; const uint4* piv; const uint32_t* meta; };
 
+// What the emit kernel knows about a slot one slot ahead of processing it (stage A -> stage B, through shared memory)
+struct SlotPlan {
+    uint64_t entity;          // Philox entity / replay mark index
+    const uint32_t* errs;     // substitution overlay of the slot's amplicon
+    uint32_t ampIdx, fragNo, nerr, cr, ci;
+    int32_t pos, isz;
+    uint32_t woff[2];         // window of mate m starts woff[m] bases into win[m]; bit 31: read it backwards and complemented
+    uint32_t noff[2];         // same for the N mask (bases into winn[m])
+    int32_t valid;
+};
+
 struct WarpScratch {
     uint8_t ref[kRLCap];
     uint8_t src[kSrcCap];
     char rec[kRecCap];
     int16_t ev_pos[kMaxEvents]; int16_t ev_len[kMaxEvents]; uint32_t ev_ci[kMaxEvents];
 };
+// per-warp staging of the emit kernel: packed genome windows of the next slots land here through cp.async.bulk (TMA)
+struct __align__(16) WarpStage {
+    uint8_t win[2][2][kWinBytes];     // [buffer][mate]
+    uint8_t winn[2][2][kWinNBytes];   // N mask, only filled when the genome holds N
+    SlotPlan plan[2];
+    uint64_t bar[2];                  // mbarrier per buffer: completes when the buffer's bulk copies have landed
+};
 
-// draws base+4*lane .. base+4*lane+3 of one engine, one Philox block per lane (+ a neighbour shuffle)
-__device__ __forceinline__ void warp_draws4(const Stream& S, int eng, uint32_t base, int lane, uint32_t x[4]) {
+// ---- mbarrier + bulk-copy (TMA) primitives, sm_90+ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Draws base+4*lane .. base+4*lane+3 of one engine: one Philox block per lane. When `base` is not a multiple of 4 a lane also
+// needs the first words of its right neighbour's block; instead of running a 33rd block for lane 31 alone (a whole Philox for one
+// lane), only lanes 0..30 own positions in that case. Returns the number of draws the step covers (128 or 124).
+__device__ __forceinline__ int warp_draws4(const Stream& S, int eng, uint32_t base, int lane, uint32_t x[4]) {
     if (S.replay()) {
         const uint32_t* p = S.t[eng] + base + 4u * lane;
         x[0] = p[0]; x[1] = p[1]; x[2] = p[2]; x[3] = p[3];
-        return;
+        return 128;
     }
     uint32_t o[4], nx[4];
     const uint32_t B = (base >> 2) + lane, sh = base & 3u;
     S.block(eng, B, o);
-    if (sh == 0) { x[0] = o[0]; x[1] = o[1]; x[2] = o[2]; x[3] = o[3]; return; }
+    if (sh == 0) { x[0] = o[0]; x[1] = o[1]; x[2] = o[2]; x[3] = o[3]; return 128; }
 #pragma unroll
-    for (int q = 0; q < 4; q++) nx[q] = __shfl_down_sync(0xffffffffu, o[q], 1);
-    if (lane == 31) S.block(eng, B + 1, nx);
+    for (int q = 0; q < 3; q++) nx[q] = __shfl_down_sync(0xffffffffu, o[q], 1);
     if (sh == 1) { x[0] = o[1]; x[1] = o[2]; x[2] = o[3]; x[3] = nx[0]; }
     else if (sh == 2) { x[0] = o[2]; x[1] = o[3]; x[2] = nx[0]; x[3] = nx[1]; }
     else { x[0] = o[3]; x[1] = nx[0]; x[2] = nx[1]; x[3] = nx[2]; }
+    return 124;
 }
 
 // Indel pass of Profile::predict (Profile.cpp:1603-1630) over n source positions. Advances the real /
@@ -86,13 +137,15 @@ __device__ __forceinline__ int indel_pass(const Stream& S, const ReadTables& T, 
     int j = 0, delta = 0, nev = 0;
     while (j < n) {
         uint32_t x[4];
-        warp_draws4(S, E_REAL, cr, lane, x);
+        const int P = warp_draws4(S, E_REAL, cr, lane, x) >> 1;   // positions covered by this step (2 draws each)
         const int pA = j + 2 * lane;
         int ev = 0;
-        if (pA < n) { if ((uint64_t)x[0] < T.thrIns) ev = 1; else if ((uint64_t)x[1] < T.thrDel) ev = 2; }
-        if (!ev && pA + 1 < n) { if ((uint64_t)x[2] < T.thrIns) ev = 3; else if ((uint64_t)x[3] < T.thrDel) ev = 4; }
+        if (2 * lane < P) {
+            if (pA < n) { if ((uint64_t)x[0] < T.thrIns) ev = 1; else if ((uint64_t)x[1] < T.thrDel) ev = 2; }
+            if (!ev && pA + 1 < n) { if ((uint64_t)x[2] < T.thrIns) ev = 3; else if ((uint64_t)x[3] < T.thrDel) ev = 4; }
+        }
         const uint32_t any = __ballot_sync(0xffffffffu, ev != 0);
-        if (!any) { int used = min(64, n - j); j += used; cr += 2u * used; continue; }
+        if (!any) { int used = min(P, n - j); j += used; cr += 2u * used; continue; }
         const int l0 = __ffs(any) - 1;
         const int e = __shfl_sync(0xffffffffu, ev, l0);
         const int p = j + 2 * l0 + (e >= 3);
@@ -171,28 +224,40 @@ __device__ __forceinline__ int sample_quality(const ReadTables& T, const QualSme
     return count_le(T.qual + row * kQualN, (int)T.qualEff[row], xq);
 }
 
-// substitution + quality loop (Profile.cpp:1656-1694): two output positions per lane per step
+// substitution + quality loop (Profile.cpp:1656-1694): two output positions per lane per step. The threshold rows of both
+// positions are requested before the Philox block is computed, so the L2 latency of the loads hides under the ~100 ALU instructions.
 __device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTables& T, const QualSmem* Q, const uint8_t* __restrict__ src, int np,
                                                    int isRead1, uint32_t& cr, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
-    const uint32_t* __restrict__ subs = (!isRead1 && T.subs2) ? T.subs2 : T.subs1;
+    const uint4* __restrict__ subs = reinterpret_cast<const uint4*>((!isRead1 && T.subs2) ? T.subs2 : T.subs1);
     const int bins = T.RL;
-    for (int m0 = 0; m0 < np; m0 += 64) {
+    const int P = S.replay() ? 64 : (((cr & 3u) == 0) ? 64 : 62);   // the alignment of cr + 2*m0 does not change inside the pass
+    for (int m0 = 0; m0 < np; m0 += P) {
+        uint4 th[2]; uint32_t b0[2]; int bin[2]; bool ok[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int m = m0 + 2 * lane + h;
+            ok[h] = (2 * lane < P) && m < np;
+            b0[h] = 0; bin[h] = 0; th[h] = make_uint4(0, 0, 0, 0);
+            if (ok[h]) {
+                b0[h] = src[m];
+                uint32_t ki;
+                if (m == 0) ki = b0[h];
+                else if (m == 1) ki = 4u + 4u * src[0] + b0[h];
+                else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0[h];
+                bin[h] = (np == bins) ? m : m * bins / np;
+                th[h] = __ldg(subs + ((size_t)ki * bins + bin[h]));
+            }
+        }
         uint32_t x[4];
         warp_draws4(S, E_REAL, cr + 2u * m0, lane, x);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int m = m0 + 2 * lane + h;
-            if (m < np) {
-                const uint32_t b0 = src[m];
-                uint32_t ki;
-                if (m == 0) ki = b0;
-                else if (m == 1) ki = 4u + 4u * src[0] + b0;
-                else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0;
-                const int bin = (np == bins) ? m : m * bins / np;
-                const uint4 th = __ldg(reinterpret_cast<const uint4*>(subs) + ((size_t)ki * bins + bin));
+            if (ok[h]) {
+                const int m = m0 + 2 * lane + h;
                 const uint32_t xs = x[2 * h], xq = x[2 * h + 1];
-                const uint32_t k = (uint32_t)(th.w > 0 && th.x <= xs) + (uint32_t)(th.w > 1 && th.y <= xs) + (uint32_t)(th.w > 2 && th.z <= xs);
-                const int q = sample_quality(T, Q, b0, k, bin, xq);
+                // thresholds are non-decreasing and padded with 0xFFFFFFFF: the leading count, capped by the row's entry count
+                const uint32_t k = min((uint32_t)(th[h].x <= xs) + (uint32_t)(th[h].y <= xs) + (uint32_t)(th[h].z <= xs), th[h].w);
+                const int q = sample_quality(T, Q, b0[h], k, bin[h], xq);
                 oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);   // "ACGT"[k]
                 oqual[m] = (char)(33 + q);
             }
@@ -252,28 +317,28 @@ __device__ __forceinline__ void subst_quality_pass_n(const Stream& S, const Read
 __device__ __forceinline__ int dec_digits(uint32_t v) {
     return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }
+__constant__ uint32_t kPow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 // "@%d#%d" (+"/1" | "/2") + "\n": the %d of a negative amplicon index never occurs (index < 2^31)
-__device__ __forceinline__ int header_len(uint32_t amp, uint32_t frag, int paired) { return 1 + dec_digits(amp) + 1 + dec_digits(frag) + (paired ? 2 : 0) + 1; }
-__device__ __forceinline__ int write_header(char* p, uint32_t amp, uint32_t frag, int mate) {
-    int n = 0; p[n++] = '@';
-    int d = dec_digits(amp); for (int i = d - 1; i >= 0; i--) { p[n + i] = (char)('0' + amp % 10u); amp /= 10u; } n += d;
-    p[n++] = '#';
-    d = dec_digits(frag); for (int i = d - 1; i >= 0; i--) { p[n + i] = (char)('0' + frag % 10u); frag /= 10u; } n += d;
-    if (mate) { p[n++] = '/'; p[n++] = (char)('0' + mate); }
-    p[n++] = '\n';
-    return n;
+__device__ __forceinline__ int header_len(int da, int df, int paired) { return 1 + da + 1 + df + (paired ? 2 : 0) + 1; }
+// the whole record frame in one go, one character per lane: header digits (lane l = l-th character after '@'), "/m", and the
+// three separators "\n+\n" ... "\n" around the sequence and quality lines of np characters each
+__device__ __forceinline__ void write_frame(char* rec, uint32_t amp, uint32_t frag, int da, int df, int mate, int hl, int np, int lane) {
+    if (lane < da) rec[1 + lane] = (char)('0' + (amp / kPow10[da - 1 - lane]) % 10u);
+    else if (lane == da) rec[1 + da] = '#';
+    else if (lane < da + 1 + df) { const int t = lane - da - 1; rec[2 + da + t] = (char)('0' + (frag / kPow10[df - 1 - t]) % 10u); }
+    else if (lane == 24) rec[0] = '@';
+    else if (lane == 25) { if (mate) { rec[hl - 3] = '/'; rec[hl - 2] = (char)('0' + mate); } rec[hl - 1] = '\n'; }
+    else if (lane == 26) { rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; }
+    else if (lane == 27) rec[hl + 2 * np + 3] = '\n';
 }
 
-// copy n bytes smem -> global where (smem address & 15) == (global address & 15)
+// copy ceil(n/16) 16-byte vectors smem -> global, both 16-byte aligned (the staging stride is a multiple of 16, so the
+// few bytes copied past the record stay inside its own staging cell)
 __device__ __forceinline__ void copy_out(char* __restrict__ dst, const char* __restrict__ srcp, int n, int lane) {
-    const int head = min(n, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
-    if (lane < head) dst[lane] = srcp[lane];
-    const int nvec = (n - head) >> 4;
-    const uint4* s4 = reinterpret_cast<const uint4*>(srcp + head);
-    uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+    const int nvec = (n + 15) >> 4;
+    const uint4* s4 = reinterpret_cast<const uint4*>(srcp);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
     for (int i = lane; i < nvec; i += 32) d4[i] = s4[i];
-    const int done = head + (nvec << 4);
-    if (done + lane < n) dst[done + lane] = srcp[done + lane];
 }
 
 struct SlabArgs {
@@ -286,8 +351,10 @@ struct SlabArgs {
     const uint32_t* hdr_no;            // slow path: fragCount per slot (0 = dropped); nullptr -> slot index + 1
     const uint32_t* nfail;             // slow path: failed insert-size attempts before the slot's success
     uint64_t fail_base;                // hdr_no / nfail are indexed by (slot - fail_base)
-    uint64_t slab_cap;                 // bytes available in each output slab (emit bounds check)
-    uint64_t stage_stride;             // staged emit: record of slot ls goes to stage + ls * stage_stride (a multiple of 16)
+    uint64_t slab_cap;                 // bytes available in each output slab
+    uint64_t stage_stride;             // record of slot ls goes to stage + ls * stage_stride (a multiple of 16)
+    const uint32_t* coarse;            // amplicon of slot coarse_base + j * 2^kCoarseShift (one entry more than needed)
+    uint64_t coarse_base;
 };
 
 // count_le on a long row, evaluated by the whole warp: 32 pivots, then the segment between two pivots (2 ballots)
@@ -296,19 +363,19 @@ __device__ __forceinline__ int warp_count_le(const uint32_t* __restrict__ row, i
     if (n > 1024) return count_le(row, n, x);
     const int step = (n + 31) >> 5;
     const int pi = min((lane + 1) * step, n) - 1;                       // last entry of lane's segment
-    const uint32_t below = __ballot_sync(0xffffffffu, __ldg(row + pi) <= x);   // a prefix of lanes (row is non-decreasing)
+    const uint32_t below = __ballot_sync(0xffffffffu, row[pi] <= x);    // a prefix of lanes (row is non-decreasing)
     const int seg = __popc(below);                                      // segments fully <= x
     if (seg >= 32) return n;
     const int base = seg * step;
     if (base >= n) return n;
     const int idx = base + lane;
-    const bool le = lane < step && idx < n && __ldg(row + idx) <= x;
+    const bool le = lane < step && idx < n && row[idx] <= x;
     return base + __popc(__ballot_sync(0xffffffffu, le));
 }
 
-// amplicon of a slot: last a with slot_base[a] <= slot, by a warp-cooperative 32-ary search (4 probes for 1e6 amplicons)
-__device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ slot_base, uint64_t n_amp, uint64_t slot, int lane) {
-    uint64_t lo = 0, hi = n_amp;   // invariant: slot_base[lo] <= slot < slot_base[hi]
+// amplicon of a slot: last a in [lo, hi) with slot_base[a] <= slot, by a warp-cooperative 32-ary search.
+// Precondition: slot_base[lo] <= slot < slot_base[hi] (the coarse index narrows [lo, hi) to a few dozen amplicons: one probe).
+__device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ slot_base, uint64_t lo, uint64_t hi, uint64_t slot, int lane) {
     while (hi - lo > 1) {
         const uint64_t width = hi - lo, step = (width + 31) >> 5;
         const uint64_t idx = lo + (uint64_t)lane * step;
@@ -321,92 +388,192 @@ __device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ s
     return lo;
 }
 
-// One slot (SE read / PE pair): every record goes to its slot's fixed-stride place in the staging buffer and its size is recorded;
-// compact_records_kernel packs them afterwards.
-__device__ __forceinline__ void do_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
-                                        WarpScratch* ws, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2, char* __restrict__ out1,
-                                        char* __restrict__ out2, int* flags, unsigned long long* records) {
+// ---- stage A: everything a slot needs before its bases arrive — amplicon lookup, header numbers, insert size and position
+// ---- draws — then ONE lane asks the TMA unit for the packed windows of both mates (cp.async.bulk -> this warp's shared memory).
+// ---- Runs one slot ahead of stage B, so the dependent-load chain (coarse index -> slot prefix -> descriptor -> genome) of the
+// ---- next slot overlaps the synthesis of the current one.
+__device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const uint32_t* __restrict__ isize_row, const SlabArgs& A,
+                                          uint64_t ls, int lane, WarpStage* st, int buf) {
     const uint64_t slot = A.slot0 + ls;
-    const uint64_t a = find_amplicon(A.slot_base, A.n_amp, slot, lane);
+    const uint64_t cj = (slot - A.coarse_base) >> kCoarseShift;
+    const uint64_t a = find_amplicon(A.slot_base, __ldg(A.coarse + cj), min((uint64_t)__ldg(A.coarse + cj + 1) + 1, A.n_amp), slot, lane);
     const Tmpl F = unpack_desc(__ldg(A.desc + a));
-    const int RL = T.RL; const int ampLen = (int)F.len;
     const uint64_t sb = __ldg(A.slot_base + a);
-    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot - A.fail_base] : (uint32_t)(slot - sb) + 1u;
+    const uint64_t er = __ldg(A.errref + a);
     const uint32_t ampIdx = A.amp_gidx ? (uint32_t)__ldg(A.amp_gidx + a) : (uint32_t)a;
     const uint64_t entity = __ldg(A.slot_gbase + a) + (slot - sb);
-    if (fragNo == 0 || ampLen < RL) return;   // dropped slot / Amplicon.cpp:442 (sizes were zeroed before the launch)
-    Stream S; S.init(dsrc, D_READ, entity, entity);
-    uint32_t cr = 0, ci = 0;
-    int pos = 0, isz = RL;
-    if (T.paired) {
-        if (A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
-        isz = T.minInsert + warp_count_le(T.isize, T.isizeEff, S.at(E_REAL, cr), lane);
-        cr += 1;
-        pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
-    } else {
-        pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
+    const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot - A.fail_base] : (uint32_t)(slot - sb) + 1u;
+    const int RL = T.RL; const int ampLen = (int)F.len;
+    const bool valid = fragNo != 0 && ampLen >= RL;   // dropped slot / Amplicon.cpp:442
+    uint32_t cr = 0, ci = 0; int pos = 0, isz = RL;
+    uint32_t woff[2] = {0, 0}, noff[2] = {0, 0};
+    __syncwarp();   // every lane is done reading this buffer's previous windows and plan
+    if (valid) {
+        Stream S; S.init(dsrc, D_READ, entity, entity);
+        if (T.paired) {
+            if (A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
+            isz = T.minInsert + warp_count_le(isize_row, T.isizeEff, S.at(E_REAL, cr), lane);
+            cr += 1;
+            pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
+        } else {
+            pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
+        }
+        // genome interval [lo, lo + RL) of each mate and its reading direction. Window base i of the amplicon is
+        // rc ? comp(G[gstart - i]) : G[gstart + i]; mate 1 reads window bases pos .. pos+RL-1, mate 2 the reverse complement of
+        // pos+isz-RL .. pos+isz-1 (Amplicon.cpp:508-512)
+        uint64_t lo[2]; uint32_t rev[2];
+        if (!F.rc) { lo[0] = F.gstart + (uint64_t)pos; rev[0] = 0; lo[1] = F.gstart + (uint64_t)(pos + isz - RL); rev[1] = 1; }
+        else { lo[0] = F.gstart - (uint64_t)(pos + RL - 1); rev[0] = 1; lo[1] = F.gstart - (uint64_t)(pos + isz - 1); rev[1] = 0; }
+        const int nm = T.paired ? 2 : 1;
+        uint32_t tx = 0; uint64_t b0[2], n0[2]; uint32_t bn[2], nn[2];
+#pragma unroll
+        for (int m = 0; m < 2; m++) {
+            if (m < nm) {
+                const uint64_t first = lo[m] >> 2, last = (lo[m] + (uint64_t)RL - 1) >> 2;
+                b0[m] = first & ~15ull; bn[m] = (uint32_t)(((last - b0[m]) + 16) & ~15ull);
+                woff[m] = (uint32_t)(lo[m] - (b0[m] << 2)) | (rev[m] << 31);
+                tx += bn[m];
+                if (g.has_n) {
+                    const uint64_t nf = lo[m] >> 3, nl = (lo[m] + (uint64_t)RL - 1) >> 3;
+                    n0[m] = nf & ~15ull; nn[m] = (uint32_t)(((nl - n0[m]) + 16) & ~15ull);
+                    noff[m] = (uint32_t)(lo[m] - (n0[m] << 3));
+                    tx += nn[m];
+                }
+            }
+        }
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&st->bar[buf], tx);
+            const uint8_t* gw = reinterpret_cast<const uint8_t*>(g.words); const uint8_t* gn = reinterpret_cast<const uint8_t*>(g.nmask);
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                if (m < nm) {
+                    bulk_g2s(st->win[buf][m], gw + b0[m], bn[m], &st->bar[buf]);
+                    if (g.has_n) bulk_g2s(st->winn[buf][m], gn + n0[m], nn[m], &st->bar[buf]);
+                }
+            }
+        }
     }
-    const uint64_t er = __ldg(A.errref + a);
-    const uint32_t nerr = (uint32_t)(er & 0xFFFF); const uint32_t* __restrict__ errs = A.err_pool + (er >> 16);
+    if (lane == 0) {
+        SlotPlan& P = st->plan[buf];
+        P.entity = entity; P.errs = A.err_pool + (er >> 16); P.ampIdx = ampIdx; P.fragNo = fragNo; P.nerr = (uint32_t)(er & 0xFFFF);
+        P.cr = cr; P.ci = ci; P.pos = pos; P.isz = isz; P.woff[0] = woff[0]; P.woff[1] = woff[1]; P.noff[0] = noff[0]; P.noff[1] = noff[1];
+        P.valid = valid ? 1 : 0;
+    }
+    __syncwarp();
+}
+
+// ---- stage B: one slot (SE read / PE pair). Every record goes to its slot's fixed-stride cell of the staging buffer and its size
+// ---- is recorded; compact_records_kernel packs them afterwards.
+__device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
+                                              WarpScratch* ws, WarpStage* st, int buf, uint32_t& phases, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
+                                              char* __restrict__ out1, char* __restrict__ out2, int* flags) {
+    const SlotPlan& P = st->plan[buf];
+    if (!P.valid) return 0;   // sizes were zeroed before the launch
+    const int RL = T.RL;
+    const uint32_t ampIdx = P.ampIdx, fragNo = P.fragNo, nerr = P.nerr;
+    const uint32_t* __restrict__ errs = P.errs;
+    const int pos = P.pos, isz = P.isz;
+    uint32_t cr = P.cr, ci = P.ci;
+    Stream S; S.init(dsrc, D_READ, P.entity, P.entity);
+    const int da = dec_digits(ampIdx), df = dec_digits(fragNo);
+    const int hl = header_len(da, df, T.paired);
+    mbar_wait(&st->bar[buf], (phases >> buf) & 1u);   // the packed windows have landed
+    phases ^= 1u << buf;                              // a buffer's barrier advances one phase per valid slot that used it
+    uint32_t made = 0;
 #pragma unroll 1
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
-        // source window (read 2 = reverse complement of the insert's far end, Amplicon.cpp:508-512)
+        // ---- decode the staged window: 2-bit codes -> one byte per base, in read direction
+        const uint32_t wo = P.woff[mate - 1], off = wo & 0x7FFFFFFFu; const bool rev = (wo >> 31) != 0;
+        const uint8_t* __restrict__ win = st->win[buf][mate - 1];
         __syncwarp();
         bool myN = false;
         for (int i = lane; i < RL; i += 32) {
-            const uint32_t fi = (mate == 1) ? (uint32_t)(pos + i) : (uint32_t)(pos + isz - 1 - i);
-            uint32_t b = window_base(g, F.gstart, F.rc, fi);
-            for (uint32_t e = 0; e < nerr; e++) { const uint32_t v = errs[e]; if (err_pos(v) == fi) b = err_base(v); }
-            b = (mate == 1) ? b : comp_code(b);
-            myN |= (b == 4u);
+            const uint32_t q = off + (uint32_t)(rev ? (RL - 1 - i) : i);
+            uint32_t b = ((uint32_t)win[q >> 2] >> ((q & 3u) * 2u)) & 3u;
+            if (rev) b ^= 3u;
+            if (g.has_n) {
+                const uint32_t qn = P.noff[mate - 1] + (uint32_t)(rev ? (RL - 1 - i) : i);
+                if ((st->winn[buf][mate - 1][qn >> 3] >> (qn & 7u)) & 1u) { b = 4u; myN = true; }
+            }
             ws->ref[i] = (uint8_t)b;
         }
-        const bool hasN = g.has_n && __any_sync(0xffffffffu, myN);
+        __syncwarp();
+        // ---- substitution overlay of the amplicon, once per window: an error at window base fi lands at read position
+        // ---- fi - pos (mate 1) or pos + isz - 1 - fi, complemented (mate 2). It also overrides an N.
+        for (uint32_t e = lane; e < nerr; e += 32) {
+            const uint32_t v = errs[e];
+            const int fi = (int)err_pos(v);
+            const int i = (mate == 1) ? fi - pos : pos + isz - 1 - fi;
+            if (i >= 0 && i < RL) ws->ref[i] = (uint8_t)((mate == 1) ? err_base(v) : 3u - err_base(v));
+        }
+        const bool hasN = g.has_n && __any_sync(0xffffffffu, myN);   // conservative when an overlay replaced the only N: the N path is exact for any window
         __syncwarp();
         int nev = 0;
         const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
-        if (np > kSrcCap) { if (lane == 0) atomicOr(flags, 8); return; }
+        if (np > kSrcCap) { if (lane == 0) atomicOr(flags, 8); return made; }
         __syncwarp();
         const uint8_t* src = build_source(S, np, nev, lane, ws);
-        const int hl = header_len(ampIdx, fragNo, T.paired);
         const int total = hl + 2 * np + 4;
-        if ((uint64_t)total > A.stage_stride) { if (lane == 0) atomicOr(flags, 16); return; }
-        char* dst = ((mate == 1) ? out1 : out2) + ls * A.stage_stride;
-        char* rec = ws->rec + (reinterpret_cast<uintptr_t>(dst) & 15);
-        if (lane == 0) {
-            write_header(rec, ampIdx, fragNo, T.paired ? mate : 0);
-            rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; rec[hl + 2 * np + 3] = '\n';
-        }
+        if ((uint64_t)total > A.stage_stride) { if (lane == 0) atomicOr(flags, 16); return made; }
+        char* rec = ws->rec;
+        write_frame(rec, ampIdx, fragNo, da, df, T.paired ? mate : 0, hl, np, lane);
         if (hasN) subst_quality_pass_n<true>(S, T, Q, src, np, mate == 1, cr, ci, lane, rec + hl, rec + hl + np + 3);
         else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
         __syncwarp();
-        copy_out(dst, rec, total, lane);
+        copy_out(((mate == 1) ? out1 : out2) + ls * A.stage_stride, rec, total, lane);
         if (lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;
+        made++;
     }
-    if (lane == 0) atomicAdd(records, T.paired ? 2ull : 1ull);
+    return made;
 }
 
-// emit: persistent CTAs (one per SM); the diagonal quality tables are staged in shared memory once per CTA
+// emit: persistent CTAs (one per SM). The diagonal quality tables and the insert-size thresholds are staged in shared memory once
+// per CTA; every warp then walks its slots with a two-deep software pipeline: plan_slot (lookups, draws, TMA request for the
+// genome windows) for slot k+1, then emit_slot for slot k whose windows have landed meanwhile.
 __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, char* __restrict__ out1, char* __restrict__ out2,
                                                                   int* flags, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
-                                                                  unsigned long long* __restrict__ records) {
+                                                                  unsigned long long* __restrict__ records, int isize_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (int)(blockDim.x >> 5);   // <= kEmitWarps: long-read profiles leave room for fewer warp scratch areas
     const int nrows = 4 * T.RL;
     uint32_t* srows = reinterpret_cast<uint32_t*>(smem_raw);
     uint4* spiv = reinterpret_cast<uint4*>(srows + (size_t)nrows * kDiagStride);
     uint32_t* smeta = reinterpret_cast<uint32_t*>(spiv + nrows);
-    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(smeta + ((nrows + 3) & ~3));
+    uint32_t* sisize = smeta + ((nrows + 3) & ~3);
+    WarpStage* stages = reinterpret_cast<WarpStage*>(sisize + ((isize_smem + 3) & ~3));
+    WarpScratch* scratch = reinterpret_cast<WarpScratch*>(stages + nwarps);
     {
         const uint4* grows = reinterpret_cast<const uint4*>(T.diagRows); uint4* s4 = reinterpret_cast<uint4*>(srows);
         for (int i = threadIdx.x; i < nrows * (kDiagStride / 4); i += blockDim.x) s4[i] = __ldg(grows + i);
         for (int i = threadIdx.x; i < nrows; i += blockDim.x) { spiv[i] = __ldg(T.diagPiv + i); smeta[i] = __ldg(T.diagMeta + i); }
+        for (int i = threadIdx.x; i < isize_smem; i += blockDim.x) sisize[i] = __ldg(T.isize + i);
     }
+    WarpStage* st = &stages[warp];
+    if (lane == 0) { mbar_init(&st->bar[0], 1); mbar_init(&st->bar[1], 1); mbar_fence_init(); }
     __syncthreads();
     QualSmem Q; Q.rows = srows; Q.piv = spiv; Q.meta = smeta;
-    const int nwarps = (int)(blockDim.x >> 5);   // <= kEmitWarps: long-read profiles leave room for fewer warp scratch areas
-    for (uint64_t ls = (uint64_t)blockIdx.x * nwarps + warp; ls < A.nslots; ls += (uint64_t)gridDim.x * nwarps)
-        do_slot(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], size1, size2, out1, out2, flags, records);
+    const uint32_t* isize_row = isize_smem ? sisize : T.isize;
+    const uint64_t stride = (uint64_t)gridDim.x * nwarps;
+    uint64_t ls = (uint64_t)blockIdx.x * nwarps + warp;
+    uint32_t made = 0, it = 0, phases = 0;
+    if (ls < A.nslots) plan_slot(g, dsrc, T, isize_row, A, ls, lane, st, 0);
+    for (; ls < A.nslots; ls += stride, it++) {
+        const int buf = (int)(it & 1u);
+        if (ls + stride < A.nslots) plan_slot(g, dsrc, T, isize_row, A, ls + stride, lane, st, buf ^ 1);
+        made += emit_slot(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], st, buf, phases, size1, size2, out1, out2, flags);
+    }
+    if (lane == 0 && made) atomicAdd(records, (unsigned long long)made);
+}
+
+// per coarse entry j: the amplicon that holds slot base + j * 2^kCoarseShift (slots past the end map to the last amplicon)
+__global__ void __launch_bounds__(256) coarse_index_kernel(const uint64_t* __restrict__ slot_base, uint64_t n_amp, uint64_t base, uint64_t n, uint32_t* __restrict__ coarse) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t slot = base + (j << kCoarseShift);
+    uint64_t lo = 0, hi = n_amp;   // last a with slot_base[a] <= slot
+    while (hi - lo > 1) { const uint64_t mid = (lo + hi) >> 1; if (slot_base[mid] <= slot) lo = mid; else hi = mid; }
+    coarse[j] = (uint32_t)lo;
 }
 
 // pack the staged records of one file: warp per record, 16-byte stores at the destination's alignment, the source realigned by
@@ -619,10 +786,18 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     // shared memory of a persistent emit CTA: the diagonal quality tables + one scratch area per warp; as many warps (<= 24) as fit
     const size_t table_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4;
     int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(table_smem, (size_t)smem_max)) / sizeof(WarpScratch));
+    const int isize_smem = (c->P.paired && T.isizeEff <= kISizeSmemCap) ? T.isizeEff : 0;
+    const size_t fixed_smem = table_smem + (size_t)((isize_smem + 3) & ~3) * 4, per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
+    const int emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(fixed_smem, (size_t)smem_max)) / per_warp);
     if (emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
-    const size_t emit_smem = table_smem + sizeof(WarpScratch) * (size_t)emit_warps;
+    const size_t emit_smem = fixed_smem + per_warp * (size_t)emit_warps;
     SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+
+    // coarse slot -> amplicon index of this rank's slot range (one entry per 1024 slots): the per-slot search starts from it
+    const uint64_t n_coarse = ((nslots - 1) >> kCoarseShift) + 2;
+    SCS_CUDA(c, W.coarse.reserve(n_coarse + 1));
+    coarse_index_kernel<<<(unsigned)((n_coarse + 255) / 256), 256, 0, c->st>>>(A.slot_base, A.n_amp, slot_lo, n_coarse, W.coarse.p); SCS_LAUNCHED(c);
+    A.coarse = W.coarse.p; A.coarse_base = slot_lo;
 
     StageGuard G(c);   // from here on every return drains the streams and frees the events
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
@@ -695,7 +870,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         if (nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
         SCS_CUDA(c, cudaEventRecord(tq[b][1], c->st));
         emit_kernel<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p,
-                                                                W.records.p);
+                                                                W.records.p, isize_smem);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
         if (int rc = scan_u32_noalloc(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;

@@ -165,16 +165,20 @@ def test_slab_limits_are_clean_errors(tmp_path):
         with pytest.raises(api.ScsError) as e:
             g.yield_reads_bytes()
         assert e.value.code == api.SCS_E_ARG
-    # insertion rate 0.06: ~7.5 events per read, every read ~18 bases longer than the profile's read length
     lines = open(prof).read().split("\n")
     i = lines.index("[Insert Rate]")
-    lines[i + 1] = "0.06"
-    heavy = os.path.join(str(tmp_path), "heavy.profile")
-    open(heavy, "w").write("\n".join(lines))
+
+    def with_insert_rate(rate, name):
+        lines[i + 1] = str(rate)
+        path = os.path.join(str(tmp_path), name)
+        open(path, "w").write("\n".join(lines))
+        return path
+    # insertion rate 0.12: ~15 insertions per read, every record ~55 bytes longer than the typical record the batch is sized for
     with api.GenReads(gamma=2e-10, coverage=40.0, layout="PE", seed=3, slab_bytes=256 << 10) as g:
-        g.load_profile(heavy).set_genome([("chrA_1_300000", seq)]).create_frags().amplify()
+        g.load_profile(with_insert_rate(0.12, "heavier.profile")).set_genome([("chrA_1_300000", seq)]).create_frags().amplify()
         with pytest.raises(api.ScsError) as e:
             g.yield_reads_bytes()
         assert e.value.code == api.SCS_E_NOMEM, e.value
+    heavy = with_insert_rate(0.06, "heavy.profile")   # ~7.5 insertions per read
     # same profile with a roomy slab: equals the oracle (reads with many indel events)
     _run_case(str(tmp_path), "heavy", 1, 300_000, 5, heavy, "PE", 2e-10, 8.0, 260, seed=3, slab_bytes=8 << 20)
