@@ -57,8 +57,8 @@ typedef struct scs_params {
                              cut into contiguous ranges in proportion to scs_set_shard_weight(), so a GPU behind a slower host
                              link gets fewer reads; the shards then concatenate (rank order) to exactly the 1-GPU files */
     uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (64 MiB) */
-    int32_t io_threads;   /* host threads that pwrite() each slab to the output files (the CLI's -t); 0 -> default (4) */
-    int32_t reserved;
+    int32_t io_threads;   /* host threads that pwrite() the slabs to the output files (the CLI's -t); 0 -> default (4) */
+    int32_t ring_slabs;   /* scs_yield_reads: pinned host slabs per file the asynchronous file sink may hold; 0 -> default (6) */
 } scs_params;
 
 void scs_default_params(scs_params* p);
@@ -100,9 +100,13 @@ int scs_amplify(scs_ctx* ctx);        /* Malbac::amplify, Malbac.cpp:173-201 */
  * host memory. file = 0 for <prefix>.fq / <prefix>_1.fq, 1 for <prefix>_2.fq. Return non-zero to abort. */
 typedef int (*scs_sink_fn)(void* user, int file, const char* data, size_t nbytes);
 int scs_yield_reads_sink(scs_ctx* ctx, scs_sink_fn sink, void* user);
-/* Malbac::yieldReads: writes <prefix>_1.fq/_2.fq (PE) or <prefix>.fq (SE). For world > 1 rank r
- * writes <prefix>.rank<r>... shard files whose concatenation in rank order is the full output. */
+/* Malbac::yieldReads: writes <prefix>_1.fq/_2.fq (PE) or <prefix>.fq (SE) through an asynchronous sink (writer threads behind a
+ * ring of pinned slabs; O_DIRECT + fallocate where the file system has them). For world > 1 all ranks write ONE pair of files:
+ * the byte count of every shard is computed first (scs_plan_fastq_bytes), exchanged through the collective hook, and every rank
+ * writes its shard at its final offset (with balance = 1 the files are byte-identical to a single-rank run). */
 int scs_yield_reads(scs_ctx* ctx, const char* prefix);
+/* Exact number of FASTQ bytes this rank will write to each file (a sizing pass over the indel draws; nothing is emitted). */
+int scs_plan_fastq_bytes(scs_ctx* ctx, uint64_t bytes[2]);
 /* Read allocation only (Malbac::setReadCounts); scs_yield_reads* call it themselves if needed. */
 int scs_set_read_counts(scs_ctx* ctx);
 
@@ -175,6 +179,12 @@ int64_t scs_svplan_dump(const scs_svplan* plan, int what, void* buf, uint64_t ca
  * sink in slabs of slab_bytes with the given thread count; returns 0 on success. */
 int64_t scs_test_fasta_index(const char* path, uint64_t* recs, uint64_t cap, char* names, uint64_t names_cap);
 int scs_test_file_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads);
+/* The asynchronous file sink of scs_yield_reads without a GPU: feeds n bytes in slabs of slab_bytes through a ring of `ring`
+ * page-aligned host buffers into `path` starting at file offset `base` (create != 0: create/truncate and preallocate `prealloc`
+ * bytes; otherwise the file must exist — several callers can fill disjoint regions of one file). direct != 0 asks for O_DIRECT;
+ * *used_direct tells whether the file system granted it. Returns 0 on success. */
+int scs_test_async_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads, int ring, uint64_t base, int create,
+                          uint64_t prealloc, int direct, int* used_direct);
 /* The first n values of libc rand() after srand(seed), as reproduced by the library. */
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out);
 

@@ -35,7 +35,7 @@ class Params(C.Structure):
     _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
                 ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64), ("io_threads", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("ring_slabs", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 
 class SimuVarsParams(C.Structure):
-    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("ring_slabs", C.c_int32)]
 
 
 class SimuVarsStats(C.Structure):
@@ -84,11 +84,11 @@ AR_DEV_I64_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 # every symbol include/scssim_b200.h declares
 EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", "scs_load_profile", "scs_read_length",
            "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_set_shard_weight", "scs_create_frags", "scs_amplify",
-           "scs_yield_reads_sink", "scs_yield_reads", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
+           "scs_yield_reads_sink", "scs_yield_reads", "scs_plan_fastq_bytes", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version", "scs_device_count",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
-           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer"]
+           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer", "scs_test_async_writer"]
 
 _lib = None
 
@@ -117,6 +117,7 @@ def lib():
             getattr(L, f).argtypes = [C.c_void_p]
         L.scs_yield_reads_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
         L.scs_yield_reads.argtypes = [C.c_void_p, C.c_char_p]
+        L.scs_plan_fastq_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.scs_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.scs_set_replay.argtypes = [C.c_void_p, C.POINTER(Replay)]
         L.scs_dump.restype = C.c_int64
@@ -149,6 +150,8 @@ def lib():
         L.scs_test_fasta_index.restype = C.c_int64
         L.scs_test_fasta_index.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint64]
         L.scs_test_file_writer.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
+        L.scs_test_async_writer.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_uint64, C.c_int,
+                                            C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -175,6 +178,16 @@ def write_file_parallel(path: str, data: bytes, slab_bytes: int, threads: int) -
     rc = lib().scs_test_file_writer(path.encode(), data, len(data), slab_bytes, threads)
     if rc != SCS_OK:
         raise ScsError(rc, f"can not write {path}")
+
+
+def write_file_async(path: str, data: bytes, slab_bytes: int, threads: int = 4, ring: int = 4, base: int = 0, create: bool = True, prealloc: int = 0,
+                     direct: bool = True) -> bool:
+    """Feed `data` through the asynchronous file sink of scs_yield_reads (host only). Returns whether O_DIRECT was in use."""
+    used = C.c_int(0)
+    rc = lib().scs_test_async_writer(path.encode(), data, len(data), slab_bytes, threads, ring, base, int(create), prealloc, int(direct), C.byref(used))
+    if rc != SCS_OK:
+        raise ScsError(rc, f"can not write {path}")
+    return bool(used.value)
 
 
 def shard_sequences(lens, rank: int, world: int):
@@ -208,7 +221,7 @@ class GenReads:
 
     def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
                  layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
-                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0):
+                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0, ring_slabs: int = 0):
         if layout not in ("SE", "PE"):
             raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
         L = lib()
@@ -218,6 +231,7 @@ class GenReads:
         p.paired, p.seed, p.device, p.rank, p.world, p.slab_bytes = int(layout == "PE"), seed, device, rank, world, slab_bytes
         p.balance = int(balance)
         p.io_threads = io_threads
+        p.ring_slabs = ring_slabs
         self._h = C.c_void_p()
         rc = L.scs_create(C.byref(p), C.byref(self._h))
         if rc != SCS_OK:
@@ -326,6 +340,12 @@ class GenReads:
     def yield_reads(self, prefix: str):         # malbac.yieldReads() -> <prefix>_1.fq/_2.fq | <prefix>.fq
         self._ck(lib().scs_yield_reads(self._h, prefix.encode()))
         return self
+
+    def plan_fastq_bytes(self):
+        """Exact FASTQ bytes this rank will write to each file (sizing pass)."""
+        b = (C.c_uint64 * 2)()
+        self._ck(lib().scs_plan_fastq_bytes(self._h, b))
+        return [int(b[0]), int(b[1])]
 
     def yield_reads_bytes(self):
         """FASTQ text of both files as bytes (tests; small runs)."""

@@ -22,7 +22,7 @@ int scs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
     p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
-    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0;
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0; p->ring_slabs = 0;
 }
 
 int scs_create(const scs_params* p, scs_ctx** out) {
@@ -125,16 +125,63 @@ int scs_yield_reads_sink(scs_ctx* c, scs_sink_fn sink, void* user) {
     return yield_reads(c, cb);
 }
 
-int scs_yield_reads(scs_ctx* c, const char* prefix) {   // Malbac.cpp:426-435: <prefix>_1.fq/_2.fq or <prefix>.fq
+int scs_plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]) {
+    if (!c || !bytes) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
+    return plan_fastq_bytes(c, bytes);
+}
+
+// Malbac::yieldReads' file side (Malbac.cpp:426-435, SeqWriter.cpp:12-54): <prefix>_1.fq/_2.fq or <prefix>.fq through the
+// asynchronous sink. With several ranks all of them write ONE pair of files: a sizing pass gives every rank the exact number of
+// bytes it will produce, the byte counts are exchanged, rank 0 creates and preallocates the files and every rank pwrite()s its
+// shard at its final offset — no per-rank shard files, no concatenation pass.
+int scs_yield_reads(scs_ctx* c, const char* prefix) {
     if (!c || !prefix) return SCS_E_ARG;
-    std::string base = prefix;
-    if (c->P.world > 1) base += ".rank" + std::to_string(c->P.rank);
-    std::string n1 = c->P.paired ? base + "_1.fq" : base + ".fq", n2 = base + "_2.fq";
-    ParallelFileWriter w(c->P.io_threads > 0 ? c->P.io_threads : 4);
-    if (!w.open(0, n1)) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n1);
-    if (c->P.paired && !w.open(1, n2)) return c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + n2);
-    int rc = scs_yield_reads_sink(c, parallel_file_sink, &w);
-    if (w.close() != 0 && rc == SCS_OK) rc = c->fail(SCS_E_IO, "Error: can not write fastq file:\n" + n1);
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
+    const int W = std::max(1, c->P.world), R = c->P.rank, nfiles = c->P.paired ? 2 : 1;
+    const std::string base = prefix;
+    const std::string name[2] = {c->P.paired ? base + "_1.fq" : base + ".fq", base + "_2.fq"};
+    if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
+    if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
+    uint64_t off[2] = {0, 0}, total[2] = {0, 0}, mine[2] = {0, 0};
+    if (W > 1) {
+        if (int rc = plan_fastq_bytes(c, mine)) {   // every rank must still take part in the exchange
+            std::vector<uint64_t> v(2 * (size_t)W + 1, 0); v[2 * (size_t)W] = 1; (void)allreduce_u64(c, v.data(), v.size());
+            return rc;
+        }
+        std::vector<uint64_t> v(2 * (size_t)W + 1, 0);
+        v[2 * (size_t)R] = mine[0]; v[2 * (size_t)R + 1] = mine[1];
+        if (int rc = allreduce_u64(c, v.data(), v.size())) return rc;
+        if (v[2 * (size_t)W]) return c->fail(SCS_E_STATE, "scs_yield_reads: another rank failed in the sizing pass");
+        for (int r = 0; r < W; r++) for (int f = 0; f < 2; f++) { if (r < R) off[f] += v[2 * (size_t)r + f]; total[f] += v[2 * (size_t)r + f]; }
+    } else {
+        const uint64_t slots = c->global_view ? c->g_slot_hi - c->g_slot_lo : c->n_slots;
+        total[0] = total[1] = slots * (uint64_t)(30 + 2 * (c->prof.readLength + 8) + 4);   // preallocation only: trimmed to the bytes written
+    }
+    AsyncFileConsumer sink(c->P.io_threads > 0 ? c->P.io_threads : 4, c->P.ring_slabs > 0 ? c->P.ring_slabs : 6, c->P.device, getenv("SCS_NO_ODIRECT") == nullptr);
+    int rc = SCS_OK;
+    auto open_all = [&](bool create) {
+        for (int f = 0; f < nfiles && rc == SCS_OK; f++)
+            if (!sink.open(f, name[f], off[f], create, create ? total[f] : 0, W == 1)) rc = c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + name[f]);
+    };
+    if (R == 0) open_all(true);
+    if (W > 1) {   // the files exist (or rank 0 could not create them) before the other ranks open them
+        uint64_t bad = rc != SCS_OK ? 1 : 0;
+        if (int rc2 = allreduce_u64(c, &bad, 1)) return rc2;
+        if (bad) return rc != SCS_OK ? rc : c->fail(SCS_E_IO, "Error: can not open fastq file to save results:\n" + name[0]);
+        if (R != 0) open_all(false);
+    }
+    if (rc == SCS_OK) rc = yield_reads(c, sink);
+    else (void)sink.finish();
+    if (rc == SCS_OK && W > 1 && (sink.bytes(0) != mine[0] || (nfiles == 2 && sink.bytes(1) != mine[1])))
+        rc = c->fail(SCS_E_STATE, "scs_yield_reads: shard size differs from the sizing pass");
+    if (W > 1) {   // nobody returns before every shard is in the files
+        uint64_t bad = rc != SCS_OK ? 1 : 0;
+        if (int rc2 = allreduce_u64(c, &bad, 1)) return rc != SCS_OK ? rc : rc2;
+        if (bad && rc == SCS_OK) rc = c->fail(SCS_E_IO, "scs_yield_reads: another rank failed while writing " + name[0]);
+    }
     return rc;
 }
 
@@ -223,6 +270,31 @@ int scs_test_file_writer(const char* path, const char* data, uint64_t n, uint64_
     if (!w.open(0, path)) return SCS_E_IO;
     for (uint64_t o = 0; o < n; o += slab_bytes) if (w.write(0, data + o, (size_t)std::min(slab_bytes, n - o))) return SCS_E_IO;
     return w.close() ? SCS_E_IO : SCS_OK;
+}
+// The asynchronous file sink without a GPU: `n` bytes are fed slab by slab through a ring of page-aligned host buffers exactly as
+// the read stage feeds it (each slab placed at the phase the sink asks for, no copy event), starting at file offset `base`.
+int scs_test_async_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads, int ring, uint64_t base, int create,
+                          uint64_t prealloc, int direct, int* used_direct) {
+    if (!path || (!data && n) || slab_bytes == 0) return SCS_E_ARG;
+    AsyncFileConsumer sink(threads, ring, -1, direct != 0);
+    if (!sink.open(0, path, base, create != 0, prealloc, false)) return SCS_E_IO;
+    if (used_direct) *used_direct = sink.direct(0) ? 1 : 0;
+    const int R = sink.ring_slots();
+    std::vector<char*> slots((size_t)R, nullptr);
+    for (auto& q : slots) if (posix_memalign((void**)&q, 4096, slab_bytes + 4096 + 64) != 0) return SCS_E_NOMEM;
+    int rc = SCS_OK; uint64_t k = 0;
+    for (uint64_t o = 0; o < n && rc == SCS_OK; o += slab_bytes, k++) {
+        const uint64_t m = std::min(slab_bytes, n - o);
+        const int slot = (int)(k % (uint64_t)R);
+        if (sink.acquire(slot)) { rc = SCS_E_IO; break; }
+        char* p[2] = {slots[slot] + (sink.phase(0) & 4095), nullptr};
+        memcpy(p[0], data + o, m);
+        const uint64_t bytes[2] = {m, 0};
+        if (sink.submit(slot, nullptr, p, bytes)) rc = SCS_E_IO;
+    }
+    if (sink.finish()) rc = SCS_E_IO;
+    for (char* q : slots) free(q);
+    return rc;
 }
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out) {
     if (!out || n < 0) return SCS_E_ARG;

@@ -168,15 +168,6 @@ struct ThreadSum {
 static int sum_u64(void* u, uint64_t* b, size_t n) { ThreadSum* t = (ThreadSum*)u; return t->sum(t->au, b, n); }
 static int sum_f64(void* u, double* b, size_t n) { ThreadSum* t = (ThreadSum*)u; return t->sum(t->ad, b, n); }
 
-static int append_file(const std::string& dst, const std::string& src, bool truncate) {
-    FILE* o = fopen(dst.c_str(), truncate ? "wb" : "ab"); FILE* i = fopen(src.c_str(), "rb");
-    if (!o || !i) { if (o) fclose(o); if (i) fclose(i); return 1; }
-    std::vector<char> buf(8 << 20); size_t n;
-    while ((n = fread(buf.data(), 1, buf.size(), i)) > 0) if (fwrite(buf.data(), 1, n, o) != n) { fclose(o); fclose(i); return 1; }
-    fclose(o); fclose(i); remove(src.c_str());
-    return 0;
-}
-
 static int die(scs_ctx* c, int rc) {
     cerr << scs_last_error(c) << endl;
     if (c) scs_destroy(c);
@@ -256,7 +247,7 @@ int main(int argc, char* argv[]) {
         std::vector<uint64_t> reads(gpus, 0);
         cerr << "\nReference sequence and profile are loaded by " << gpus << " GPU workers" << endl << "\nMALBAC amplification..." << endl;
         auto worker = [&](int r) {
-            scs_params Q = P; Q.rank = r; Q.world = gpus; Q.balance = 1;   // equal slot ranges; shards concatenate to the 1-GPU files
+            scs_params Q = P; Q.rank = r; Q.world = gpus; Q.balance = 1;   // equal slot ranges; the shards are consecutive regions of the output files
             Q.device = getenv("SCS_CLI_SAME_DEVICE") ? P.device : P.device + r;   // test hook: all workers on one GPU
             scs_ctx* c = nullptr;
             int rc = scs_create(&Q, &c);
@@ -276,14 +267,8 @@ int main(int argc, char* argv[]) {
         int bad = -1;
         for (int r = 0; r < gpus; r++) if (rcs[r] && (bad < 0 || errs[bad].find("callback failed") != string::npos)) bad = r;
         if (bad >= 0) { cerr << errs[bad] << endl; return rcs[bad] == SCS_E_IO ? -1 : 1; }
+        // every worker wrote its shard at its final offset of the reference's file names (scs_yield_reads: sizing pass + exchange)
         cerr << "\nNumber of reads to generate: " << reads[0] << endl << "\n*****Producing reads*****" << endl;
-        // shards <prefix>.rank<r>... are concatenated in rank order into the reference's file names
-        for (int r = 0; r < gpus; r++) {
-            string sh = outputPrefix + ".rank" + to_string(r);
-            int bad = P.paired ? (append_file(outputPrefix + "_1.fq", sh + "_1.fq", r == 0) | append_file(outputPrefix + "_2.fq", sh + "_2.fq", r == 0))
-                               : append_file(outputPrefix + ".fq", sh + ".fq", r == 0);
-            if (bad) { cerr << "Error: can not open fastq file to save results:\n" << outputPrefix << endl; return -1; }
-        }
         cerr << "\nReads generation done!" << endl;
         long used = (long)(time(NULL) - start_t);
         cerr << "\nElapsed time: " << used / 60 << " minutes and " << used % 60 << " seconds!\n" << endl;

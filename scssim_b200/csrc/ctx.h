@@ -270,6 +270,7 @@ int amplify(scs_ctx* c);
 int set_read_counts(scs_ctx* c);
 struct SlabConsumer;
 int yield_reads(scs_ctx* c, SlabConsumer& sink);
+int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]);
 int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
                  uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len);
 int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written);

@@ -29,7 +29,10 @@ __device__ __noinline__ void philox4x32_10_call(uint32_t c0, uint32_t c1, uint32
 }
 
 constexpr int kReadWarps = 8;         // warps per CTA (test kernels)
-constexpr int kEmitWarps = 24;        // warps per persistent CTA of the emit kernel (one CTA per SM)
+#ifndef SCS_EMIT_WARPS
+#define SCS_EMIT_WARPS 24
+#endif
+constexpr int kEmitWarps = SCS_EMIT_WARPS;   // warps per persistent CTA of the emit kernel (one CTA per SM); tuning: profiles/ab_warps.sh
 constexpr int kDiagW = 40;            // entries per compact quality row kept in shared memory (shipped profiles need <= 39)
 constexpr int kDiagStride = 44;       // words per row: 40 + 4 pad; 44*r mod 32 is a distinct multiple of 4 for 8 neighbouring rows,
                                       // so their 128-bit loads are bank-conflict free
@@ -54,6 +57,21 @@ struct ReadTables {
 };
 
 struct QualSmem { const uint32_t* rows; const uint4* piv; const uint32_t* meta; };
+// what the substitution + quality pass needs, small enough to travel by value in registers (the out-of-line N path must not force
+// the kernel's parameter structs onto the stack)
+struct PassTabs {
+    const uint4* subs;                                  // substitution thresholds of this mate, [84][bins] x (3 thresholds + count)
+    const uint32_t* qual; const uint8_t* qualEff;       // global quality thresholds
+    const uint32_t* rows; const uint4* piv; const uint32_t* meta;   // compact diagonal quality rows in shared memory (rows == nullptr: none)
+    int bins;
+};
+__device__ __forceinline__ PassTabs make_pass_tabs(const ReadTables& T, const QualSmem* Q, int isRead1) {
+    PassTabs X;
+    X.subs = reinterpret_cast<const uint4*>((!isRead1 && T.subs2) ? T.subs2 : T.subs1);
+    X.qual = T.qual; X.qualEff = T.qualEff; X.bins = T.RL;
+    X.rows = Q ? Q->rows : nullptr; X.piv = Q ? Q->piv : nullptr; X.meta = Q ? Q->meta : nullptr;
+    return X;
+}
 
 // What the emit kernel knows about a slot one slot ahead of processing it (stage A -> stage B, through shared memory)
 struct SlotPlan {
@@ -107,10 +125,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// Stream with the replay decision made at compile time: the free-running kernels carry no tape branches (and no tape code —
+// the emit kernel has to stay small enough for the instruction cache), the replay instantiation no Philox.
+template <bool REPLAY> struct RStream : Stream {
+    __device__ __forceinline__ bool replay() const { return REPLAY; }
+    __device__ __forceinline__ void block(int engine, uint32_t b, uint32_t out[4]) const {
+        if (REPLAY) { const uint32_t* p = t[engine] + 4ull * b; out[0] = p[0]; out[1] = p[1]; out[2] = p[2]; out[3] = p[3]; }
+        else philox4x32_10(e0, e1, b, dom2 + (uint32_t)engine, k0, k1, out);
+    }
+    __device__ __forceinline__ uint32_t at(int engine, uint32_t i) const {
+        if (REPLAY) return t[engine][i];
+        uint32_t o[4];
+        philox4x32_10_call(e0, e1, i >> 2, dom2 + (uint32_t)engine, k0, k1, o);
+        return o[i & 3];
+    }
+};
+
 // Draws base+4*lane .. base+4*lane+3 of one engine: one Philox block per lane. When `base` is not a multiple of 4 a lane also
 // needs the first words of its right neighbour's block; instead of running a 33rd block for lane 31 alone (a whole Philox for one
 // lane), only lanes 0..30 own positions in that case. Returns the number of draws the step covers (128 or 124).
-__device__ __forceinline__ int warp_draws4(const Stream& S, int eng, uint32_t base, int lane, uint32_t x[4]) {
+template <class SX>
+__device__ __forceinline__ int warp_draws4(const SX& S, int eng, uint32_t base, int lane, uint32_t x[4]) {
     if (S.replay()) {
         const uint32_t* p = S.t[eng] + base + 4u * lane;
         x[0] = p[0]; x[1] = p[1]; x[2] = p[2]; x[3] = p[3];
@@ -132,7 +167,8 @@ __device__ __forceinline__ int warp_draws4(const Stream& S, int eng, uint32_t ba
 // int cursors exactly as the sequential code does; returns the output length n'. Events (position,
 // +inserted / -deleted, first int draw) go to the warp scratch; *nev = 0 if there are none or if the
 // "< 50 bases" guard discarded them.
-__device__ __forceinline__ int indel_pass(const Stream& S, const ReadTables& T, int n, uint32_t& cr, uint32_t& ci, int lane, WarpScratch* ws,
+template <class SX>
+__device__ __forceinline__ int indel_pass(const SX& S, const ReadTables& T, int n, uint32_t& cr, uint32_t& ci, int lane, WarpScratch* ws,
                                           int* nev_out, int* flags) {
     int j = 0, delta = 0, nev = 0;
     while (j < n) {
@@ -180,8 +216,8 @@ __device__ __forceinline__ int indel_pass(const Stream& S, const ReadTables& T, 
 
 // source sequence after indels (Profile.cpp:1632-1654): every lane maps its output positions back through the
 // (few) recorded events, so there is no serial walk
-__device__ __forceinline__ const uint8_t* build_source(const Stream& S, int np, int nev, int lane, WarpScratch* ws) {
-    if (nev == 0) return ws->ref;
+template <class SX>
+__device__ __noinline__ void build_source_events(const SX S, int np, int nev, int lane, WarpScratch* ws) {
     for (int m = lane; m < np; m += 32) {
         int shift = 0; uint32_t b = 0; bool done = false;
         for (int e = 0; e < nev; e++) {
@@ -199,37 +235,44 @@ __device__ __forceinline__ const uint8_t* build_source(const Stream& S, int np, 
         ws->src[m] = done ? (uint8_t)b : ws->ref[m - shift];
     }
     __syncwarp();
+}
+// only ~11 % of the reads carry an indel event: the rebuild stays out of line so that the hot path is short
+template <class SX>
+__device__ __forceinline__ const uint8_t* build_source(const SX& S, int np, int nev, int lane, WarpScratch* ws) {
+    if (nev == 0) return ws->ref;
+    build_source_events(S, np, nev, lane, ws);
     return ws->src;
 }
 
 // quality index for (reference base b0, emitted base k, bin): diagonal rows from shared memory with a
 // 4-pivot + 8-entry search (two dependent 128-bit loads), everything else by binary search in global memory
-__device__ __forceinline__ int sample_quality(const ReadTables& T, const QualSmem* Q, uint32_t b0, uint32_t k, int bin, uint32_t xq) {
-    if (Q != nullptr && k == b0) {
-        const int r = (int)b0 * T.RL + bin;
-        const uint32_t meta = Q->meta[r];
+__device__ __forceinline__ int sample_quality(const PassTabs& X, uint32_t b0, uint32_t k, int bin, uint32_t xq) {
+    if (X.rows != nullptr && k == b0) {
+        const int r = (int)b0 * X.bins + bin;
+        const uint32_t meta = X.meta[r];
         if ((meta >> 16) == 0) {
             const int lo = (int)(meta & 0xFFu), cnt = (int)((meta >> 8) & 0xFFu);
-            const uint4 pv = Q->piv[r];
+            const uint4 pv = X.piv[r];
             // pivots = entries 7, 15, 23, 31: they select one of five octets, which is then counted
             const int oct = (int)(pv.x <= xq) + (int)(pv.y <= xq) + (int)(pv.z <= xq) + (int)(pv.w <= xq);
-            const uint4* row = reinterpret_cast<const uint4*>(Q->rows + (size_t)r * kDiagStride + oct * 8);
+            const uint4* row = reinterpret_cast<const uint4*>(X.rows + (size_t)r * kDiagStride + oct * 8);
             const uint4 a = row[0], d = row[1];
             const int c = oct * 8 + (int)(a.x <= xq) + (int)(a.y <= xq) + (int)(a.z <= xq) + (int)(a.w <= xq) + (int)(d.x <= xq) + (int)(d.y <= xq) +
                           (int)(d.z <= xq) + (int)(d.w <= xq);
             return lo + min(c, cnt);
         }
     }
-    const size_t row = (size_t)(b0 * 4u + k) * T.RL + bin;
-    return count_le(T.qual + row * kQualN, (int)T.qualEff[row], xq);
+    const size_t row = (size_t)(b0 * 4u + k) * X.bins + bin;
+    return count_le(X.qual + row * kQualN, (int)X.qualEff[row], xq);
 }
 
 // substitution + quality loop (Profile.cpp:1656-1694): two output positions per lane per step. The threshold rows of both
 // positions are requested before the Philox block is computed, so the L2 latency of the loads hides under the ~100 ALU instructions.
-__device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTables& T, const QualSmem* Q, const uint8_t* __restrict__ src, int np,
-                                                   int isRead1, uint32_t& cr, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
-    const uint4* __restrict__ subs = reinterpret_cast<const uint4*>((!isRead1 && T.subs2) ? T.subs2 : T.subs1);
-    const int bins = T.RL;
+template <class SX>
+__device__ __forceinline__ void subst_quality_pass(const SX& S, const PassTabs& X, const uint8_t* __restrict__ src, int np,
+                                                   uint32_t& cr, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
+    const uint4* __restrict__ subs = X.subs;
+    const int bins = X.bins;
     const int P = S.replay() ? 64 : (((cr & 3u) == 0) ? 64 : 62);   // the alignment of cr + 2*m0 does not change inside the pass
     for (int m0 = 0; m0 < np; m0 += P) {
         uint4 th[2]; uint32_t b0[2]; int bin[2]; bool ok[2];
@@ -257,7 +300,7 @@ __device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTa
                 const uint32_t xs = x[2 * h], xq = x[2 * h + 1];
                 // thresholds are non-decreasing and padded with 0xFFFFFFFF: the leading count, capped by the row's entry count
                 const uint32_t k = min((uint32_t)(th[h].x <= xs) + (uint32_t)(th[h].y <= xs) + (uint32_t)(th[h].z <= xs), th[h].w);
-                const int q = sample_quality(T, Q, b0[h], k, bin[h], xq);
+                const int q = sample_quality(X, b0[h], k, bin[h], xq);
                 oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);   // "ACGT"[k]
                 oqual[m] = (char)(33 + q);
             }
@@ -270,11 +313,11 @@ __device__ __forceinline__ void subst_quality_pass(const Stream& S, const ReadTa
 // (emitted as 'N' with quality randomInteger(33,53), Profile.cpp:1578-1580,1686-1688), 1 real when only the k-mer context
 // holds an N (no substitution draw, Profile.cpp:1527-1529), 2 otherwise — so draw indices come from a warp prefix sum.
 // WRITE = false only advances the cursors (plan kernel).
-template <bool WRITE>
-__device__ __forceinline__ void subst_quality_pass_n(const Stream& S, const ReadTables& T, const QualSmem* Q, const uint8_t* __restrict__ src, int np,
-                                                     int isRead1, uint32_t& cr, uint32_t& ci, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
-    const uint32_t* __restrict__ subs = (!isRead1 && T.subs2) ? T.subs2 : T.subs1;
-    const int bins = T.RL;
+template <bool WRITE, class SX>
+__device__ __noinline__ uint2 subst_quality_pass_n(const SX S, const PassTabs X, const uint8_t* __restrict__ src, int np,
+                                                     uint32_t cr, uint32_t ci, int lane, char* __restrict__ oseq, char* __restrict__ oqual) {
+    const uint4* __restrict__ subs = X.subs;
+    const int bins = X.bins;
     for (int m0 = 0; m0 < np; m0 += 32) {
         const int m = m0 + lane;
         const bool valid = m < np;
@@ -300,32 +343,39 @@ __device__ __forceinline__ void subst_quality_pass_n(const Stream& S, const Read
                 if (!ctxN) {
                     uint32_t ki;
                     if (m == 0) ki = b0; else if (m == 1) ki = 4u + 4u * src[0] + b0; else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0;
-                    const uint4 th = __ldg(reinterpret_cast<const uint4*>(subs) + ((size_t)ki * bins + bin));
+                    const uint4 th = __ldg(subs + ((size_t)ki * bins + bin));
                     const uint32_t xs = S.at(E_REAL, ir);
                     k = (uint32_t)(th.w > 0 && th.x <= xs) + (uint32_t)(th.w > 1 && th.y <= xs) + (uint32_t)(th.w > 2 && th.z <= xs);
                     xq = S.at(E_REAL, ir + 1);
                 } else xq = S.at(E_REAL, ir);
-                const int q = sample_quality(T, Q, b0, k, bin, xq);
+                const int q = sample_quality(X, b0, k, bin, xq);
                 oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);
                 oqual[m] = (char)(33 + q);
             }
         }
         cr += tot_r; ci += tot_i;
     }
+    return make_uint2(cr, ci);   // the cursors after the pass
 }
 
 __device__ __forceinline__ int dec_digits(uint32_t v) {
     return v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 : v < 10000000u ? 7 : v < 100000000u ? 8 : v < 1000000000u ? 9 : 10;
 }
-__constant__ uint32_t kPow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+// floor(2^64 / 10^k) + 1: v / 10^k == umul64hi(v, kInvPow10[k]) for every 32-bit v (error < 2^-32 < 10^-9 <= 1/10^k); k = 0 unused
+__constant__ uint64_t kInvPow10[10] = {0ull, 1844674407370955162ull, 184467440737095517ull, 18446744073709552ull, 1844674407370956ull,
+                                       184467440737096ull, 18446744073710ull, 1844674407371ull, 184467440738ull, 18446744074ull};
 // "@%d#%d" (+"/1" | "/2") + "\n": the %d of a negative amplicon index never occurs (index < 2^31)
 __device__ __forceinline__ int header_len(int da, int df, int paired) { return 1 + da + 1 + df + (paired ? 2 : 0) + 1; }
 // the whole record frame in one go, one character per lane: header digits (lane l = l-th character after '@'), "/m", and the
 // three separators "\n+\n" ... "\n" around the sequence and quality lines of np characters each
 __device__ __forceinline__ void write_frame(char* rec, uint32_t amp, uint32_t frag, int da, int df, int mate, int hl, int np, int lane) {
-    if (lane < da) rec[1 + lane] = (char)('0' + (amp / kPow10[da - 1 - lane]) % 10u);
-    else if (lane == da) rec[1 + da] = '#';
-    else if (lane < da + 1 + df) { const int t = lane - da - 1; rec[2 + da + t] = (char)('0' + (frag / kPow10[df - 1 - t]) % 10u); }
+    if (lane < da + 1 + df && lane != da) {   // one digit: value / 10^k % 10 by multiplication with the 64-bit reciprocal
+        const bool first = lane < da;
+        const uint32_t v = first ? amp : frag;
+        const int k = first ? da - 1 - lane : df - 1 - (lane - da - 1);
+        const uint32_t q = k ? (uint32_t)__umul64hi((uint64_t)v, kInvPow10[k]) : v;
+        rec[1 + lane] = (char)('0' + q % 10u);
+    } else if (lane == da) rec[1 + da] = '#';
     else if (lane == 24) rec[0] = '@';
     else if (lane == 25) { if (mate) { rec[hl - 3] = '/'; rec[hl - 2] = (char)('0' + mate); } rec[hl - 1] = '\n'; }
     else if (lane == 26) { rec[hl + np] = '\n'; rec[hl + np + 1] = '+'; rec[hl + np + 2] = '\n'; }
@@ -392,6 +442,7 @@ __device__ __forceinline__ uint64_t find_amplicon(const uint64_t* __restrict__ s
 // ---- draws — then ONE lane asks the TMA unit for the packed windows of both mates (cp.async.bulk -> this warp's shared memory).
 // ---- Runs one slot ahead of stage B, so the dependent-load chain (coarse index -> slot prefix -> descriptor -> genome) of the
 // ---- next slot overlaps the synthesis of the current one.
+template <bool SIZE_ONLY, bool REPLAY>
 __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const uint32_t* __restrict__ isize_row, const SlabArgs& A,
                                           uint64_t ls, int lane, WarpStage* st, int buf) {
     const uint64_t slot = A.slot0 + ls;
@@ -405,11 +456,12 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
     const uint32_t fragNo = A.hdr_no ? A.hdr_no[slot - A.fail_base] : (uint32_t)(slot - sb) + 1u;
     const int RL = T.RL; const int ampLen = (int)F.len;
     const bool valid = fragNo != 0 && ampLen >= RL;   // dropped slot / Amplicon.cpp:442
+    const bool need_bases = !SIZE_ONLY || g.has_n;    // record sizes depend on the bases only through the draws an N consumes
     uint32_t cr = 0, ci = 0; int pos = 0, isz = RL;
     uint32_t woff[2] = {0, 0}, noff[2] = {0, 0};
     __syncwarp();   // every lane is done reading this buffer's previous windows and plan
     if (valid) {
-        Stream S; S.init(dsrc, D_READ, entity, entity);
+        RStream<REPLAY> S; S.init(dsrc, D_READ, entity, entity);
         if (T.paired) {
             if (A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
             isz = T.minInsert + warp_count_le(isize_row, T.isizeEff, S.at(E_REAL, cr), lane);
@@ -441,7 +493,7 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
                 }
             }
         }
-        if (lane == 0) {
+        if (lane == 0 && need_bases) {
             mbar_arrive_expect_tx(&st->bar[buf], tx);
             const uint8_t* gw = reinterpret_cast<const uint8_t*>(g.words); const uint8_t* gn = reinterpret_cast<const uint8_t*>(g.nmask);
 #pragma unroll
@@ -464,6 +516,7 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
 
 // ---- stage B: one slot (SE read / PE pair). Every record goes to its slot's fixed-stride cell of the staging buffer and its size
 // ---- is recorded; compact_records_kernel packs them afterwards.
+template <bool SIZE_ONLY, bool REPLAY>
 __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& dsrc, const ReadTables& T, const QualSmem* Q, const SlabArgs& A, uint64_t ls, int lane,
                                               WarpScratch* ws, WarpStage* st, int buf, uint32_t& phases, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
                                               char* __restrict__ out1, char* __restrict__ out2, int* flags) {
@@ -474,11 +527,14 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
     const uint32_t* __restrict__ errs = P.errs;
     const int pos = P.pos, isz = P.isz;
     uint32_t cr = P.cr, ci = P.ci;
-    Stream S; S.init(dsrc, D_READ, P.entity, P.entity);
+    RStream<REPLAY> S; S.init(dsrc, D_READ, P.entity, P.entity);
     const int da = dec_digits(ampIdx), df = dec_digits(fragNo);
     const int hl = header_len(da, df, T.paired);
-    mbar_wait(&st->bar[buf], (phases >> buf) & 1u);   // the packed windows have landed
-    phases ^= 1u << buf;                              // a buffer's barrier advances one phase per valid slot that used it
+    const bool need_bases = !SIZE_ONLY || g.has_n;
+    if (need_bases) {
+        mbar_wait(&st->bar[buf], (phases >> buf) & 1u);   // the packed windows have landed
+        phases ^= 1u << buf;                              // a buffer's barrier advances one phase per valid slot that used it
+    }
     uint32_t made = 0;
 #pragma unroll 1
     for (int mate = 1; mate <= (T.paired ? 2 : 1); mate++) {
@@ -487,7 +543,7 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         const uint8_t* __restrict__ win = st->win[buf][mate - 1];
         __syncwarp();
         bool myN = false;
-        for (int i = lane; i < RL; i += 32) {
+        if (need_bases) for (int i = lane; i < RL; i += 32) {
             const uint32_t q = off + (uint32_t)(rev ? (RL - 1 - i) : i);
             uint32_t b = ((uint32_t)win[q >> 2] >> ((q & 3u) * 2u)) & 3u;
             if (rev) b ^= 3u;
@@ -500,7 +556,7 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         __syncwarp();
         // ---- substitution overlay of the amplicon, once per window: an error at window base fi lands at read position
         // ---- fi - pos (mate 1) or pos + isz - 1 - fi, complemented (mate 2). It also overrides an N.
-        for (uint32_t e = lane; e < nerr; e += 32) {
+        if (need_bases) for (uint32_t e = lane; e < nerr; e += 32) {
             const uint32_t v = errs[e];
             const int fi = (int)err_pos(v);
             const int i = (mate == 1) ? fi - pos : pos + isz - 1 - fi;
@@ -512,13 +568,25 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
         if (np > kSrcCap) { if (lane == 0) atomicOr(flags, 8); return made; }
         __syncwarp();
-        const uint8_t* src = build_source(S, np, nev, lane, ws);
         const int total = hl + 2 * np + 4;
         if ((uint64_t)total > A.stage_stride) { if (lane == 0) atomicOr(flags, 16); return made; }
+        if (SIZE_ONLY) {   // only the cursors and the record size: the substitution / quality pass draws twice per base, fewer around an N
+            if (hasN) {
+                const uint8_t* srcn = build_source(S, np, nev, lane, ws);
+                const uint2 cc = subst_quality_pass_n<false>(S, make_pass_tabs(T, nullptr, mate == 1), srcn, np, cr, ci, lane, nullptr, nullptr);
+                cr = cc.x; ci = cc.y;
+            }
+            else cr += 2u * (uint32_t)np;
+            if (lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;
+            made++;
+            continue;
+        }
+        const uint8_t* src = build_source(S, np, nev, lane, ws);
         char* rec = ws->rec;
         write_frame(rec, ampIdx, fragNo, da, df, T.paired ? mate : 0, hl, np, lane);
-        if (hasN) subst_quality_pass_n<true>(S, T, Q, src, np, mate == 1, cr, ci, lane, rec + hl, rec + hl + np + 3);
-        else subst_quality_pass(S, T, Q, src, np, mate == 1, cr, lane, rec + hl, rec + hl + np + 3);
+        const PassTabs X = make_pass_tabs(T, Q, mate == 1);
+        if (hasN) { const uint2 cc = subst_quality_pass_n<true>(S, X, src, np, cr, ci, lane, rec + hl, rec + hl + np + 3); cr = cc.x; ci = cc.y; }
+        else subst_quality_pass(S, X, src, np, cr, lane, rec + hl, rec + hl + np + 3);
         __syncwarp();
         copy_out(((mate == 1) ? out1 : out2) + ls * A.stage_stride, rec, total, lane);
         if (lane == 0) ((mate == 1) ? size1 : size2)[ls] = (uint32_t)total;
@@ -530,6 +598,7 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
 // emit: persistent CTAs (one per SM). The diagonal quality tables and the insert-size thresholds are staged in shared memory once
 // per CTA; every warp then walks its slots with a two-deep software pipeline: plan_slot (lookups, draws, TMA request for the
 // genome windows) for slot k+1, then emit_slot for slot k whose windows have landed meanwhile.
+template <bool SIZE_ONLY, bool REPLAY>
 __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, char* __restrict__ out1, char* __restrict__ out2,
                                                                   int* flags, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
                                                                   unsigned long long* __restrict__ records, int isize_smem) {
@@ -555,13 +624,13 @@ __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, Draw
     QualSmem Q; Q.rows = srows; Q.piv = spiv; Q.meta = smeta;
     const uint32_t* isize_row = isize_smem ? sisize : T.isize;
     const uint64_t stride = (uint64_t)gridDim.x * nwarps;
-    uint64_t ls = (uint64_t)blockIdx.x * nwarps + warp;
-    uint32_t made = 0, it = 0, phases = 0;
-    if (ls < A.nslots) plan_slot(g, dsrc, T, isize_row, A, ls, lane, st, 0);
-    for (; ls < A.nslots; ls += stride, it++) {
+    // iteration `it` plans slot `it` (lookups, draws, TMA request) and then emits slot `it - 1`, whose windows have landed meanwhile
+    const uint64_t first = (uint64_t)blockIdx.x * nwarps + warp;
+    uint32_t made = 0, phases = 0;
+    for (uint64_t ls = first, it = 0; ls < A.nslots + stride; ls += stride, it++) {
         const int buf = (int)(it & 1u);
-        if (ls + stride < A.nslots) plan_slot(g, dsrc, T, isize_row, A, ls + stride, lane, st, buf ^ 1);
-        made += emit_slot(g, dsrc, T, &Q, A, ls, lane, &scratch[warp], st, buf, phases, size1, size2, out1, out2, flags);
+        if (ls < A.nslots) plan_slot<SIZE_ONLY, REPLAY>(g, dsrc, T, isize_row, A, ls, lane, st, buf);
+        if (it) made += emit_slot<SIZE_ONLY, REPLAY>(g, dsrc, T, &Q, A, ls - stride, lane, &scratch[warp], st, buf ^ 1, phases, size1, size2, out1, out2, flags);
     }
     if (lane == 0 && made) atomicAdd(records, (unsigned long long)made);
 }
@@ -725,29 +794,145 @@ int CallbackConsumer::finish() {
     return 0;
 }
 
-int yield_reads(scs_ctx* c, SlabConsumer& sink) {
+// sum of the record sizes of one batch, per file
+__global__ void __launch_bounds__(256) sum_sizes_kernel(const uint32_t* __restrict__ size1, const uint32_t* __restrict__ size2, uint64_t n,
+                                                        unsigned long long* __restrict__ totals) {
+    unsigned long long a = 0, b = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) { a += size1[i]; if (size2) b += size2[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { if (a) atomicAdd(totals, a); if (b) atomicAdd(totals + 1, b); }
+}
+
+namespace {
+// everything the slab loop needs: tables, the slot range, launch geometry, scratch, the coarse index and the slow-path numbering
+struct ReadRun {
+    ReadTables T; Genome g; DrawSrc dsrc; SlabArgs A;
+    uint64_t slot_lo = 0, slot_hi = 0, nslots = 0, slab = 0, stride = 0, batch = 0;
+    int nfiles = 1, sms = 148, emit_warps = kEmitWarps, isize_smem = 0; size_t emit_smem = 0;
+};
+}  // namespace
+
+static int prepare_read_run(scs_ctx* c, ReadRun& R) {
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
     if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
     const HostProfile& P = c->prof;
     if (P.readLength > kRLCap) return c->fail(SCS_E_UNSUPPORTED, "read length above 256 is not supported by the kernels");
     if (c->P.paired && !P.hasISize) return c->fail(SCS_E_ARG, "Error: unrecognized parameter name \"insertSize\"");   // Profile.cpp:1484 -> Config.cpp:71-78
-    c->stats.records = 0; c->stats.fastq_bytes[0] = c->stats.fastq_bytes[1] = 0;
-    c->stats.ms_reads = c->stats.ms_reads_kernels = c->stats.ms_emit_kernel = 0; c->stats.emit_launches = 0; c->stats.genome_window_bytes = 0;
     // what this rank reads from: its own amplicons and genome, or (balance = 1) the cell-wide copies and a slot range
     const bool gv = c->global_view;
-    const uint64_t slot_lo = gv ? c->g_slot_lo : 0, slot_hi = gv ? c->g_slot_hi : c->n_slots;
-    const uint64_t nslots = slot_hi - slot_lo;
-    const int nfiles = c->P.paired ? 2 : 1;
-    const uint64_t slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
-    const uint64_t stride = ((uint64_t)kRecCap + 15) & ~15ull;
-    if (slab < 64 * stride) return c->fail(SCS_E_ARG, "slab_bytes is too small (needs room for 64 records of the largest size, 53 KiB)");
-    if (nslots == 0) return sink.finish() ? c->fail(SCS_E_IO, "FASTQ sink failed") : SCS_OK;
+    R.slot_lo = gv ? c->g_slot_lo : 0; R.slot_hi = gv ? c->g_slot_hi : c->n_slots; R.nslots = R.slot_hi - R.slot_lo;
+    R.nfiles = c->P.paired ? 2 : 1;
+    R.slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
+    R.stride = ((uint64_t)kRecCap + 15) & ~15ull;
+    if (R.slab < 64 * R.stride) return c->fail(SCS_E_ARG, "slab_bytes is too small (needs room for 64 records of the largest size, 53 KiB)");
+    if (R.nslots == 0) return SCS_OK;
     // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4. A batch whose records are longer than
     // that on average (heavy insertion profiles) can exceed the slab: the compaction kernel then skips the records that do not
     // fit, and the run ends with SCS_E_NOMEM ("raise slab_bytes") — nothing is ever written outside the slab.
     const uint64_t typical = 30 + 2ull * (P.readLength + 8) + 4;
-    const uint64_t batch = std::min<uint64_t>(std::max<uint64_t>(64, slab / typical), 2048ull * 2048ull);
-    const int R = std::max(2, sink.ring_slots());
+    R.batch = std::min<uint64_t>(std::max<uint64_t>(64, R.slab / typical), 2048ull * 2048ull);
+    R.T = make_tables(c); R.g = c->dev_genome(); R.dsrc = draw_src(c, D_READ);
+    SlabArgs& A = R.A;
+    A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
+    A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = R.slab;
+    A.fail_base = 0; A.stage_stride = R.stride; A.slot0 = 0; A.nslots = 0;
+    if (gv) {
+        R.g.words = c->g_words.p; R.g.nmask = c->g_nmask.p; R.g.n_bases = c->g_bases; R.g.has_n = c->g_has_n;
+        A.slot_gbase = c->g_slot_base.p; A.amp_gidx = nullptr; A.n_amp = c->g_n_amp; A.slot_base = c->g_slot_base.p;
+        A.desc = c->g_desc.p; A.errref = c->g_errref.p; A.err_pool = c->g_errs.p;
+    }
+    ReadScratch& W = c->rscratch;
+    SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));
+    SCS_CUDA(c, W.size1.reserve(R.batch + 1)); SCS_CUDA(c, W.size2.reserve(R.batch + 1));
+    SCS_CUDA(c, W.off1.reserve(R.batch + 1)); SCS_CUDA(c, W.off2.reserve(R.batch + 1)); SCS_CUDA(c, W.scan.reserve(2 * 2048 + 16));
+    // slab byte totals are written by the scan kernel straight into mapped pinned memory: a D2H memcpy on the compute
+    // stream would queue behind the previous slab's 0.5 GB copy on the same copy engine and stall the emit kernel
+    if (!W.htotals) {
+        SCS_CUDA(c, cudaHostAlloc((void**)&W.htotals, 64, cudaHostAllocMapped));
+        SCS_CUDA(c, cudaHostGetDevicePointer((void**)&W.dtotals_mapped, W.htotals, 0));
+    }
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sms, cudaDevAttrMultiProcessorCount, dev);
+    // shared memory of a persistent emit CTA: the diagonal quality tables, the insert-size thresholds, and per warp a scratch area
+    // plus the TMA staging of its next two slots; as many warps (<= 24) as fit
+    const size_t table_smem = (size_t)4 * R.T.RL * kDiagStride * 4 + (size_t)4 * R.T.RL * 16 + (size_t)((4 * R.T.RL + 3) & ~3) * 4;
+    int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    R.isize_smem = (c->P.paired && R.T.isizeEff <= kISizeSmemCap) ? R.T.isizeEff : 0;
+    const size_t fixed_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4, per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
+    R.emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(fixed_smem, (size_t)smem_max)) / per_warp);
+    if (R.emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
+    R.emit_smem = fixed_smem + per_warp * (size_t)R.emit_warps;
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.emit_smem));
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.emit_smem));
+    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.emit_smem));
+    // coarse slot -> amplicon index of this rank's slot range (one entry per 1024 slots): the per-slot search starts from it
+    const uint64_t n_coarse = ((R.nslots - 1) >> kCoarseShift) + 2;
+    SCS_CUDA(c, W.coarse.reserve(n_coarse + 1));
+    coarse_index_kernel<<<(unsigned)((n_coarse + 255) / 256), 256, 0, c->st>>>(A.slot_base, A.n_amp, R.slot_lo, n_coarse, W.coarse.p); SCS_LAUNCHED(c);
+    A.coarse = W.coarse.p; A.coarse_base = R.slot_lo;
+    // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
+    if (c->P.paired && P.maxInsert > 1000) {
+        // the numbering of an amplicon's pairs depends on all of its earlier pairs: cover whole amplicons around the range
+        uint64_t a_first = 0, a_last = A.n_amp - 1, ext_lo = R.slot_lo, ext_hi = R.slot_hi;
+        if (gv) {
+            std::vector<uint64_t> hb(A.n_amp + 1);
+            SCS_CUDA(c, memcpy_sync(c, hb.data(), A.slot_base, (A.n_amp + 1) * 8, cudaMemcpyDeviceToHost));
+            a_first = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), R.slot_lo) - hb.begin()) - 1;
+            a_last = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), R.slot_hi - 1) - hb.begin()) - 1;
+            ext_lo = hb[a_first]; ext_hi = hb[a_last + 1];
+        }
+        const uint64_t ext_n = ext_hi - ext_lo;
+        SCS_CUDA(c, W.nfail.reserve(ext_n + 1)); SCS_CUDA(c, W.hdrno.reserve(ext_n + 1));
+        SlabArgs F = A; F.fail_base = ext_lo; F.nslots = ext_n;
+        fail_count_kernel<<<(unsigned)((ext_n + 255) / 256), 256, 0, c->st>>>(R.dsrc, R.T, F, W.nfail.p); SCS_LAUNCHED(c);
+        F.slot0 = a_first; F.nslots = a_last - a_first + 1;
+        fail_scan_kernel<<<(unsigned)((F.nslots + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
+        A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p; A.fail_base = ext_lo;
+    }
+    return SCS_OK;
+}
+
+// Exact FASTQ bytes this rank will write to each file: the sizing pass (indel draws only; bases are fetched only when the genome
+// holds N, because an N changes how many draws a base consumes). Used to give every rank its final offset in ONE output file.
+int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]) {
+    bytes[0] = bytes[1] = 0;
+    if (c->replay.on) return c->fail(SCS_E_UNSUPPORTED, "the sizing pass is not available in replay mode (replay runs on one rank)");
+    ReadRun R;
+    if (int rc = prepare_read_run(c, R)) return rc;
+    if (R.nslots == 0) return SCS_OK;
+    ReadScratch& W = c->rscratch;
+    StageGuard G(c);
+    SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.totals.p, 0, 16, c->st));
+    for (uint64_t s0 = R.slot_lo; s0 < R.slot_hi; s0 += R.batch) {
+        const uint64_t m = std::min(R.batch, R.slot_hi - s0);
+        R.A.slot0 = s0; R.A.nslots = m;
+        SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
+        if (R.nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
+        emit_kernel<true, false><<<R.sms, R.emit_warps * 32, R.emit_smem, c->st>>>(R.g, R.dsrc, R.T, R.A, nullptr, nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p, R.isize_smem);
+        SCS_LAUNCHED(c);
+        sum_sizes_kernel<<<R.sms, 256, 0, c->st>>>(W.size1.p, R.nfiles == 2 ? W.size2.p : nullptr, m, reinterpret_cast<unsigned long long*>(W.totals.p)); SCS_LAUNCHED(c);
+    }
+    uint64_t h[2] = {0, 0}; int hflags = 0;
+    SCS_CUDA(c, memcpy_sync(c, h, W.totals.p, 16, cudaMemcpyDeviceToHost));
+    SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
+    if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
+    if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
+    bytes[0] = h[0]; bytes[1] = h[1];
+    return SCS_OK;
+}
+
+int yield_reads(scs_ctx* c, SlabConsumer& sink) {
+    ReadRun R;
+    if (int rc = prepare_read_run(c, R)) return rc;
+    c->stats.records = 0; c->stats.fastq_bytes[0] = c->stats.fastq_bytes[1] = 0;
+    c->stats.ms_reads = c->stats.ms_reads_kernels = c->stats.ms_emit_kernel = 0; c->stats.emit_launches = 0; c->stats.genome_window_bytes = 0;
+    if (R.nslots == 0) return sink.finish() ? c->fail(SCS_E_IO, "FASTQ sink failed") : SCS_OK;
+    const int nfiles = R.nfiles, sms = R.sms, emit_warps = R.emit_warps, isize_smem = R.isize_smem;
+    const uint64_t slab = R.slab, stride = R.stride, batch = R.batch, slot_lo = R.slot_lo, slot_hi = R.slot_hi;
+    const size_t emit_smem = R.emit_smem;
+    ReadTables& T = R.T; Genome& g = R.g; DrawSrc& dsrc = R.dsrc; SlabArgs& A = R.A;
+    ReadScratch& W = c->rscratch;
+    const int Rn = std::max(2, sink.ring_slots());
     // device slabs (double buffered) + ring of pinned host slots; both keep their capacity between calls
     if (c->slab_cap != slab) {
         for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) c->slab_dev[b][f].release();
@@ -755,49 +940,12 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         c->slab_cap = slab;
     }
     for (int b = 0; b < 2; b++) for (int f = 0; f < nfiles; f++) if (!c->slab_dev[b][f].p) SCS_CUDA(c, c->slab_dev[b][f].reserve(slab + 64));
-    for (int f = 0; f < nfiles; f++) while ((int)c->ring_host[f].size() < R) {
+    for (int f = 0; f < nfiles; f++) while ((int)c->ring_host[f].size() < Rn) {
         char* q = nullptr;
         SCS_CUDA(c, cudaMallocHost((void**)&q, slab + 4096 + 64));   // + one block: file sinks place the slab at its file offset mod 4096
         c->ring_host[f].push_back(q);
     }
-    ReadTables T = make_tables(c);
-    Genome g = c->dev_genome();
-    DrawSrc dsrc = draw_src(c, D_READ);
-    SlabArgs A; A.slot_gbase = c->slot_gbase.p; A.amp_gidx = c->full_gidx.p; A.n_amp = c->fulls.n; A.slot_base = c->slot_base.p;
-    A.desc = c->fulls.desc.p; A.errref = c->fulls.errref.p; A.err_pool = c->err_pool.p; A.hdr_no = nullptr; A.nfail = nullptr; A.slab_cap = slab;
-    A.fail_base = 0; A.stage_stride = stride;
-    if (gv) {
-        g.words = c->g_words.p; g.nmask = c->g_nmask.p; g.n_bases = c->g_bases; g.has_n = c->g_has_n;
-        A.slot_gbase = c->g_slot_base.p; A.amp_gidx = nullptr; A.n_amp = c->g_n_amp; A.slot_base = c->g_slot_base.p;
-        A.desc = c->g_desc.p; A.errref = c->g_errref.p; A.err_pool = c->g_errs.p;
-    }
-    ReadScratch& W = c->rscratch;
-    SCS_CUDA(c, W.flags.reserve(1)); SCS_CUDA(c, W.records.reserve(1)); SCS_CUDA(c, W.totals.reserve(4));
-    SCS_CUDA(c, W.size1.reserve(batch + 1)); SCS_CUDA(c, W.size2.reserve(batch + 1));
-    SCS_CUDA(c, W.off1.reserve(batch + 1)); SCS_CUDA(c, W.off2.reserve(batch + 1)); SCS_CUDA(c, W.scan.reserve(2 * 2048 + 16));
     for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
-    // slab byte totals are written by the scan kernel straight into mapped pinned memory: a D2H memcpy on the compute
-    // stream would queue behind the previous slab's 0.5 GB copy on the same copy engine and stall the emit kernel
-    if (!W.htotals) {
-        SCS_CUDA(c, cudaHostAlloc((void**)&W.htotals, 64, cudaHostAllocMapped));
-        SCS_CUDA(c, cudaHostGetDevicePointer((void**)&W.dtotals_mapped, W.htotals, 0));
-    }
-    int dev = 0; cudaGetDevice(&dev); int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // shared memory of a persistent emit CTA: the diagonal quality tables + one scratch area per warp; as many warps (<= 24) as fit
-    const size_t table_smem = (size_t)4 * T.RL * kDiagStride * 4 + (size_t)4 * T.RL * 16 + (size_t)((4 * T.RL + 3) & ~3) * 4;
-    int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    const int isize_smem = (c->P.paired && T.isizeEff <= kISizeSmemCap) ? T.isizeEff : 0;
-    const size_t fixed_smem = table_smem + (size_t)((isize_smem + 3) & ~3) * 4, per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
-    const int emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(fixed_smem, (size_t)smem_max)) / per_warp);
-    if (emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
-    const size_t emit_smem = fixed_smem + per_warp * (size_t)emit_warps;
-    SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
-
-    // coarse slot -> amplicon index of this rank's slot range (one entry per 1024 slots): the per-slot search starts from it
-    const uint64_t n_coarse = ((nslots - 1) >> kCoarseShift) + 2;
-    SCS_CUDA(c, W.coarse.reserve(n_coarse + 1));
-    coarse_index_kernel<<<(unsigned)((n_coarse + 255) / 256), 256, 0, c->st>>>(A.slot_base, A.n_amp, slot_lo, n_coarse, W.coarse.p); SCS_LAUNCHED(c);
-    A.coarse = W.coarse.p; A.coarse_base = slot_lo;
 
     StageGuard G(c);   // from here on every return drains the streams and frees the events
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
@@ -807,7 +955,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         ecopy[b] = G.make(cudaEventDisableTiming); ekern[b] = G.make(cudaEventDisableTiming); etotb[b] = G.make(cudaEventDisableTiming);
         for (int q = 0; q < 4; q++) tq[b][q] = G.make(cudaEventDefault);
     }
-    std::vector<cudaEvent_t> eslot(R); for (int i = 0; i < R; i++) eslot[i] = G.make(cudaEventDisableTiming);
+    std::vector<cudaEvent_t> eslot(Rn); for (int i = 0; i < Rn; i++) eslot[i] = G.make(cudaEventDisableTiming);
     double msk = 0, mse = 0;
     auto harvest = [&](int b) {   // kernel times of the slab that used buffer b (its events are complete: a later event was waited for)
         if (!timed[b]) return;
@@ -816,25 +964,6 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         timed[b] = false;
     };
     SCS_CUDA(c, cudaEventRecord(e0, c->st));
-    // slow path: insert sizes that can fail (isize > amplicon length; amplicons are 1000..2000 long)
-    if (c->P.paired && P.maxInsert > 1000) {
-        // the numbering of an amplicon's pairs depends on all of its earlier pairs: cover whole amplicons around the range
-        uint64_t a_first = 0, a_last = A.n_amp - 1, ext_lo = slot_lo, ext_hi = slot_hi;
-        if (gv) {
-            std::vector<uint64_t> hb(A.n_amp + 1);
-            SCS_CUDA(c, memcpy_sync(c, hb.data(), A.slot_base, (A.n_amp + 1) * 8, cudaMemcpyDeviceToHost));
-            a_first = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), slot_lo) - hb.begin()) - 1;
-            a_last = (uint64_t)(std::upper_bound(hb.begin(), hb.end(), slot_hi - 1) - hb.begin()) - 1;
-            ext_lo = hb[a_first]; ext_hi = hb[a_last + 1];
-        }
-        const uint64_t ext_n = ext_hi - ext_lo;
-        SCS_CUDA(c, W.nfail.reserve(ext_n + 1)); SCS_CUDA(c, W.hdrno.reserve(ext_n + 1));
-        SlabArgs F = A; F.fail_base = ext_lo; F.nslots = ext_n;
-        fail_count_kernel<<<(unsigned)((ext_n + 255) / 256), 256, 0, c->st>>>(dsrc, T, F, W.nfail.p); SCS_LAUNCHED(c);
-        F.slot0 = a_first; F.nslots = a_last - a_first + 1;
-        fail_scan_kernel<<<(unsigned)((F.nslots + 255) / 256), 256, 0, c->st>>>(F, W.nfail.p, W.hdrno.p); SCS_LAUNCHED(c);
-        A.hdr_no = W.hdrno.p; A.nfail = W.nfail.p; A.fail_base = ext_lo;
-    }
     // ---- per slab: emit (staging + sizes) -> scans -> compaction into the packed device slab -> D2H into a pinned ring slot.
     // Software-pipelined on the host: slab k is launched before the host waits for the byte totals of slab k-1, so the kernels
     // run back to back; the consumer is serviced in between.
@@ -845,7 +974,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         dv[b].launched = false;
         const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};
         if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
-        const int slot = (int)(dv[b].k % (uint64_t)R);
+        const int slot = (int)(dv[b].k % (uint64_t)Rn);
         if (sink.acquire(slot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
         SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
         char* p[2] = {nullptr, nullptr};
@@ -869,8 +998,9 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
         if (nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
         SCS_CUDA(c, cudaEventRecord(tq[b][1], c->st));
-        emit_kernel<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p,
-                                                                W.records.p, isize_smem);
+        auto kern = c->replay.on ? emit_kernel<false, true> : emit_kernel<false, false>;
+        kern<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p,
+                                                         isize_smem);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
         if (int rc = scan_u32_noalloc(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;
@@ -912,7 +1042,7 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     const int r = blockIdx.x * kReadWarps + warp;
     if (r >= n_reads) return;
     WarpScratch* ws = &scratch[warp];
-    Stream S; S.k0 = S.k1 = S.e0 = S.e1 = S.dom2 = 0; S.t[0] = real + (uint64_t)r * stride_real; S.t[1] = ints + (uint64_t)r * stride_int;
+    RStream<true> S; S.k0 = S.k1 = S.e0 = S.e1 = S.dom2 = 0; S.t[0] = real + (uint64_t)r * stride_real; S.t[1] = ints + (uint64_t)r * stride_int;
     const int RL = T.RL;
     for (int i = lane; i < RL; i += 32) {
         char ch = srcAscii[(size_t)r * RL + i];
@@ -929,8 +1059,9 @@ __global__ void __launch_bounds__(kReadWarps * 32) test_predict_kernel(ReadTable
     if (np > kSrcCap || np > out_stride) { if (lane == 0) out_len[r] = -1; return; }
     __syncwarp();
     const uint8_t* src = build_source(S, np, nev, lane, ws);
-    if (hasN) subst_quality_pass_n<true>(S, T, nullptr, src, np, isRead1, cr, ci, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
-    else subst_quality_pass(S, T, nullptr, src, np, isRead1, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
+    const PassTabs X = make_pass_tabs(T, nullptr, isRead1);
+    if (hasN) (void)subst_quality_pass_n<true>(S, X, src, np, cr, ci, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
+    else subst_quality_pass(S, X, src, np, cr, lane, out_seq + (size_t)r * out_stride, out_qual + (size_t)r * out_stride);
     if (lane == 0) out_len[r] = np;
 }
 

@@ -182,3 +182,28 @@ def test_slab_limits_are_clean_errors(tmp_path):
     heavy = with_insert_rate(0.06, "heavy.profile")   # ~7.5 insertions per read
     # same profile with a roomy slab: equals the oracle (reads with many indel events)
     _run_case(str(tmp_path), "heavy", 1, 300_000, 5, heavy, "PE", 2e-10, 8.0, 260, seed=3, slab_bytes=8 << 20)
+
+
+@pytest.mark.parametrize("layout,direct", [("PE", True), ("PE", False), ("SE", True)])
+def test_file_sink_equals_the_oracle(tmp_path, layout, direct, monkeypatch):
+    """scs_yield_reads(prefix): the asynchronous file sink (ring of pinned slabs, writer threads, O_DIRECT with carried partial
+    blocks or plain buffered writes) must leave exactly the oracle's files; 1 MiB slabs, so dozens of slabs per file."""
+    from scssim_b200 import api
+    if not direct:
+        monkeypatch.setenv("SCS_NO_ODIRECT", "1")
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome(fa, 1, 500_000, 23)
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, layout, 2e-10, 30.0, 260)
+    H.run_oracle(fa, os.path.join(tmp, "orc"), args, seed=77)
+    with api.GenReads(gamma=2e-10, coverage=30.0, layout=layout, seed=77, slab_bytes=1 << 20, ring_slabs=3, io_threads=3) as g:
+        g.load_profile(prof).load_genome(fa).create_frags().amplify()
+        want = g.plan_fastq_bytes()
+        g.yield_reads(os.path.join(tmp, "gpu"))
+        st = g.stats()
+        g.yield_reads(os.path.join(tmp, "gpu"))          # a second run into the same files (truncate + rewrite)
+    assert st["emit_launches"] >= 10
+    for i, (a, b) in enumerate(zip(H.fastq_names(os.path.join(tmp, "gpu"), layout), H.fastq_names(os.path.join(tmp, "orc"), layout))):
+        assert H.read_bytes(a) == H.read_bytes(b)
+        assert want[i] == os.path.getsize(b)             # the sizing pass predicts the file size exactly

@@ -195,6 +195,43 @@ def test_parallel_file_writer_round_trip(tmp_path):
         api.write_file_parallel(os.path.join(str(tmp_path), "no_such_dir", "x"), b"abc", 16, 2)
 
 
+def test_async_file_sink_writes_exact_bytes(tmp_path):
+    """The asynchronous sink behind scs_yield_reads (file_sink.h): slabs of awkward sizes through a small ring, O_DIRECT where the
+    file system grants it (whole blocks direct, < 4 KiB carried from slab to slab, the last partial block buffered) and plain
+    buffered writes; preallocation larger and smaller than the data; the file must hold exactly the bytes fed."""
+    rng = np.random.default_rng(11)
+    data = rng.integers(0, 256, size=3_000_017, dtype=np.uint8).tobytes()
+    modes = set()
+    for direct in (True, False):
+        for slab, ring, threads, prealloc in [(4096, 2, 1, 0), (5000, 3, 4, 10_000_000), (65_537, 4, 3, 1000), (1 << 20, 2, 8, len(data)), (len(data) + 5, 2, 2, 0)]:
+            p = os.path.join(str(tmp_path), f"a{int(direct)}_{slab}.bin")
+            used = api.write_file_async(p, data, slab, threads=threads, ring=ring, prealloc=prealloc, direct=direct)
+            modes.add(used)
+            got = open(p, "rb").read()
+            if prealloc > len(data):
+                assert len(got) == prealloc and got[len(data):] == bytes(prealloc - len(data))   # the test hook does not own the end
+                got = got[:len(data)]
+            assert got == data, (direct, slab, ring, threads)
+    assert False in modes
+    with pytest.raises(api.ScsError):
+        api.write_file_async(os.path.join(str(tmp_path), "no_such_dir", "x"), b"abc", 16)
+
+
+def test_async_file_sink_ranks_share_one_file(tmp_path):
+    """Several ranks write disjoint regions of ONE file at unaligned offsets (scs_yield_reads with world > 1): the first rank creates
+    and preallocates it, the others open it; a block shared by two regions is written through the page cache by both."""
+    rng = np.random.default_rng(12)
+    parts = [rng.integers(0, 256, size=n, dtype=np.uint8).tobytes() for n in (1_234_567, 5, 70_001, 4096, 900_000)]
+    total = sum(len(x) for x in parts)
+    for direct in (True, False):
+        p = os.path.join(str(tmp_path), f"shared{int(direct)}.bin")
+        api.write_file_async(p, b"", 4096, create=True, prealloc=total, direct=direct)
+        off = [sum(len(x) for x in parts[:i]) for i in range(len(parts))]
+        for i in (3, 0, 4, 2, 1):   # any order
+            api.write_file_async(p, parts[i], 50_000, threads=2, ring=3, base=off[i], create=False, direct=direct)
+        assert open(p, "rb").read() == b"".join(parts)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver times beside ours): one JSON line with the contract's keys, produced by
     the compiled reference when it exists, else by the CPU oracle — on a tiny debug genome here."""
