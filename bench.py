@@ -372,10 +372,14 @@ def main():
                          slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance))
         weight = d2h_per_rank[rank]
         if world > 1:
-            from scssim_b200.dist import make_collectives, make_device_allreduce
+            # the library's own NCCL communicator (scs_nccl_init): rank 0's id reaches the other ranks through the process group that
+            # torchrun set up; from here on no collective of the hot path goes through Python
+            idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(api.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, src=0)
+            g.nccl_init(bytes(idt.cpu().numpy().tobytes()))
             g.set_shard_weight(weight)
-            g.set_collectives(*make_collectives(dist, device=dev))
-            g.set_device_collective(*make_device_allreduce(dist, dev))
         g.load_profile(profile)
         g.set_genome(named).create_frags()
 
@@ -523,8 +527,8 @@ def main():
             "detail": {"reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": gbps, "full_amplicons": n_fulls, "semi_amplicons": n_semis,
                        "stage_ms_per_step_rank0": {"amplify": amp_ms / a.steps, "alloc": alloc_ms / a.steps, "reads": reads_ms / a.steps},
                        "reads_stage_ms_max_rank": reads_ms_max / a.steps,
-                       "parallelism": (f"one cell over {world} GPUs: sequences sharded for the amplification, packed genome + amplicon table replicated "
-                                       f"over NCCL, read slots cut into {world} contiguous ranges") if world > 1 else "one GPU",
+                       "parallelism": (f"one cell over {world} GPUs: sequences sharded for the amplification, packed genome + amplicon table all-gathered "
+                                       f"over NCCL inside the library (v{api.lib().scs_nccl_version()}), read slots cut into {world} contiguous ranges") if world > 1 else "one GPU",
                        "device_map": devmap, "share_of_reads_per_rank": [round(s / max(reads_all, 1), 4) for s in shares],
                        "shard_weight_history": weights_hist[-3:]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": config["genome_bases"], "d2h_bytes_per_step": bytes_all, "steps": e2e_steps,

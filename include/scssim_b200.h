@@ -90,6 +90,17 @@ typedef int (*scs_allreduce_dev_f64_fn)(void* user, double* dev_buf, size_t n);
  * exactly one rank, so the sum is a gather). */
 typedef int (*scs_allreduce_dev_i64_fn)(void* user, int64_t* dev_buf, size_t n);
 int scs_set_device_collective(scs_ctx* ctx, scs_allreduce_dev_f64_fn fn_f64, scs_allreduce_dev_i64_fn fn_i64, void* user);
+/* NCCL inside the library (replaces the hooks above): rank 0 obtains an id, hands the 128 bytes to the other ranks by any means
+ * (shared memory between the CLI's worker threads, a broadcast in bench.py), and every rank calls scs_nccl_init — collectively,
+ * like ncclCommInitRank. From then on all collectives of the context run on that communicator over NVLink: ncclAllReduce for
+ * the per-pass counters and the cell-wide weight vector, ncclAllGather for the replication of the packed genome and the
+ * amplicon table (balance = 1). libnccl.so.2 is resolved at run time; a copy already loaded into the process is reused.
+ * scs_nccl_abort may be called from another thread to release a rank that waits in a collective for a peer that failed. */
+#define SCS_NCCL_ID_BYTES 128
+int scs_nccl_unique_id(char* id_out);
+int scs_nccl_init(scs_ctx* ctx, const char* id);
+int scs_nccl_abort(scs_ctx* ctx);
+int scs_nccl_version(void);   /* 0 when NCCL cannot be loaded */
 /* Relative share of the cell's reads this rank should write when balance = 1 (e.g. its measured D2H rate). Default 1. */
 int scs_set_shard_weight(scs_ctx* ctx, double weight);
 

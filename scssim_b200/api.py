@@ -86,7 +86,7 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_load_genome", "scs_set_genome", "scs_set_collectives", "scs_set_device_collective", "scs_set_shard_weight", "scs_create_frags", "scs_amplify",
            "scs_yield_reads_sink", "scs_yield_reads", "scs_plan_fastq_bytes", "scs_set_read_counts", "scs_get_stats", "scs_set_replay", "scs_dump",
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
-           "scs_version", "scs_device_count",
+           "scs_version", "scs_device_count", "scs_nccl_unique_id", "scs_nccl_init", "scs_nccl_abort", "scs_nccl_version",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
            "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer", "scs_test_async_writer"]
 
@@ -113,6 +113,9 @@ def lib():
         L.scs_set_collectives.argtypes = [C.c_void_p, AR_U64_FN, AR_F64_FN, C.c_void_p]
         L.scs_set_device_collective.argtypes = [C.c_void_p, AR_DEV_F64_FN, AR_DEV_I64_FN, C.c_void_p]
         L.scs_set_shard_weight.argtypes = [C.c_void_p, C.c_double]
+        L.scs_nccl_unique_id.argtypes = [C.c_char_p]
+        L.scs_nccl_init.argtypes = [C.c_void_p, C.c_char_p]
+        L.scs_nccl_abort.argtypes = [C.c_void_p]
         for f in ("scs_create_frags", "scs_amplify", "scs_set_read_counts"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.scs_yield_reads_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
@@ -154,6 +157,14 @@ def lib():
                                             C.POINTER(C.c_int)]
         _lib = L
     return _lib
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().scs_nccl_unique_id(buf)
+    if rc != SCS_OK:
+        raise ScsError(rc, lib().scs_last_error(None).decode())
+    return buf.raw
 
 
 def shard_range(n: int, rank: int, world: int):
@@ -319,6 +330,13 @@ class GenReads:
             return 0
         self._cb_dev = (AR_DEV_F64_FN(fd), AR_DEV_I64_FN(fi))
         self._ck(lib().scs_set_device_collective(self._h, self._cb_dev[0], self._cb_dev[1], None))
+        return self
+
+    def nccl_init(self, unique_id: bytes):
+        """Collective: join the communicator named by `unique_id` (from nccl_unique_id() on rank 0); the library then runs all of its
+        collectives on NCCL itself and needs no hooks."""
+        assert len(unique_id) == 128
+        self._ck(lib().scs_nccl_init(self._h, unique_id))
         return self
 
     def set_shard_weight(self, w: float):

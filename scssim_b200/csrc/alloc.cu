@@ -40,16 +40,16 @@ __global__ void __launch_bounds__(256) gather_counts_kernel(const double* __rest
     w[i] = wg[g]; counts[i] = v; slot_gbase[i] = sbase_g[g]; slots[i] = paired ? (v >> 1) : v;
 }
 
-// balance = 1: this rank's amplicons scattered into the cell-wide table, rebased to the cell-wide genome / error pool
-__global__ void __launch_bounds__(256) scatter_amplicons_kernel(const uint64_t* __restrict__ desc, const uint64_t* __restrict__ errref,
-                                                                const uint64_t* __restrict__ gidx, uint64_t n, uint64_t base_bases, uint64_t err_base,
-                                                                uint64_t* __restrict__ gdesc, uint64_t* __restrict__ gerrref) {
+// balance = 1: one rank's block of the gathered (desc, errref, global index) triples scattered into the cell-wide table, rebased
+// to that rank's place in the cell-wide genome / error pool
+__global__ void __launch_bounds__(256) scatter_amplicons_kernel(const uint64_t* __restrict__ triples, uint64_t stride, uint64_t n, uint64_t base_bases,
+                                                                uint64_t err_base, uint64_t* __restrict__ gdesc, uint64_t* __restrict__ gerrref) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t g = gidx[i];
-    Tmpl t = unpack_desc(desc[i]);
+    const uint64_t g = triples[2 * stride + i];
+    Tmpl t = unpack_desc(triples[i]);
     gdesc[g] = pack_desc(t.gstart + base_bases, t.rc, t.len);
-    const uint64_t er = errref[i];
+    const uint64_t er = triples[stride + i];
     gerrref[g] = (er & 0xFFFFull) ? ((((er >> 16) + err_base) << 16) | (er & 0xFFFFull)) : 0ull;
 }
 
@@ -186,15 +186,7 @@ int set_read_counts(scs_ctx* c) {
         wg = wg_buf.p; cg = cg_buf.p;
         SCS_CUDA(c, cudaMemsetAsync(wg, 0, N * 8, c->st));
         if (n) { scatter_f64_kernel<<<nbl, 256, 0, c->st>>>(c->weights.p, c->full_gidx.p, n, wg); SCS_LAUNCHED(c); }
-        if (c->ar_dev_f64) {   // NCCL on the device buffer
-            SCS_CUDA(c, cudaStreamSynchronize(c->st));
-            if (c->ar_dev_f64(c->ar_dev_user, wg, N)) return c->fail(SCS_E_STATE, "device allreduce callback failed");
-        } else {
-            std::vector<double> hw(N);
-            SCS_CUDA(c, memcpy_sync(c, hw.data(), wg, N * 8, cudaMemcpyDeviceToHost));
-            if (int rc = allreduce_f64(c, hw.data(), N)) return rc;
-            SCS_CUDA(c, memcpy_sync(c, wg, hw.data(), N * 8, cudaMemcpyHostToDevice));
-        }
+        if (int rc = allreduce_dev_f64(c, wg, N)) return rc;   // NCCL over NVLink (or the caller's hook)
     }
     const uint64_t nch = (N + kChunk - 1) / kChunk;
     DevBuf<double> dsums; SCS_CUDA(c, dsums.reserve(nch + 1));
@@ -262,40 +254,54 @@ int set_read_counts(scs_ctx* c) {
     SCS_CUDA(c, cudaMemcpyAsync(c->slot_base.p + n, &c->n_slots, 8, cudaMemcpyHostToDevice, c->st));
     c->global_view = false;
     if (multi && c->P.balance) {
-        // ---- replicate genome + amplicon table over the ranks and cut the cell's slots by shard weight ----
+        // ---- replicate genome + amplicon table over the ranks (all-gathers over NVLink) and cut the cell's slots by shard weight.
+        // ---- Every rank's block sits at rank * stride of the cell-wide arrays (stride = the largest rank's size, padded), so the
+        // ---- gathers are in place and need no displacements.
         const int W = c->P.world, R = c->P.rank;
         unsigned long long etop = 0;
         SCS_CUDA(c, memcpy_sync(c, &etop, c->err_top.p, 8, cudaMemcpyDeviceToHost));
-        const uint64_t my_words = c->genome_bases / 32, my_errs = (etop + 1) & ~1ull;   // error sections padded to 8 bytes
-        std::vector<uint64_t> v(3 * (size_t)W, 0);
-        v[R] = my_words; v[W + R] = my_errs; v[2 * W + R] = (uint64_t)c->genome_has_n;
+        std::vector<uint64_t> v(5 * (size_t)W, 0);
+        v[R] = c->genome_bases / 32; v[W + R] = etop; v[2 * W + R] = (uint64_t)c->genome_has_n; v[3 * W + R] = n; v[4 * W + R] = c->genome_version;
         if (int rc = allreduce_u64(c, v.data(), v.size())) return rc;
-        uint64_t word_base = 0, err_base = 0, tot_words = 0, tot_errs = 0; int any_n = 0;
-        for (int r = 0; r < W; r++) { if (r < R) { word_base += v[r]; err_base += v[W + r]; } tot_words += v[r]; tot_errs += v[W + r]; any_n |= (int)v[2 * W + r]; }
-        const uint64_t mask_words = (tot_words + 1) & ~1ull;
-        SCS_CUDA(c, c->g_words.reserve(tot_words + 2)); SCS_CUDA(c, c->g_nmask.reserve(mask_words + 2));
-        SCS_CUDA(c, c->g_desc.reserve(N + 1)); SCS_CUDA(c, c->g_errref.reserve(N + 1)); SCS_CUDA(c, c->g_errs.reserve(tot_errs + 2));
-        SCS_CUDA(c, c->g_slot_base.reserve(N + 2));
-        SCS_CUDA(c, cudaMemsetAsync(c->g_words.p, 0, tot_words * 8, c->st));
-        if (my_words) SCS_CUDA(c, cudaMemcpyAsync(c->g_words.p + word_base, c->genome_words.p, my_words * 8, cudaMemcpyDeviceToDevice, c->st));
-        if (int rc = allreduce_dev_i64(c, c->g_words.p, tot_words)) return rc;
-        if (any_n) {
-            SCS_CUDA(c, cudaMemsetAsync(c->g_nmask.p, 0, mask_words * 4, c->st));
-            if (my_words) {
-                if (c->genome_has_n) SCS_CUDA(c, cudaMemcpyAsync(c->g_nmask.p + word_base, c->genome_nmask.p, my_words * 4, cudaMemcpyDeviceToDevice, c->st));
-            }
-            if (int rc = allreduce_dev_i64(c, c->g_nmask.p, mask_words / 2)) return rc;
+        uint64_t word_stride = 0, err_stride = 0, amp_stride = 0, version_sum = 0; int any_n = 0;
+        for (int r = 0; r < W; r++) {
+            word_stride = std::max(word_stride, v[r]); err_stride = std::max(err_stride, v[W + r]); amp_stride = std::max(amp_stride, v[3 * W + r]);
+            any_n |= (int)v[2 * W + r]; version_sum += v[4 * W + r] * (uint64_t)(r + 1);
         }
-        SCS_CUDA(c, cudaMemsetAsync(c->g_errs.p, 0, (tot_errs + 2) * 4, c->st));
-        if (etop) SCS_CUDA(c, cudaMemcpyAsync(c->g_errs.p + err_base, c->err_pool.p, etop * 4, cudaMemcpyDeviceToDevice, c->st));
-        if (int rc = allreduce_dev_i64(c, c->g_errs.p, tot_errs / 2)) return rc;
-        SCS_CUDA(c, cudaMemsetAsync(c->g_desc.p, 0, N * 8, c->st)); SCS_CUDA(c, cudaMemsetAsync(c->g_errref.p, 0, N * 8, c->st));
+        word_stride = (word_stride + 3) & ~3ull;   // 32-byte blocks: genome words (8 B) and mask words (4 B) both stay 16-byte aligned per rank
+        err_stride = (err_stride + 1) & ~1ull; amp_stride = std::max<uint64_t>(amp_stride, 1);
+        const uint64_t tot_words = word_stride * (uint64_t)W, tot_errs = err_stride * (uint64_t)W;
+        SCS_CUDA(c, c->g_words.reserve(tot_words + 16)); SCS_CUDA(c, c->g_nmask.reserve(tot_words + 16));
+        SCS_CUDA(c, c->g_desc.reserve(N + 1)); SCS_CUDA(c, c->g_errref.reserve(N + 1)); SCS_CUDA(c, c->g_errs.reserve(tot_errs + 2));
+        SCS_CUDA(c, c->g_slot_base.reserve(N + 2)); SCS_CUDA(c, c->g_gather.reserve(3 * amp_stride * (uint64_t)W + 8));
+        // the packed genome (and its N mask) only when some rank loaded a new one since the last replication
+        if (c->g_genome_version != version_sum || c->g_genome_stride != word_stride) {
+            if (v[R]) SCS_CUDA(c, cudaMemcpyAsync(c->g_words.p + (uint64_t)R * word_stride, c->genome_words.p, v[R] * 8, cudaMemcpyDeviceToDevice, c->st));
+            if (int rc = allgather_dev(c, c->g_words.p, word_stride, 8)) return rc;
+            if (any_n) {
+                if (c->genome_has_n && v[R]) SCS_CUDA(c, cudaMemcpyAsync(c->g_nmask.p + (uint64_t)R * word_stride, c->genome_nmask.p, v[R] * 4, cudaMemcpyDeviceToDevice, c->st));
+                else SCS_CUDA(c, cudaMemsetAsync(c->g_nmask.p + (uint64_t)R * word_stride, 0, word_stride * 4, c->st));
+                if (int rc = allgather_dev(c, c->g_nmask.p, word_stride, 4)) return rc;
+            }
+            c->g_genome_version = version_sum; c->g_genome_stride = word_stride;
+        }
+        // error lists and amplicon triples change with every amplification
+        if (etop) SCS_CUDA(c, cudaMemcpyAsync(c->g_errs.p + (uint64_t)R * err_stride, c->err_pool.p, etop * 4, cudaMemcpyDeviceToDevice, c->st));
+        if (int rc = allgather_dev(c, c->g_errs.p, err_stride, 4)) return rc;
+        uint64_t* mine = c->g_gather.p + 3 * amp_stride * (uint64_t)R;
         if (n) {
-            scatter_amplicons_kernel<<<nbl, 256, 0, c->st>>>(c->fulls.desc.p, c->fulls.errref.p, c->full_gidx.p, n, word_base * 32, err_base, c->g_desc.p, c->g_errref.p);
+            SCS_CUDA(c, cudaMemcpyAsync(mine, c->fulls.desc.p, n * 8, cudaMemcpyDeviceToDevice, c->st));
+            SCS_CUDA(c, cudaMemcpyAsync(mine + amp_stride, c->fulls.errref.p, n * 8, cudaMemcpyDeviceToDevice, c->st));
+            SCS_CUDA(c, cudaMemcpyAsync(mine + 2 * amp_stride, c->full_gidx.p, n * 8, cudaMemcpyDeviceToDevice, c->st));
+        }
+        if (int rc = allgather_dev(c, c->g_gather.p, 3 * amp_stride, 8)) return rc;
+        for (int r = 0; r < W; r++) {
+            const uint64_t nr = v[3 * W + r];
+            if (!nr) continue;
+            scatter_amplicons_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, c->st>>>(c->g_gather.p + 3 * amp_stride * (uint64_t)r, amp_stride, nr,
+                                                                                     (uint64_t)r * word_stride * 32, (uint64_t)r * err_stride, c->g_desc.p, c->g_errref.p);
             SCS_LAUNCHED(c);
         }
-        if (int rc = allreduce_dev_i64(c, c->g_desc.p, N)) return rc;
-        if (int rc = allreduce_dev_i64(c, c->g_errref.p, N)) return rc;
         // cell-wide slot prefix (identical on every rank) and this rank's range by weight
         uint64_t total_slots = 0;
         { unsigned long long last_base = 0; uint32_t last_slots = 0;

@@ -61,6 +61,7 @@ void scs_destroy(scs_ctx* c) {
     if (dev) {
         cudaSetDevice(c->P.device); alloc_stream() = c->st;
         cudaDeviceSynchronize();
+        if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
         for (int f = 0; f < 2; f++) for (char* q : c->ring_host[f]) cudaFreeHost(q);
         if (c->rscratch.htotals) cudaFreeHost(c->rscratch.htotals);
         for (int b = 0; b < 2; b++) if (c->sv_pinned[b]) cudaFreeHost(c->sv_pinned[b]);
@@ -108,6 +109,39 @@ int scs_set_device_collective(scs_ctx* c, scs_allreduce_dev_f64_fn fn_f64, scs_a
     c->ar_dev_f64 = fn_f64; c->ar_dev_i64 = fn_i64; c->ar_dev_user = user;
     return SCS_OK;
 }
+// ---- NCCL inside the library
+int scs_nccl_unique_id(char* id) {
+    if (!id) return SCS_E_ARG;
+    NcclApi& A = nccl_api();
+    if (!A.ok) { g_create_error = "NCCL is not available: " + A.why; return SCS_E_UNSUPPORTED; }
+    ncclUniqueId u;
+    if (A.GetUniqueId(&u) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return SCS_E_CUDA; }
+    memcpy(id, u.internal, SCS_NCCL_ID_BYTES);
+    return SCS_OK;
+}
+int scs_nccl_init(scs_ctx* c, const char* id) {
+    if (!c || !id) return SCS_E_ARG;
+    if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
+    if (c->P.world <= 1) return SCS_OK;
+    NcclApi& A = nccl_api();
+    if (!A.ok) return c->fail(SCS_E_UNSUPPORTED, "NCCL is not available: " + A.why);
+    cudaSetDevice(c->P.device); alloc_stream() = c->st;
+    if (c->comm) { A.CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId u; memcpy(u.internal, id, SCS_NCCL_ID_BYTES);
+    ncclResult_t r = A.CommInitRank(&c->comm, c->P.world, u, c->P.rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return c->fail(SCS_E_CUDA, std::string("ncclCommInitRank: ") + A.GetErrorString(r)); }
+    int n = 0; A.CommCount(c->comm, &n);
+    if (n != c->P.world) return c->fail(SCS_E_STATE, "NCCL communicator size differs from world");
+    return SCS_OK;
+}
+int scs_nccl_abort(scs_ctx* c) {   // may be called from another thread: releases a rank that waits in a collective for a failed peer
+    if (!c) return SCS_E_ARG;
+    ncclComm_t comm = c->comm;
+    if (comm) { c->comm = nullptr; nccl_api().CommAbort(comm); }
+    return SCS_OK;
+}
+int scs_nccl_version(void) { NcclApi& A = nccl_api(); int v = 0; if (A.ok) A.GetVersion(&v); return v; }
+
 int scs_set_shard_weight(scs_ctx* c, double w) {
     if (!c || !(w > 0)) return SCS_E_ARG;
     c->shard_weight = w; c->have_counts = false;

@@ -140,8 +140,8 @@ static void usage_genReads(const char* app) {
          << "    scssim " << app << " -i /path/to/ref.fa -m /path/to/hiseq2500.profile -t 5 -o /path/to/reads" << endl << endl;
 }
 
-// --gpus N: one host thread per GPU in this process; the library's collectives (a few words per amplification pass, once
-// the weight vector) are plain sums through shared memory behind a barrier. (bench.py runs one process per GPU with NCCL.)
+// --gpus N: one host thread per GPU in this process, collectives over NCCL inside the library (scs_nccl_init). ThreadSum is the
+// stand-in for the single-GPU test hook only (SCS_CLI_SAME_DEVICE=1): plain sums through shared memory behind a barrier.
 struct ThreadSum {
     int world; std::mutex mu; std::condition_variable cv; int arrived = 0; long gen = 0; bool aborted = false;
     std::vector<uint64_t> au; std::vector<double> ad;
@@ -242,30 +242,51 @@ int main(int argc, char* argv[]) {
             cerr << "Error: --gpus " << gpus << " from device " << P.device << " needs " << P.device + gpus << " CUDA devices, found " << scs_device_count() << endl;
             return 1;
         }
+        // Collectives: NCCL inside the library, one communicator per worker (NVLink / NVSwitch). The contexts are created first, so a
+        // GPU that cannot be opened is reported before anybody waits in ncclCommInitRank. SCS_CLI_SAME_DEVICE=1 (test hook: all
+        // workers on one GPU, which NCCL refuses) uses host sums between the worker threads instead.
+        const bool same_device = getenv("SCS_CLI_SAME_DEVICE") != nullptr;
         ThreadSum coll(gpus);
         std::vector<int> rcs(gpus, 0); std::vector<string> errs(gpus);
         std::vector<uint64_t> reads(gpus, 0);
+        std::vector<scs_ctx*> ctxs(gpus, nullptr);
+        char nccl_id[SCS_NCCL_ID_BYTES];
+        if (!same_device && scs_nccl_unique_id(nccl_id)) { cerr << scs_last_error(nullptr) << endl; return 1; }
+        for (int r = 0; r < gpus; r++) {
+            scs_params Q = P; Q.rank = r; Q.world = gpus; Q.balance = 1;   // contiguous slot ranges; the shards are consecutive regions of the output files
+            Q.device = same_device ? P.device : P.device + r;
+            if (int rc = scs_create(&Q, &ctxs[r])) {
+                cerr << scs_last_error(nullptr) << endl;
+                for (scs_ctx* c : ctxs) if (c) scs_destroy(c);
+                return rc == SCS_E_IO ? -1 : 1;
+            }
+        }
         cerr << "\nReference sequence and profile are loaded by " << gpus << " GPU workers" << endl << "\nMALBAC amplification..." << endl;
+        std::mutex abort_mu;
+        auto abort_all = [&](int self) {   // a failed worker releases everybody who waits for it in a collective
+            std::lock_guard<std::mutex> lk(abort_mu);
+            coll.abort();
+            if (!same_device) for (int r = 0; r < gpus; r++) if (r != self) scs_nccl_abort(ctxs[r]);
+        };
         auto worker = [&](int r) {
-            scs_params Q = P; Q.rank = r; Q.world = gpus; Q.balance = 1;   // equal slot ranges; the shards are consecutive regions of the output files
-            Q.device = getenv("SCS_CLI_SAME_DEVICE") ? P.device : P.device + r;   // test hook: all workers on one GPU
-            scs_ctx* c = nullptr;
-            int rc = scs_create(&Q, &c);
-            if (rc) { errs[r] = scs_last_error(nullptr); rcs[r] = rc; coll.abort(); return; }
-            scs_set_collectives(c, sum_u64, sum_f64, &coll);
-            if ((rc = scs_load_genome(c, fa.c_str())) || (rc = scs_load_profile(c, modelFile.c_str())) || (rc = scs_create_frags(c)) ||
+            scs_ctx* c = ctxs[r];
+            int rc = 0;
+            if (same_device) scs_set_collectives(c, sum_u64, sum_f64, &coll);
+            else rc = scs_nccl_init(c, nccl_id);
+            if (rc || (rc = scs_load_genome(c, fa.c_str())) || (rc = scs_load_profile(c, modelFile.c_str())) || (rc = scs_create_frags(c)) ||
                 (rc = scs_amplify(c)) || (rc = scs_set_read_counts(c)) || (rc = scs_yield_reads(c, outputPrefix.c_str()))) {
-                errs[r] = scs_last_error(c); rcs[r] = rc; coll.abort();   // the other workers leave their collectives with an error
+                errs[r] = scs_last_error(c); rcs[r] = rc; abort_all(r);
             }
             scs_stats st; scs_get_stats(c, &st); reads[r] = st.reads_requested;
-            scs_destroy(c);
         };
         std::vector<std::thread> ts;
         for (int r = 0; r < gpus; r++) ts.emplace_back(worker, r);
         for (auto& t : ts) t.join();
+        for (scs_ctx* c : ctxs) scs_destroy(c);
         // report the worker that failed first-hand, not the ones that were released from a collective by its failure
         int bad = -1;
-        for (int r = 0; r < gpus; r++) if (rcs[r] && (bad < 0 || errs[bad].find("callback failed") != string::npos)) bad = r;
+        for (int r = 0; r < gpus; r++)
+            if (rcs[r] && (bad < 0 || errs[bad].find("callback failed") != string::npos || errs[bad].find("NCCL error") != string::npos)) bad = r;
         if (bad >= 0) { cerr << errs[bad] << endl; return rcs[bad] == SCS_E_IO ? -1 : 1; }
         // every worker wrote its shard at its final offset of the reference's file names (scs_yield_reads: sizing pass + exchange)
         cerr << "\nNumber of reads to generate: " << reads[0] << endl << "\n*****Producing reads*****" << endl;

@@ -13,6 +13,7 @@
 #include "device_common.cuh"
 #include "profile_host.h"
 #include "vmm.h"
+#include "nccl_shim.h"
 
 namespace scs {
 
@@ -199,10 +200,15 @@ struct scs_ctx {
     scs::ReplayDev replay;
     scs_allreduce_u64_fn ar_u64 = nullptr; scs_allreduce_f64_fn ar_f64 = nullptr; void* ar_user = nullptr;
     scs_allreduce_dev_f64_fn ar_dev_f64 = nullptr; scs_allreduce_dev_i64_fn ar_dev_i64 = nullptr; void* ar_dev_user = nullptr;
+    // NCCL communicator of this context (scs_nccl_init): when set, every collective of the library runs on it and the hooks are unused
+    ncclComm_t comm = nullptr; scs::DevBuf<uint64_t> coll_dev;
     double shard_weight = 1.0;
     // balance = 1: cell-wide copies (identical on every rank) that the read stage works from, and this rank's slot range
     scs::DevBuf<uint64_t> g_words, g_desc, g_errref, g_slot_base; scs::DevBuf<uint32_t> g_nmask, g_errs;
     bool global_view = false; uint64_t g_n_amp = 0, g_slot_lo = 0, g_slot_hi = 0, g_bases = 0; int g_has_n = 0;
+    scs::DevBuf<uint64_t> g_gather;     // all ranks' (desc, errref, global index) triples before they are scattered into g_desc / g_errref
+    uint64_t genome_version = 0;        // bumped by every genome load
+    uint64_t g_genome_version = ~0ull, g_genome_stride = 0;   // what the replicated genome was built from: skipped while unchanged
     scs_stats stats{};
     scs_simuvars_stats sv_stats{}; std::string sv_warnings;
 
@@ -285,6 +291,11 @@ int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n);
 int allreduce_f64(scs_ctx* c, double* v, size_t n);
 // in-place sum over ranks of n 64-bit words in device memory (NCCL hook if set, else staged through the host hook)
 int allreduce_dev_i64(scs_ctx* c, void* dev, size_t n);
+int allreduce_dev_f64(scs_ctx* c, double* dev, size_t n);
+// all-gather in device memory: every rank's `count` elements of `elem` bytes (count * elem a multiple of 8) already sit at
+// buf + rank * count * elem; on return every rank holds all W blocks. ncclAllGather over NVLink when the context has a
+// communicator, otherwise a sum of zero-padded copies through the caller's hooks.
+int allgather_dev(scs_ctx* c, void* buf, size_t count, size_t elem);
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
 // same for n <= 2048*2048 without allocation or synchronisation: scratch holds 2048+8 u64, the total is left in *total_dev
 int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev);

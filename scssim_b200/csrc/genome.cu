@@ -249,7 +249,7 @@ int genome_from_sources(scs_ctx* c, int n, const char* const* names, const SeqSr
     SCS_CUDA(c, memcpy_sync(c, &hbad, bad.p, 4, cudaMemcpyDeviceToHost));
     c->genome_has_n = hbad ? 1 : 0;
     c->stats.n_sequences = n; c->stats.genome_bases = 0; for (auto l : c->seq_len) c->stats.genome_bases += l;
-    c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
+    c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false; c->genome_version++;
     return SCS_OK;
 }
 
@@ -280,7 +280,7 @@ int genome_from_fasta(scs_ctx* c, const char* path) {
     if (np.empty()) {   // more ranks than sequences: this rank holds nothing but still takes part in the collectives
         c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear(); c->ref_len_sum = 0; c->ref_len_half = 0; c->genome_bases = 0;
         SCS_CUDA(c, c->genome_words.reserve(2)); SCS_CUDA(c, c->genome_nmask.reserve(2));
-        c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
+        c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false; c->genome_version++;
         return SCS_OK;
     }
     return genome_from_sources(c, (int)np.size(), np.data(), sp.data());
@@ -314,19 +314,39 @@ uint32_t host_draw(const scs_ctx* c, int domain, int engine, uint64_t entity, ui
     return o[i & 3];
 }
 
+// ---- collectives. With a communicator (scs_nccl_init) everything runs on NCCL: small host vectors are staged through a device
+// ---- scratch buffer (a few words per amplification pass), device vectors are reduced / gathered in place over NVLink.
+#define SCS_NCCL(ctx, call)                                                                                                        \
+    do {                                                                                                                           \
+        ncclResult_t r__ = (call);                                                                                                 \
+        if (r__ != ncclSuccess) return (ctx)->fail(SCS_E_CUDA, std::string("NCCL error: ") + nccl_api().GetErrorString(r__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+static int nccl_allreduce_host(scs_ctx* c, void* v, size_t n, ncclDataType_t t) {
+    SCS_CUDA(c, c->coll_dev.reserve(n + 8));
+    SCS_CUDA(c, cudaMemcpyAsync(c->coll_dev.p, v, n * 8, cudaMemcpyHostToDevice, c->st));
+    SCS_NCCL(c, nccl_api().AllReduce(c->coll_dev.p, c->coll_dev.p, n, t, ncclSum, c->comm, c->st));
+    SCS_CUDA(c, cudaMemcpyAsync(v, c->coll_dev.p, n * 8, cudaMemcpyDeviceToHost, c->st));
+    SCS_CUDA(c, cudaStreamSynchronize(c->st));
+    return SCS_OK;
+}
+
 int allreduce_u64(scs_ctx* c, uint64_t* v, size_t n) {
-    if (c->P.world <= 1) return SCS_OK;
-    if (!c->ar_u64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
+    if (c->P.world <= 1 || n == 0) return SCS_OK;
+    if (c->comm) return nccl_allreduce_host(c, v, n, ncclUint64);
+    if (!c->ar_u64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_nccl_init or scs_set_collectives)");
     return c->ar_u64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
 }
 int allreduce_f64(scs_ctx* c, double* v, size_t n) {
-    if (c->P.world <= 1) return SCS_OK;
-    if (!c->ar_f64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_set_collectives)");
+    if (c->P.world <= 1 || n == 0) return SCS_OK;
+    if (c->comm) return nccl_allreduce_host(c, v, n, ncclFloat64);
+    if (!c->ar_f64) return c->fail(SCS_E_STATE, "world > 1 but no collectives set (scs_nccl_init or scs_set_collectives)");
     return c->ar_f64(c->ar_user, v, n) ? c->fail(SCS_E_STATE, "allreduce callback failed") : SCS_OK;
 }
 
 int allreduce_dev_i64(scs_ctx* c, void* dev, size_t n) {
     if (c->P.world <= 1 || n == 0) return SCS_OK;
+    if (c->comm) { SCS_NCCL(c, nccl_api().AllReduce(dev, dev, n, ncclUint64, ncclSum, c->comm, c->st)); return SCS_OK; }
     if (c->ar_dev_i64) {
         SCS_CUDA(c, cudaStreamSynchronize(c->st));
         return c->ar_dev_i64(c->ar_dev_user, (int64_t*)dev, n) ? c->fail(SCS_E_STATE, "device allreduce callback failed") : SCS_OK;
@@ -336,6 +356,35 @@ int allreduce_dev_i64(scs_ctx* c, void* dev, size_t n) {
     if (int rc = allreduce_u64(c, h.data(), n)) return rc;
     SCS_CUDA(c, memcpy_sync(c, dev, h.data(), n * 8, cudaMemcpyHostToDevice));
     return SCS_OK;
+}
+int allreduce_dev_f64(scs_ctx* c, double* dev, size_t n) {
+    if (c->P.world <= 1 || n == 0) return SCS_OK;
+    if (c->comm) { SCS_NCCL(c, nccl_api().AllReduce(dev, dev, n, ncclFloat64, ncclSum, c->comm, c->st)); return SCS_OK; }
+    if (c->ar_dev_f64) {   // caller's hook on the device buffer
+        SCS_CUDA(c, cudaStreamSynchronize(c->st));
+        return c->ar_dev_f64(c->ar_dev_user, dev, n) ? c->fail(SCS_E_STATE, "device allreduce callback failed") : SCS_OK;
+    }
+    std::vector<double> h(n);
+    SCS_CUDA(c, memcpy_sync(c, h.data(), dev, n * 8, cudaMemcpyDeviceToHost));
+    if (int rc = allreduce_f64(c, h.data(), n)) return rc;
+    SCS_CUDA(c, memcpy_sync(c, dev, h.data(), n * 8, cudaMemcpyHostToDevice));
+    return SCS_OK;
+}
+
+int allgather_dev(scs_ctx* c, void* buf, size_t count, size_t elem) {
+    const int W = c->P.world, R = c->P.rank;
+    if (W <= 1 || count == 0) return SCS_OK;
+    const size_t block = count * elem;
+    if (block % 8) return c->fail(SCS_E_ARG, "allgather_dev: block size must be a multiple of 8 bytes");
+    char* base = static_cast<char*>(buf);
+    if (c->comm) {   // in place: this rank's block is already at its position
+        SCS_NCCL(c, nccl_api().AllGather(base + (size_t)R * block, base, block, ncclUint8, c->comm, c->st));
+        return SCS_OK;
+    }
+    // hooks: every other block zeroed, then a sum over ranks (each element is non-zero on at most one rank)
+    if (R > 0) SCS_CUDA(c, cudaMemsetAsync(base, 0, (size_t)R * block, c->st));
+    if (R + 1 < W) SCS_CUDA(c, cudaMemsetAsync(base + (size_t)(R + 1) * block, 0, (size_t)(W - 1 - R) * block, c->st));
+    return allreduce_dev_i64(c, buf, (size_t)W * block / 8);
 }
 
 int create_frags(scs_ctx* c) {   // Genome::splitToFrags, Genome.cpp:753-782

@@ -274,35 +274,34 @@ __device__ __forceinline__ void subst_quality_pass(const SX& S, const PassTabs& 
     const uint4* __restrict__ subs = X.subs;
     const int bins = X.bins;
     const int P = S.replay() ? 64 : (((cr & 3u) == 0) ? 64 : 62);   // the alignment of cr + 2*m0 does not change inside the pass
+    // bin = m * bins / np (Profile.cpp:1667): m itself for a read without indels, else by multiplication with ceil(2^32 / np)
+    // (exact: m * bins * np < 2^32)
+    const uint32_t inv = (np == bins) ? 0u : (uint32_t)((0x100000000ull + (uint32_t)np - 1u) / (uint32_t)np);
     for (int m0 = 0; m0 < np; m0 += P) {
-        uint4 th[2]; uint32_t b0[2]; int bin[2]; bool ok[2];
+        uint4 th[2]; uint32_t b0[2]; int bin[2];
+        const int mA = m0 + 2 * lane;
+        const bool okA = (2 * lane < P) && mA < np, okB = okA && mA + 1 < np;
+        // requests for the threshold rows of both positions first (addresses clamped for idle lanes: no predication around the loads)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int m = m0 + 2 * lane + h;
-            ok[h] = (2 * lane < P) && m < np;
-            b0[h] = 0; bin[h] = 0; th[h] = make_uint4(0, 0, 0, 0);
-            if (ok[h]) {
-                b0[h] = src[m];
-                uint32_t ki;
-                if (m == 0) ki = b0[h];
-                else if (m == 1) ki = 4u + 4u * src[0] + b0[h];
-                else ki = 20u + 16u * src[m - 2] + 4u * src[m - 1] + b0[h];
-                bin[h] = (np == bins) ? m : m * bins / np;
-                th[h] = __ldg(subs + ((size_t)ki * bins + bin[h]));
-            }
+            const int m = min(mA + h, np - 1);
+            b0[h] = src[m];
+            const uint32_t p1 = src[max(m - 1, 0)], p2 = src[max(m - 2, 0)];
+            const uint32_t ki = (m == 0) ? b0[h] : (m == 1) ? 4u + 4u * p1 + b0[h] : 20u + 16u * p2 + 4u * p1 + b0[h];
+            bin[h] = inv ? (int)__umulhi((uint32_t)(m * bins), inv) : m;
+            th[h] = __ldg(subs + ((size_t)ki * bins + bin[h]));
         }
         uint32_t x[4];
         warp_draws4(S, E_REAL, cr + 2u * m0, lane, x);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            if (ok[h]) {
-                const int m = m0 + 2 * lane + h;
-                const uint32_t xs = x[2 * h], xq = x[2 * h + 1];
-                // thresholds are non-decreasing and padded with 0xFFFFFFFF: the leading count, capped by the row's entry count
-                const uint32_t k = min((uint32_t)(th[h].x <= xs) + (uint32_t)(th[h].y <= xs) + (uint32_t)(th[h].z <= xs), th[h].w);
-                const int q = sample_quality(X, b0[h], k, bin[h], xq);
-                oseq[m] = (char)((0x54474341u >> (8u * k)) & 0xFFu);   // "ACGT"[k]
-                oqual[m] = (char)(33 + q);
+            const uint32_t xs = x[2 * h], xq = x[2 * h + 1];
+            // thresholds are non-decreasing and padded with 0xFFFFFFFF: the leading count, capped by the row's entry count
+            const uint32_t k = min((uint32_t)(th[h].x <= xs) + (uint32_t)(th[h].y <= xs) + (uint32_t)(th[h].z <= xs), th[h].w);
+            const int q = sample_quality(X, b0[h], k, bin[h], xq);
+            if (h == 0 ? okA : okB) {
+                oseq[mA + h] = (char)((0x54474341u >> (8u * k)) & 0xFFu);   // "ACGT"[k]
+                oqual[mA + h] = (char)(33 + q);
             }
         }
     }

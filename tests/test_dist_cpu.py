@@ -109,3 +109,40 @@ def test_sequence_sharding_more_ranks_than_sequences():
     got = [api.shard_sequences([100, 100], r, 5) for r in range(5)]
     owned = [g for g in got if g[1] > g[0]]
     assert sorted(owned) == [(0, 1), (1, 2)] and all(g == (0, 0) for g in got if g[1] == g[0])
+
+
+def _file_worker(rank, world, port, q, path):
+    """The host side of scs_yield_reads with world > 1, on CPU: exchange shard sizes (all-reduce of a zero-padded vector), rank 0
+    creates and preallocates the file, a second all-reduce is the barrier, every rank writes its shard at its offset through the
+    asynchronous sink."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from scssim_b200 import api
+    from scssim_b200.dist import make_collectives
+    ar_u64, _ = make_collectives(dist, device="cpu")
+    rng = np.random.default_rng(100 + rank)
+    mine = rng.integers(0, 256, size=[700_001, 13, 1_250_000][rank], dtype=np.uint8).tobytes()
+    v = np.zeros(world, dtype=np.uint64); v[rank] = len(mine)
+    ar_u64(v)
+    off, total = int(v[:rank].sum()), int(v.sum())
+    if rank == 0:
+        api.write_file_async(path, mine, 64_000, base=0, create=True, prealloc=total)
+    b = np.zeros(1, dtype=np.uint64); ar_u64(b)      # the file exists before the others open it
+    if rank != 0:
+        api.write_file_async(path, mine, 64_000, base=off, create=False)
+    b = np.zeros(1, dtype=np.uint64); ar_u64(b)
+    q.put((rank, mine))
+    dist.destroy_process_group()
+
+
+def test_ranks_write_one_file_at_exchanged_offsets(tmp_path):
+    world, port = 3, _free_port()
+    path = os.path.join(str(tmp_path), "shared.fq")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_file_worker, args=(r, world, port, q, path)) for r in range(world)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert all(p.exitcode == 0 for p in ps)
+    assert open(path, "rb").read() == b"".join(m for _, m in res)
