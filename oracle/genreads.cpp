@@ -161,17 +161,35 @@ void Sim::amplify_template(GetBase tb, uint32_t length, int primerNum, bool from
         for (uint32_t j = 0; j < alen; j++) { char c = tb(spos + j); if (c == 'G' || c == 'C') gcNum++; else if (c == 'N') anyN = true; }
         if (anyN) gcNum = 0;
         uint32_t eoff = (uint32_t)errs.size(), en = 0;
-        for (uint32_t j = 8; j < alen; j++) {
-            double p = uni_real(D->next(E_REAL), 0, 1);
-            if (p < P.ber) {
-                char base = tb(spos + j); unsigned n;
-                do {
-                    n = fromFragment ? (unsigned)uni_int(D->next(E_INT), 0, 4)        /* Fragment.cpp:110 */
-                                     : (unsigned)uni_real(D->next(E_REAL), 0, 4);    /* Amplicon.cpp:213 */
-                } while (BASES[n] == base);
-                if (BASES[n] == 'C' || BASES[n] == 'G') gcNum++;
-                if (base == 'C' || base == 'G') gcNum--;
-                errs.push_back({j, (uint8_t)n}); en++;
+        auto substitute = [&](uint32_t j) {   /* Fragment.cpp:108-122 / Amplicon.cpp:211-225 */
+            char base = tb(spos + j); unsigned n;
+            do {
+                n = fromFragment ? (unsigned)uni_int(D->next(E_INT), 0, 4)        /* Fragment.cpp:110 */
+                                 : (unsigned)uni_real(D->next(E_REAL), 0, 4);    /* Amplicon.cpp:213 */
+            } while (BASES[n] == base);
+            if (BASES[n] == 'C' || BASES[n] == 'G') gcNum++;
+            if (base == 'C' || base == 'G') gcNum--;
+            errs.push_back({j, (uint8_t)n}); en++;
+        };
+        if (D->is_tape()) {
+            /* the reference's own loop: one draw per base, j = 8 .. alen-1 (Fragment.cpp:105-107) */
+            for (uint32_t j = 8; j < alen; j++) {
+                double p = uni_real(D->next(E_REAL), 0, 1);
+                if (p < P.ber) substitute(j);
+            }
+        } else {
+            /* free-running streams: the distance to the next error is drawn directly, P(gap = g) = (1-ber)^g * ber — the same
+             * distribution as one Bernoulli(ber) draw per base, at one draw per error instead of one per base. The CUDA path
+             * (amplify.cu) defines its Philox streams the same way; det_log keeps host and device bit-identical. */
+            const double l1p = det_log(1.0 - P.ber);
+            uint64_t j = 7;
+            for (;;) {
+                double u = ((double)D->next(E_REAL) + 0.5) / 4294967296.0;
+                double g = floor(det_log(u) / l1p);
+                if (!(g < (double)alen)) break;
+                j += 1 + (uint64_t)g;
+                if (j >= alen) break;
+                substitute((uint32_t)j);
             }
         }
         out.push_back({tmplIdx, spos, alen, (uint32_t)std::max(0, gcNum), 0, eoff, en});

@@ -30,6 +30,7 @@ constexpr int kFragBitmapWords = (100000 + 32) / 32 + 1;   // fragments are <= 1
 
 struct AmpParams {
     uint32_t thr_ber;        // error iff x < thr_ber   (p < ber, ber = 3.4e-4, Config.cpp:46)
+    double log1m_ber;        // det_log(1 - ber): free-running streams draw the gap to the next error, floor(log(u) / log(1 - ber))
     uint64_t round_tag;      // round << 40
     uint64_t base0;          // global index of this rank's template 0 (fragments: contiguous per rank)
     uint64_t mark_base;      // replay: index of template 0's mark inside the domain's mark array
@@ -206,9 +207,30 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     }
                 }
                 if (nN) gc = 0;   // countGC() gives 0 as soon as the window holds an N (MyDefine.cpp:448-450)
-                // ---- per-base polymerase errors, j = 8 .. alen-1 (Fragment.cpp:105-123)
-                // draw d on the real stream belongs to position j = 8 + (d - dbase)
-                uint32_t nown = 0; uint32_t dbase = cr, dcur = cr; const uint32_t dend_pos = alen;   // position limit
+                // ---- polymerase errors at positions j = 8 .. alen-1, each with probability ber (Fragment.cpp:105-123)
+                uint32_t nown = 0;
+                if (!S.replay()) {
+                    // free-running streams: the distance to the next error is drawn directly, P(gap = g) = (1-ber)^g * ber — the same
+                    // distribution as the reference's one Bernoulli draw per base, at one draw per error (+1) instead of ~1500 per
+                    // product. Every lane evaluates the same draws (det_log: bit-identical to the CPU oracle).
+                    uint64_t j = 7;
+                    for (;;) {
+                        const double u = __ddiv_rn(__dadd_rn((double)S.at(E_REAL, cr++), 0.5), 4294967296.0);
+                        const double gd = floor(__ddiv_rn(det_log(u), ap.log1m_ber));
+                        if (!(gd < (double)alen)) break;
+                        j += 1 + (uint64_t)gd;
+                        if (j >= alen) break;
+                        const uint32_t base = tmpl_base(g, T, terr, tnerr, spos + (uint32_t)j);
+                        uint32_t nb;
+                        if (FROM_FRAG) { do { nb = S.at(E_INT, ci++) >> 30; } while (nb == base); }     // Fragment.cpp:110
+                        else { do { nb = S.at(E_REAL, cr++) >> 30; } while (nb == base); }               // Amplicon.cpp:213
+                        gc += (int)((nb == 1u) | (nb == 2u)) - (int)((base == 1u) | (base == 2u));
+                        if (nown < kMaxErrPerAmp) { if (lane == 0) errbuf[nown] = pack_err((uint32_t)j, nb); } else if (lane == 0) atomicOr(flags, 1);
+                        nown++;
+                    }
+                } else {
+                // replay: the reference's own consumption, one draw per base. Draw d on the real stream belongs to position j = 8 + (d - dbase)
+                uint32_t dbase = cr, dcur = cr; const uint32_t dend_pos = alen;   // position limit
                 for (;;) {
                     uint32_t jcur = 8 + (dcur - dbase);
                     if (jcur >= dend_pos) break;
@@ -236,6 +258,7 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     dcur = dh + 1 + extra; dbase += extra;
                 }
                 cr = dbase + (alen - 8);
+                }
                 if (nown > kMaxErrPerAmp) nown = kMaxErrPerAmp;
                 __syncwarp();
                 // ---- emit the product into slot (slot0 + made)
@@ -319,7 +342,7 @@ struct Round {
     int allreduce_u64(uint64_t* v, size_t n) { return scs::allreduce_u64(c, v, n); }
 
     AmpParams params(int round, bool semis, int domain) {
-        AmpParams ap{}; ap.thr_ber = thr_ber; ap.round_tag = (uint64_t)round << 40;
+        AmpParams ap{}; ap.thr_ber = thr_ber; ap.log1m_ber = det_log(1.0 - 3.4e-4); ap.round_tag = (uint64_t)round << 40;
         if (semis) { ap.use_geom = 1; ap.base0 = 0; ap.geom = c->semi_geom; ap.mark_base = mark_base(domain, round); }
         else { ap.use_geom = 0; ap.base0 = c->frag_global0; ap.mark_base = mark_base(domain, round) + c->frag_global0; }
         return ap;

@@ -162,3 +162,24 @@ def test_free_running_matches_reference_distributions(tmp_path):
     # branching process (Poisson primers per template over 6 rounds), so its size has a coefficient of variation of ~20 %
     # between seeds on a genome this small: only the order of magnitude is comparable here (exact counts: replay tests).
     assert abs(R["amp_max"] - G["amp_max"]) / R["amp_max"] < 0.45
+
+
+def test_polymerase_errors_of_free_running_amplification():
+    """Free-running streams draw the distance to the next polymerase error (geometric) instead of the reference's one Bernoulli
+    draw per base (Fragment.cpp:105-107, ber = 3.4e-4): the number of own substitutions of the semi amplicons must be
+    Binomial(len - 8, ber) — total within 4 sigma, and the index of dispersion of the per-amplicon counts within 5 % of 1."""
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_genome
+    prof = H.profile_path("Illumina_HiSeq2500")
+    with api.GenReads(gamma=1e-9, coverage=1.0, layout="SE", seed=77) as g:
+        g.load_profile(prof).set_genome(synth_genome(2, 200_000, seed=3, diploid=True)).create_frags().amplify()
+        semis = g.dump(api.DUMP_SEMIS).astype(np.int64)
+    lens, nerr = semis[:, 2], semis[:, 5]
+    assert len(semis) > 30_000
+    ber = 3.4e-4
+    expect = float(((lens - 8) * ber).sum())
+    assert abs(nerr.sum() - expect) < 4 * np.sqrt(expect), (int(nerr.sum()), expect)
+    # per-amplicon counts: binomial with n ~ 1500, p = ber -> variance ~ mean once the spread of the lengths is taken out
+    resid = nerr - (lens - 8) * ber
+    assert abs(resid.var() / nerr.mean() - 1.0) < 0.05, (resid.var(), nerr.mean())
+    assert nerr.max() <= 8
