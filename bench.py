@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons")
     ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
     ap.add_argument("--files-dir", default=None, help="directory for the e2e_files leg (default: the system temp dir)")
+    ap.add_argument("--gz", action="store_true", help="(not the headline) block-gzip output on the device: compressed FASTQ lands in the pinned ring")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(a.warmup, 0)
@@ -286,6 +287,8 @@ def main():
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     config = bench_config(a.scale, a.coverage)
+    if a.gz:
+        config["workload"] = "NOT THE HEADLINE (--gz: block-gzip output) " + config["workload"]
     if a.impl == "reference":
         if rank != 0:
             return 0
@@ -369,7 +372,7 @@ def main():
         # ---- slots are cut in proportion to a per-GPU weight (balance = 1): first its measured D2H rate, then refined after every
         # ---- warm-up step from the measured read-stage times, so that all GPUs finish together
         g = api.GenReads(gamma=GAMMA, coverage=a.coverage, isize=ISIZE, layout="PE", seed=0x5C55, device=device, rank=rank, world=world,
-                         slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance))
+                         slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance), gzip=a.gz)
         weight = d2h_per_rank[rank]
         if world > 1:
             # the library's own NCCL communicator (scs_nccl_init): rank 0's id reaches the other ranks through the process group that
@@ -426,6 +429,7 @@ def main():
         launches = st["kernel_launches"] - l0
         reads_per_step = st["records"]   # FASTQ records actually written by this rank (both files)
         fastq_bytes = st["fastq_bytes"][0] + st["fastq_bytes"][1]
+        plain_bytes = st["plain_bytes"][0] + st["plain_bytes"][1]
         n_fulls, n_semis = st["n_fulls_global"], st["n_semis_global"]
 
         # ---- e2e leg (host buffers in, host bytes out); one untimed pass first (page faults of the host side)
@@ -466,6 +470,21 @@ def main():
             extras["configs1"] = {"workload": "BASELINE configs[1]: synthetic 250 Mb haploid, PE150 10x (-c 20), same profile/gamma" + ("" if a.scale == 1.0 else f" DEBUG scale {a.scale}"),
                                   "value": s1["records"] / c1_s / 1e6, "unit": UNIT, "ms_per_step": c1_s * 1e3,
                                   "fastq_GBps": (s1["fastq_bytes"][0] + s1["fastq_bytes"][1]) / c1_s / 1e9, "steps": 3, "warmup": 2}
+            # the same cell with block-gzip output (BGZF members deflated on the device): fewer bytes over PCIe
+            gz1 = api.GenReads(gamma=GAMMA, coverage=C1_COVERAGE, isize=ISIZE, layout="PE", seed=0x5C55, device=device, slab_bytes=a.slab_mb << 20, gzip=True)
+            gz1.load_profile(profile).set_genome([(f"chrS1_1_{c1len}", seq)]).create_frags()
+            for _ in range(2):
+                gz1.amplify().set_read_counts().yield_reads_discard()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(3):
+                gz1.amplify().set_read_counts().yield_reads_discard()
+            gz_s = (time.perf_counter() - t0) / 3
+            sg = gz1.stats()
+            extras["configs1_gz"] = {"workload": extras["configs1"]["workload"] + ", block-gzip output (gzip = 1; not the reference's format)", "value": sg["records"] / gz_s / 1e6,
+                                     "unit": UNIT, "ms_per_step": gz_s * 1e3, "compressed_GBps": sum(sg["fastq_bytes"]) / gz_s / 1e9,
+                                     "plain_equivalent_GBps": sum(sg["plain_bytes"]) / gz_s / 1e9, "ratio": sum(sg["plain_bytes"]) / max(1, sum(sg["fastq_bytes"])),
+                                     "read_stage_kernels_ms": sg["ms_reads_kernels"], "read_stage_ms": sg["ms_reads"]}
+            gz1.close()
             # files: <prefix>_1.fq / <prefix>_2.fq through scs_yield_reads (asynchronous sink, O_DIRECT where the file system has it)
             fdir = a.files_dir or tmp
             files = {}
@@ -524,7 +543,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": config,
-            "detail": {"reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": gbps, "full_amplicons": n_fulls, "semi_amplicons": n_semis,
+            "detail": {"reads_per_step": reads_all, "fastq_bytes_per_step": bytes_all, "fastq_GBps": gbps, "gzip": bool(a.gz), "plain_bytes_per_step_rank0": plain_bytes, "full_amplicons": n_fulls, "semi_amplicons": n_semis,
                        "stage_ms_per_step_rank0": {"amplify": amp_ms / a.steps, "alloc": alloc_ms / a.steps, "reads": reads_ms / a.steps},
                        "reads_stage_ms_max_rank": reads_ms_max / a.steps,
                        "parallelism": (f"one cell over {world} GPUs: sequences sharded for the amplification, packed genome + amplicon table all-gathered "

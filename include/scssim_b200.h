@@ -59,6 +59,11 @@ typedef struct scs_params {
     uint64_t slab_bytes;  /* FASTQ staging slab per file; 0 -> default (64 MiB) */
     int32_t io_threads;   /* host threads that pwrite() the slabs to the output files (the CLI's -t); 0 -> default (4) */
     int32_t ring_slabs;   /* scs_yield_reads: pinned host slabs per file the asynchronous file sink may hold; 0 -> default (6) */
+    int32_t gzip;         /* 1: FASTQ leaves the device block-gzip compressed (BGZF: independent gzip members of 32 KiB of text, one
+                             dynamic-Huffman block of literals each, ~2.1x smaller). Sinks receive the compressed bytes; scs_yield_reads
+                             writes <prefix>_1.fq.gz/_2.fq.gz or <prefix>.fq.gz (world > 1: one shard <prefix>.rank<r>... per rank,
+                             `cat` of the shards in rank order is the whole output). Extra flag --gz; the reference writes plain text */
+    int32_t reserved;
 } scs_params;
 
 void scs_default_params(scs_params* p);
@@ -135,6 +140,7 @@ typedef struct scs_stats {
     double ms_emit_kernel;                     /* emit kernel only, summed */
     uint64_t emit_launches;
     uint64_t genome_window_bytes;              /* algorithmic HBM read bytes of the emit kernel */
+    uint64_t plain_bytes[2];                   /* FASTQ text bytes behind fastq_bytes (equal unless gzip = 1, then fastq_bytes is compressed) */
 } scs_stats;
 int scs_get_stats(const scs_ctx* ctx, scs_stats* out);
 
@@ -196,6 +202,10 @@ int scs_test_file_writer(const char* path, const char* data, uint64_t n, uint64_
  * *used_direct tells whether the file system granted it. Returns 0 on success. */
 int scs_test_async_writer(const char* path, const char* data, uint64_t n, uint64_t slab_bytes, int threads, int ring, uint64_t base, int create,
                           uint64_t prealloc, int direct, int* used_direct);
+/* Host-only: the canonical Huffman code (lengths of literals 0..255 and of end-of-block) and the constant bit prefix (18-byte BGZF
+ * member header + dynamic-block header, least significant bit first) that the block-gzip output of this context's profile uses.
+ * Returns the number of 32-bit words of the prefix. */
+int scs_test_deflate_code(const scs_ctx* ctx, uint8_t* lens257, uint32_t* prefix_words, int cap_words, uint32_t* prefix_bits);
 /* The first n values of libc rand() after srand(seed), as reproduced by the library. */
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out);
 

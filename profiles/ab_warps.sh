@@ -6,13 +6,9 @@ set -uo pipefail
 mode=$1; shift
 cd "$(dirname "$0")/.."
 if [ "$mode" = build ]; then
-  mkdir -p scssim_b200/variants
   for w in "$@"; do
-    ( cd scssim_b200/csrc && /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false \
-        -Xcompiler -fPIC,-ffp-contract=off -Xptxas -v -DSCS_EMIT_WARPS=$w -c reads.cu -o ../variants/reads_w$w.o 2> ../variants/reads_w$w.log && \
-      /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../variants/libscssim_b200_w$w.so capi.o genome.o amplify.o alloc.o ../variants/reads_w$w.o \
-        simuvars.o profile_host.o fasta_host.o simuvars_plan.o file_sink.o vmm.o -lcudart_static -lpthread -ldl -lrt ) || exit 1
-    grep -A2 "emit_kernelILb0ELb0" scssim_b200/variants/reads_w$w.log | grep -E "registers|spill" | tr '\n' ' '; echo " <- w=$w"
+    make -s -C scssim_b200/csrc variant NAME=w$w DEFS=-DSCS_EMIT_WARPS=$w || exit 1
+    grep -A2 "emit_kernelILb0ELb0" scssim_b200/variants/reads.w$w.log | grep -E "registers|spill" | tr '\n' ' '; echo " <- w=$w"
   done
 else
   for w in "$@"; do

@@ -35,7 +35,7 @@ class Params(C.Structure):
     _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
                 ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64), ("io_threads", C.c_int32),
-                ("ring_slabs", C.c_int32)]
+                ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -45,18 +45,18 @@ class Stats(C.Structure):
                 ("total_primers_left", C.c_uint64), ("kernel_launches", C.c_uint64), ("ms_pack", C.c_double),
                 ("ms_amplify", C.c_double), ("ms_alloc", C.c_double), ("ms_reads", C.c_double),
                 ("ms_reads_kernels", C.c_double), ("ms_emit_kernel", C.c_double), ("emit_launches", C.c_uint64),
-                ("genome_window_bytes", C.c_uint64)]
+                ("genome_window_bytes", C.c_uint64), ("plain_bytes", C.c_uint64 * 2)]
 
     def as_dict(self):
         d = {}
         for name, _ in self._fields_:
             v = getattr(self, name)
-            d[name] = list(v) if name == "fastq_bytes" else v
+            d[name] = list(v) if name in ("fastq_bytes", "plain_bytes") else v
         return d
 
 
 class SimuVarsParams(C.Structure):
-    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("ring_slabs", C.c_int32)]
+    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SimuVarsStats(C.Structure):
@@ -88,7 +88,7 @@ EXPORTS = ["scs_default_params", "scs_create", "scs_destroy", "scs_last_error", 
            "scs_test_predict", "scs_test_philox", "scs_test_det_log", "scs_profile_thresholds", "scs_shard_range",
            "scs_version", "scs_device_count", "scs_nccl_unique_id", "scs_nccl_init", "scs_nccl_abort", "scs_nccl_version",
            "scs_simuvars_default_params", "scs_simuvars", "scs_simuvars_sink", "scs_simuvars_to_genome", "scs_simuvars_get_stats",
-           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer", "scs_test_async_writer"]
+           "scs_simuvars_warnings", "scs_svplan_create", "scs_svplan_destroy", "scs_svplan_dump", "scs_test_libc_rand", "scs_shard_sequences", "scs_test_fasta_index", "scs_test_file_writer", "scs_test_async_writer", "scs_test_deflate_code"]
 
 _lib = None
 
@@ -232,7 +232,7 @@ class GenReads:
 
     def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
                  layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
-                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0, ring_slabs: int = 0):
+                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0, ring_slabs: int = 0, gzip: bool = False):
         if layout not in ("SE", "PE"):
             raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
         L = lib()
@@ -243,6 +243,7 @@ class GenReads:
         p.balance = int(balance)
         p.io_threads = io_threads
         p.ring_slabs = ring_slabs
+        p.gzip = int(gzip)
         self._h = C.c_void_p()
         rc = L.scs_create(C.byref(p), C.byref(self._h))
         if rc != SCS_OK:
@@ -487,6 +488,15 @@ class GenReads:
         out = np.zeros_like(x)
         self._ck(lib().scs_test_det_log(self._h, x.ctypes.data, len(x), out.ctypes.data))
         return out
+
+    def deflate_code(self):
+        """(code lengths [257], prefix bytes, prefix bit count) of the block-gzip output for this profile (host only)."""
+        lens = np.zeros(257, dtype=np.uint8)
+        words = np.zeros(256, dtype=np.uint32)
+        nbits = C.c_uint32()
+        lib().scs_test_deflate_code.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]
+        self._ck(lib().scs_test_deflate_code(self._h, lens.ctypes.data, words.ctypes.data, len(words), C.byref(nbits)))
+        return lens, words, int(nbits.value)
 
     def thresholds(self, which: int, idx: int = 0, row: int = 0):
         out = np.zeros(4096, dtype=np.uint32)

@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256) assign_primers_kernel(DrawSrc src, AmpPar
 
 // ---------------------------------------------------------------------------------- K2
 __device__ __forceinline__ uint32_t tmpl_base(const Genome& g, const Tmpl& T, const uint32_t* __restrict__ errs, uint32_t nerr, uint32_t i) {
+    SCS_CHECK(i < T.len);
     uint32_t b = window_base(g, T.gstart, T.rc, i);
     for (uint32_t e = 0; e < nerr; e++) { uint32_t v = errs[e]; if (err_pos(v) == i) b = err_base(v); }
     return b;
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                 }
                 if (!acc) { ci += 51; cr += 51; break; }   // 51st try draws, then the template is abandoned
                 if (lane == 0) {
+                    SCS_CHECK(!use_list || made < (uint32_t)BITMAP_WORDS);
                     if (use_list) bitmap[made] = spos;   // every accepted primer yields exactly one product: `made` indexes the list
                     else { uint32_t* bm = FROM_FRAG ? gbitmap : bitmap; bm[spos >> 5] |= 1u << (spos & 31); }
                 }
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                     eoff = __shfl_sync(0xffffffffu, eoff, 0);
                     if (eoff + ntot > err_cap) { if (lane == 0) atomicOr(flags, 2); ntot = 0; eoff = 0; }
                     for (uint32_t q = lane; q < ntot; q += 32) {
+                        SCS_CHECK(q < (uint32_t)kMaxErrPerAmp && eoff + q < err_cap);
                         uint32_t v = errbuf[q];
                         // own errors of a semi are recorded in copied-window coordinates; its template is the reverse complement
                         if (FROM_FRAG) v = pack_err(alen - 1 - err_pos(v), 3u - err_base(v));
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, DrawSrc s
                 }
                 if (lane == 0) {
                     uint64_t slot = slot0 + made;
+                    SCS_CHECK(made < primerNum && slot < slot_off[t] + primers[t] && spos + alen <= T.len && spos >= 27 && alen >= (uint32_t)kAmpMin && alen <= (uint32_t)kAmpMax);
                     out_desc[slot] = pack_desc(ngstart, nrc, alen);
                     out_gc[slot] = (uint32_t)max(0, gc);
                     out_errref[slot] = ((uint64_t)eoff << 16) | ntot;

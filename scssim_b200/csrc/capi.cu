@@ -8,6 +8,7 @@
 #include "file_sink.h"
 #include "slab_sink.h"
 #include "simuvars_plan.h"
+#include "deflate_host.h"
 
 using namespace scs;
 
@@ -22,7 +23,7 @@ int scs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
     p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
-    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0; p->ring_slabs = 0;
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0; p->ring_slabs = 0; p->gzip = 0; p->reserved = 0;
 }
 
 int scs_create(const scs_params* p, scs_ctx** out) {
@@ -174,9 +175,13 @@ int scs_yield_reads(scs_ctx* c, const char* prefix) {
     if (!c || !prefix) return SCS_E_ARG;
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
     cudaSetDevice(c->P.device); alloc_stream() = c->st;
-    const int W = std::max(1, c->P.world), R = c->P.rank, nfiles = c->P.paired ? 2 : 1;
-    const std::string base = prefix;
-    const std::string name[2] = {c->P.paired ? base + "_1.fq" : base + ".fq", base + "_2.fq"};
+    const bool gz = c->P.gzip != 0;
+    // compressed shard sizes are not known before the shards exist: with gzip every rank writes its own member stream
+    // (<prefix>.rank<r>_1.fq.gz ...; gzip members concatenate, so `cat` in rank order is the whole output)
+    const int W = gz ? 1 : std::max(1, c->P.world), R = gz ? 0 : c->P.rank, nfiles = c->P.paired ? 2 : 1;
+    const std::string base = std::string(prefix) + ((gz && c->P.world > 1) ? ".rank" + std::to_string(c->P.rank) : "");
+    const std::string ext = gz ? ".fq.gz" : ".fq";
+    const std::string name[2] = {c->P.paired ? base + "_1" + ext : base + ext, base + "_2" + ext};
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
     if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
     uint64_t off[2] = {0, 0}, total[2] = {0, 0}, mine[2] = {0, 0};
@@ -192,7 +197,7 @@ int scs_yield_reads(scs_ctx* c, const char* prefix) {
         for (int r = 0; r < W; r++) for (int f = 0; f < 2; f++) { if (r < R) off[f] += v[2 * (size_t)r + f]; total[f] += v[2 * (size_t)r + f]; }
     } else {
         const uint64_t slots = c->global_view ? c->g_slot_hi - c->g_slot_lo : c->n_slots;
-        total[0] = total[1] = slots * (uint64_t)(30 + 2 * (c->prof.readLength + 8) + 4);   // preallocation only: trimmed to the bytes written
+        total[0] = total[1] = slots * (uint64_t)(30 + 2 * (c->prof.readLength + 8) + 4) / (gz ? 2 : 1);   // preallocation only: trimmed to the bytes written
     }
     AsyncFileConsumer sink(c->P.io_threads > 0 ? c->P.io_threads : 4, c->P.ring_slabs > 0 ? c->P.ring_slabs : 6, c->P.device, getenv("SCS_NO_ODIRECT") == nullptr);
     int rc = SCS_OK;
@@ -329,6 +334,20 @@ int scs_test_async_writer(const char* path, const char* data, uint64_t n, uint64
     if (sink.finish()) rc = SCS_E_IO;
     for (char* q : slots) free(q);
     return rc;
+}
+// The Huffman code the block-gzip output of this context's profile is written with (host only): code lengths of the 256 literals
+// and of end-of-block, and the constant prefix of every BGZF block (member header + dynamic-block header) as LSB-first bits.
+int scs_test_deflate_code(const scs_ctx* c, uint8_t* lens, uint32_t* prefix_words, int cap_words, uint32_t* prefix_bits) {
+    if (!c || !lens || !prefix_bits) return SCS_E_ARG;
+    if (!c->have_profile) return SCS_E_STATE;
+    uint64_t hist[257]; DeflateCode D;
+    fastq_model_histogram(c->prof, c->P.paired != 0, hist);
+    if (!build_deflate_code(hist, D)) return SCS_E_STATE;
+    memcpy(lens, D.len, 257);
+    *prefix_bits = D.prefix_bits;
+    const int nw = (int)((D.prefix_bits + 31) / 32);
+    if (prefix_words) { if (cap_words < nw) return SCS_E_ARG; memcpy(prefix_words, D.prefix_words.data(), (size_t)nw * 4); }
+    return nw;
 }
 int scs_test_libc_rand(uint32_t seed, int n, uint32_t* out) {
     if (!out || n < 0) return SCS_E_ARG;

@@ -135,7 +135,9 @@ static void usage_genReads(const char* app) {
          << "    -o, --output <string>           the prefix of output file" << endl
          << "        --seed <int>                random seed [Default:time]" << endl
          << "        --device <int>              CUDA device ordinal [Default:0]" << endl
-         << "        --gpus <int>                shard the cell's sequences over this many GPUs [Default:1]" << endl << endl
+         << "        --gpus <int>                shard the cell's sequences over this many GPUs [Default:1]" << endl
+         << "        --gz                        write block-gzip compressed FASTQ (<prefix>_1.fq.gz ...; with --gpus N one shard per GPU," << endl
+         << "                                    <prefix>.rank<r>_1.fq.gz, whose concatenation in rank order is the output)" << endl << endl
          << "Example:" << endl
          << "    scssim " << app << " -i /path/to/ref.fa -m /path/to/hiseq2500.profile -t 5 -o /path/to/reads" << endl << endl;
 }
@@ -197,7 +199,8 @@ int main(int argc, char* argv[]) {
                                     {"coverage", required_argument, 0, 'c'}, {"isize", required_argument, 0, 's'},
                                     {"threads", required_argument, 0, 't'}, {"output", required_argument, 0, 'o'},
                                     {"seed", required_argument, 0, 1000},   {"device", required_argument, 0, 1001},
-                                    {"gpus", required_argument, 0, 1002},   {0, 0, 0, 0}};
+                                    {"gpus", required_argument, 0, 1002},   {"gz", no_argument, 0, 1003},
+                                    {0, 0, 0, 0}};
     int c;
     argc -= 1; argv += 1;
     while ((c = getopt_long(argc, argv, "hi:p:r:m:l:c:s:t:o:", long_options, NULL)) != -1) {
@@ -215,6 +218,7 @@ int main(int argc, char* argv[]) {
             case 1000: P.seed = strtoull(optarg, NULL, 0); break;
             case 1001: P.device = atoi(optarg); break;
             case 1002: gpus = atoi(optarg); break;
+            case 1003: P.gzip = 1; break;
             default: usage_genReads(argv[0]); return 1;
         }
     }

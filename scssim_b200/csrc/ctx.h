@@ -157,6 +157,15 @@ struct ReadScratch {
     uint64_t* dtotals_mapped = nullptr;   // device view of htotals
 };
 
+// block-gzip output (deflate.cu): the run's Huffman code and CRC tables on the device, per-slab scratch
+struct GzState {
+    bool ready = false; uint32_t prefix_bits = 0;
+    DevBuf<uint32_t> code, prefix, crc, x2n;
+    DevBuf<char> stage[2];            // members of one slab per file at a fixed 64 KiB stride, packed by compact_records_kernel
+    DevBuf<uint32_t> sizes[2]; DevBuf<uint64_t> offs[2];
+    DevBuf<char> slab[2][2];          // [buffer][file] packed compressed slabs (what is copied to the host)
+};
+
 }  // namespace scs
 
 struct scs_ctx {
@@ -193,6 +202,7 @@ struct scs_ctx {
     uint64_t reads_requested = 0, n_slots = 0;
 
     scs::ReadScratch rscratch;
+    scs::GzState gz;
     scs::AmpScratch ascratch;
     // staging buffers that keep their capacity between calls (cold device allocations are slow and erratic on this platform)
     scs::DevBuf<uint8_t> genome_stage, sv_stage, sv_ref, sv_text[2];
@@ -277,6 +287,13 @@ int set_read_counts(scs_ctx* c);
 struct SlabConsumer;
 int yield_reads(scs_ctx* c, SlabConsumer& sink);
 int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]);
+// block-gzip output (deflate.cu)
+int gz_prepare(scs_ctx* c);
+size_t gz_smem_bytes();
+uint64_t gz_max_pieces(uint64_t slab_bytes);
+uint64_t gz_stage_stride();
+int gz_launch(scs_ctx* c, const char* plain, const uint64_t* offs, const uint32_t* sizes, uint64_t nrec, char* stage, uint32_t max_pieces, uint32_t* piece_sizes,
+              int append_eof, int* flags, int sms);
 int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const uint32_t* real, uint64_t stride_real, const uint32_t* ints,
                  uint64_t stride_int, char* out_seq, char* out_qual, int out_stride, int32_t* out_len);
 int dump_full_seqs(scs_ctx* c, char* buf, uint64_t cap, int64_t* written);

@@ -9,6 +9,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Checked build (make variant NAME=checked DEFS=-DSCS_CHECKED=1 ALL=1): every index the kernels form into shared-memory scratch,
+// staging cells, slabs, pools and the packed genome is asserted. compute-sanitizer is closed on this GPU pool; the GPU suite is run
+// against this build instead (profiles/NOTES_r02.md).
+#ifdef SCS_CHECKED
+#include <cassert>
+#define SCS_CHECK(cond) assert(cond)
+#else
+#define SCS_CHECK(cond) ((void)0)
+#endif
+
 namespace scs {
 
 enum Domain : int { D_FRAG = 0, D_POIS = 1, D_AMPF = 2, D_AMPS = 3, D_GCF = 4, D_MULTM = 5, D_MULTC = 6, D_READ = 7 };
@@ -134,6 +144,7 @@ struct Genome {
     int has_n;
 };
 __device__ __forceinline__ uint32_t genome_base(const Genome& g, uint64_t pos) {
+    SCS_CHECK(pos < g.n_bases);
     uint32_t b = (uint32_t)(__ldg(g.words + (pos >> 5)) >> ((pos & 31) * 2)) & 3u;
     if (g.has_n && ((__ldg(g.nmask + (pos >> 5)) >> (pos & 31)) & 1u)) b = 4u;
     return b;

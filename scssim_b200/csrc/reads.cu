@@ -191,6 +191,7 @@ __device__ __forceinline__ int indel_pass(const SX& S, const ReadTables& T, int 
             int k = min(count_le(T.ins, T.insEff, xl), T.insEff);
             cr = crp + 2;
             if (k > 0) {
+                SCS_CHECK(p >= 0 && p < n);
                 if (nev < kMaxEvents) { if (lane == 0) { ws->ev_pos[nev] = (int16_t)p; ws->ev_len[nev] = (int16_t)k; ws->ev_ci[nev] = ci; } }
                 else if (lane == 0) atomicOr(flags, 4);
                 nev++; delta += k; ci += (uint32_t)k;
@@ -232,6 +233,7 @@ __device__ __noinline__ void build_source_events(const SX S, int np, int nev, in
                 shift += L;
             }
         }
+        SCS_CHECK(m < kSrcCap && (done || (m - shift >= 0 && m - shift < kRLCap)));
         ws->src[m] = done ? (uint8_t)b : ws->ref[m - shift];
     }
     __syncwarp();
@@ -249,12 +251,14 @@ __device__ __forceinline__ const uint8_t* build_source(const SX& S, int np, int 
 __device__ __forceinline__ int sample_quality(const PassTabs& X, uint32_t b0, uint32_t k, int bin, uint32_t xq) {
     if (X.rows != nullptr && k == b0) {
         const int r = (int)b0 * X.bins + bin;
+        SCS_CHECK(r >= 0 && r < 4 * X.bins);
         const uint32_t meta = X.meta[r];
         if ((meta >> 16) == 0) {
             const int lo = (int)(meta & 0xFFu), cnt = (int)((meta >> 8) & 0xFFu);
             const uint4 pv = X.piv[r];
             // pivots = entries 7, 15, 23, 31: they select one of five octets, which is then counted
             const int oct = (int)(pv.x <= xq) + (int)(pv.y <= xq) + (int)(pv.z <= xq) + (int)(pv.w <= xq);
+            SCS_CHECK(oct >= 0 && oct <= 4);
             const uint4* row = reinterpret_cast<const uint4*>(X.rows + (size_t)r * kDiagStride + oct * 8);
             const uint4 a = row[0], d = row[1];
             const int c = oct * 8 + (int)(a.x <= xq) + (int)(a.y <= xq) + (int)(a.z <= xq) + (int)(a.w <= xq) + (int)(d.x <= xq) + (int)(d.y <= xq) +
@@ -289,6 +293,7 @@ __device__ __forceinline__ void subst_quality_pass(const SX& S, const PassTabs& 
             const uint32_t p1 = src[max(m - 1, 0)], p2 = src[max(m - 2, 0)];
             const uint32_t ki = (m == 0) ? b0[h] : (m == 1) ? 4u + 4u * p1 + b0[h] : 20u + 16u * p2 + 4u * p1 + b0[h];
             bin[h] = inv ? (int)__umulhi((uint32_t)(m * bins), inv) : m;
+            SCS_CHECK(ki < 84u && bin[h] >= 0 && bin[h] < bins && bin[h] == m * bins / np && b0[h] < 4u);
             th[h] = __ldg(subs + ((size_t)ki * bins + bin[h]));
         }
         uint32_t x[4];
@@ -447,6 +452,7 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
     const uint64_t slot = A.slot0 + ls;
     const uint64_t cj = (slot - A.coarse_base) >> kCoarseShift;
     const uint64_t a = find_amplicon(A.slot_base, __ldg(A.coarse + cj), min((uint64_t)__ldg(A.coarse + cj + 1) + 1, A.n_amp), slot, lane);
+    SCS_CHECK(a < A.n_amp && __ldg(A.slot_base + a) <= slot && slot < __ldg(A.slot_base + a + 1));
     const Tmpl F = unpack_desc(__ldg(A.desc + a));
     const uint64_t sb = __ldg(A.slot_base + a);
     const uint64_t er = __ldg(A.errref + a);
@@ -483,11 +489,13 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
                 const uint64_t first = lo[m] >> 2, last = (lo[m] + (uint64_t)RL - 1) >> 2;
                 b0[m] = first & ~15ull; bn[m] = (uint32_t)(((last - b0[m]) + 16) & ~15ull);
                 woff[m] = (uint32_t)(lo[m] - (b0[m] << 2)) | (rev[m] << 31);
+                SCS_CHECK(bn[m] <= (uint32_t)kWinBytes && lo[m] + (uint64_t)RL <= g.n_bases && pos >= 0 && pos + isz <= ampLen);
                 tx += bn[m];
                 if (g.has_n) {
                     const uint64_t nf = lo[m] >> 3, nl = (lo[m] + (uint64_t)RL - 1) >> 3;
                     n0[m] = nf & ~15ull; nn[m] = (uint32_t)(((nl - n0[m]) + 16) & ~15ull);
                     noff[m] = (uint32_t)(lo[m] - (n0[m] << 3));
+                    SCS_CHECK(nn[m] <= (uint32_t)kWinNBytes);
                     tx += nn[m];
                 }
             }
@@ -544,10 +552,12 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         bool myN = false;
         if (need_bases) for (int i = lane; i < RL; i += 32) {
             const uint32_t q = off + (uint32_t)(rev ? (RL - 1 - i) : i);
+            SCS_CHECK((q >> 2) < (uint32_t)kWinBytes && i < kRLCap);
             uint32_t b = ((uint32_t)win[q >> 2] >> ((q & 3u) * 2u)) & 3u;
             if (rev) b ^= 3u;
             if (g.has_n) {
                 const uint32_t qn = P.noff[mate - 1] + (uint32_t)(rev ? (RL - 1 - i) : i);
+                SCS_CHECK((qn >> 3) < (uint32_t)kWinNBytes);
                 if ((st->winn[buf][mate - 1][qn >> 3] >> (qn & 7u)) & 1u) { b = 4u; myN = true; }
             }
             ws->ref[i] = (uint8_t)b;
@@ -569,6 +579,7 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         __syncwarp();
         const int total = hl + 2 * np + 4;
         if ((uint64_t)total > A.stage_stride) { if (lane == 0) atomicOr(flags, 16); return made; }
+        SCS_CHECK(np >= 50 && np <= kSrcCap && total <= kRecCap && ls < A.nslots);
         if (SIZE_ONLY) {   // only the cursors and the record size: the substitution / quality pass draws twice per base, fewer around an N
             if (hasN) {
                 const uint8_t* srcn = build_source(S, np, nev, lane, ws);
@@ -656,6 +667,7 @@ __global__ void __launch_bounds__(256) compact_records_kernel(const char* __rest
         if (!sz) continue;
         const uint64_t o = offs[ls];
         if (o + (uint64_t)sz > cap) { if (lane == 0) atomicOr(flags, 16); continue; }
+        SCS_CHECK((uint64_t)sz <= stride);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(stage) + ls * stride;
         char* dst = out + o;
         const int head = min(sz, (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15));
@@ -923,9 +935,11 @@ int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]) {
 int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     ReadRun R;
     if (int rc = prepare_read_run(c, R)) return rc;
-    c->stats.records = 0; c->stats.fastq_bytes[0] = c->stats.fastq_bytes[1] = 0;
+    c->stats.records = 0; c->stats.fastq_bytes[0] = c->stats.fastq_bytes[1] = 0; c->stats.plain_bytes[0] = c->stats.plain_bytes[1] = 0;
     c->stats.ms_reads = c->stats.ms_reads_kernels = c->stats.ms_emit_kernel = 0; c->stats.emit_launches = 0; c->stats.genome_window_bytes = 0;
-    if (R.nslots == 0) return sink.finish() ? c->fail(SCS_E_IO, "FASTQ sink failed") : SCS_OK;
+    const bool gz = c->P.gzip != 0;
+    if (R.nslots == 0 && !gz) return sink.finish() ? c->fail(SCS_E_IO, "FASTQ sink failed") : SCS_OK;
+    if (gz) { if (int rc = gz_prepare(c)) return rc; }
     const int nfiles = R.nfiles, sms = R.sms, emit_warps = R.emit_warps, isize_smem = R.isize_smem;
     const uint64_t slab = R.slab, stride = R.stride, batch = R.batch, slot_lo = R.slot_lo, slot_hi = R.slot_hi;
     const size_t emit_smem = R.emit_smem;
@@ -945,6 +959,13 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         c->ring_host[f].push_back(q);
     }
     for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
+    // block-gzip output: members of one slab at a fixed stride, their sizes / offsets, and the packed compressed slabs
+    const uint32_t gz_pieces = gz ? (uint32_t)gz_max_pieces(slab) : 0;
+    if (gz) for (int f = 0; f < nfiles; f++) {
+        SCS_CUDA(c, c->gz.stage[f].reserve((uint64_t)gz_pieces * gz_stage_stride() + 64)); SCS_CUDA(c, c->gz.sizes[f].reserve(gz_pieces + 8));
+        SCS_CUDA(c, c->gz.offs[f].reserve(gz_pieces + 8));
+        for (int b = 0; b < 2; b++) SCS_CUDA(c, c->gz.slab[b][f].reserve(slab + 64));
+    }
 
     StageGuard G(c);   // from here on every return drains the streams and frees the events
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
@@ -963,6 +984,15 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         timed[b] = false;
     };
     SCS_CUDA(c, cudaEventRecord(e0, c->st));
+    if (R.nslots == 0) {   // gzip of an empty output: the 28-byte end-of-file member, so that the file is a valid (empty) gzip stream
+        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (sink.acquire(0)) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        char* p[2] = {nullptr, nullptr}; uint64_t tot[2] = {0, 0};
+        for (int f = 0; f < nfiles; f++) { p[f] = c->ring_host[f][0] + (sink.phase(f) & 4095); memcpy(p[f], eof, 28); tot[f] = 28; c->stats.fastq_bytes[f] = 28; }
+        SCS_CUDA(c, cudaEventRecord(eslot[0], c->st_copy));
+        if (sink.submit(0, eslot[0], p, tot) || sink.finish()) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        return SCS_OK;
+    }
     // ---- per slab: emit (staging + sizes) -> scans -> compaction into the packed device slab -> D2H into a pinned ring slot.
     // Software-pipelined on the host: slab k is launched before the host waits for the byte totals of slab k-1, so the kernels
     // run back to back; the consumer is serviced in between.
@@ -971,19 +1001,21 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         if (!dv[b].launched) return SCS_OK;
         SCS_CUDA(c, cudaEventSynchronize(etotb[b]));
         dv[b].launched = false;
-        const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};
-        if (tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
+        const uint64_t tot[2] = {W.htotals[2 * b], nfiles == 2 ? W.htotals[2 * b + 1] : 0};   // bytes to copy (compressed with gzip)
+        const uint64_t plain[2] = {gz ? W.htotals[4 + 2 * b] : tot[0], gz ? (nfiles == 2 ? W.htotals[4 + 2 * b + 1] : 0) : tot[1]};
+        if (plain[0] > slab || plain[1] > slab || tot[0] > slab || tot[1] > slab) return c->fail(SCS_E_NOMEM, "FASTQ slab too small for one batch (raise slab_bytes)");
         const int slot = (int)(dv[b].k % (uint64_t)Rn);
         if (sink.acquire(slot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
         SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
         char* p[2] = {nullptr, nullptr};
         for (int f = 0; f < nfiles; f++) {
             p[f] = c->ring_host[f][slot] + (sink.phase(f) & 4095);
-            if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(p[f], c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
+            if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(p[f], gz ? c->gz.slab[b][f].p : c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
         }
         SCS_CUDA(c, cudaEventRecord(ecopy[b], c->st_copy));
         SCS_CUDA(c, cudaEventRecord(eslot[slot], c->st_copy));
         c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
+        c->stats.plain_bytes[0] += plain[0]; c->stats.plain_bytes[1] += plain[1];
         if (sink.submit(slot, eslot[slot], p, tot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
         return SCS_OK;
     };
@@ -1002,16 +1034,36 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
                                                          isize_smem);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
-        if (int rc = scan_u32_noalloc(c, W.size1.p, W.off1.p, m, W.scan.p, W.dtotals_mapped + 2 * b)) return rc;
-        if (nfiles == 2) { if (int rc = scan_u32_noalloc(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, W.dtotals_mapped + 2 * b + 1)) return rc; }
+        uint64_t* plain_tot = W.dtotals_mapped + (gz ? 4 : 0) + 2 * b;   // with gzip the copy sizes (slots 0..3) are the compressed totals
+        if (int rc = scan_u32_noalloc(c, W.size1.p, W.off1.p, m, W.scan.p, plain_tot)) return rc;
+        if (nfiles == 2) { if (int rc = scan_u32_noalloc(c, W.size2.p, W.off2.p, m, W.scan.p + 2048 + 8, plain_tot + 1)) return rc; }
         SCS_CUDA(c, cudaEventRecord(tq[b][3], c->st));   // kernel time of the slab without the compaction (~0.05 ms), which may wait for a copy
-        SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
-        timed[b] = true;
-        // the packed device slab b is free once the copy of the slab two back is done
-        SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));
         const unsigned cgrid = (unsigned)std::min<uint64_t>((m + 7) / 8, (uint64_t)sms * 16);
-        compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[0].p, stride, W.size1.p, W.off1.p, m, c->slab_dev[b][0].p, slab, W.flags.p); SCS_LAUNCHED(c);
-        if (nfiles == 2) { compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[1].p, stride, W.size2.p, W.off2.p, m, c->slab_dev[b][1].p, slab, W.flags.p); SCS_LAUNCHED(c); }
+        if (!gz) {
+            SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
+            // the packed device slab b is free once the copy of the slab two back is done
+            SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));
+            compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[0].p, stride, W.size1.p, W.off1.p, m, c->slab_dev[b][0].p, slab, W.flags.p); SCS_LAUNCHED(c);
+            if (nfiles == 2) { compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[1].p, stride, W.size2.p, W.off2.p, m, c->slab_dev[b][1].p, slab, W.flags.p); SCS_LAUNCHED(c); }
+        } else {
+            // plain slab (device only) -> 32 KiB pieces deflated into fixed-stride cells -> scan of the member sizes -> packed compressed slab
+            const bool last = s0 + batch >= slot_hi;
+            for (int f = 0; f < nfiles; f++) {
+                const uint32_t* sz = f ? W.size2.p : W.size1.p; const uint64_t* of = f ? W.off2.p : W.off1.p;
+                compact_records_kernel<<<cgrid, 256, 0, c->st>>>(W.stage[f].p, stride, sz, of, m, c->slab_dev[b][f].p, slab, W.flags.p); SCS_LAUNCHED(c);
+                SCS_CUDA(c, cudaMemsetAsync(c->gz.sizes[f].p, 0, (gz_pieces + 1) * 4, c->st));
+                if (int rc = gz_launch(c, c->slab_dev[b][f].p, of, sz, m, c->gz.stage[f].p, gz_pieces, c->gz.sizes[f].p, last ? 1 : 0, W.flags.p, sms)) return rc;
+                if (int rc = scan_u32_noalloc(c, c->gz.sizes[f].p, c->gz.offs[f].p, gz_pieces, W.scan.p + (f ? 2048 + 8 : 0), W.dtotals_mapped + 2 * b + f)) return rc;
+            }
+            SCS_CUDA(c, cudaEventRecord(etotb[b], c->st));
+            SCS_CUDA(c, cudaStreamWaitEvent(c->st, ecopy[b], 0));   // the compressed slab b is free once the copy of the slab two back is done
+            for (int f = 0; f < nfiles; f++) {
+                compact_records_kernel<<<(unsigned)std::min<uint32_t>((gz_pieces + 7) / 8, (uint32_t)sms * 16), 256, 0, c->st>>>(c->gz.stage[f].p, gz_stage_stride(), c->gz.sizes[f].p,
+                                                                                                                            c->gz.offs[f].p, gz_pieces, c->gz.slab[b][f].p, slab, W.flags.p);
+                SCS_LAUNCHED(c);
+            }
+        }
+        timed[b] = true;
         SCS_CUDA(c, cudaEventRecord(ekern[b], c->st));
         dv[b].launched = true; dv[b].k = k;
         if (int rc = finalize(b ^ 1)) return rc;   // slab k-1: totals known -> copy queued behind its compaction
@@ -1029,6 +1081,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
     if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
     if (hflags & 16) return c->fail(SCS_E_NOMEM, "FASTQ slab overflow (raise slab_bytes)");
+    if (hflags & 32) return c->fail(SCS_E_STATE, "gzip: a byte outside the FASTQ alphabet or an oversized block");
     return SCS_OK;
 }
 

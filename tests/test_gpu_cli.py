@@ -124,3 +124,25 @@ def test_cli_with_every_buffer_on_virtual_memory(tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     for a, b in zip(H.fastq_names(os.path.join(tmp, "gpu"), "PE"), H.fastq_names(os.path.join(tmp, "orc"), "PE")):
         assert len(H.read_bytes(a)) > 100_000 and H.read_bytes(a) == H.read_bytes(b)
+
+
+def test_cli_gz_flag(tmp_path):
+    """--gz: <prefix>_1.fq.gz / _2.fq.gz decompress (gzip -dc) to the oracle's files; with --gpus 2 one shard per worker whose
+    concatenation in rank order decompresses to the same bytes."""
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome(fa, 2, 120_000, seed=33)
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, "PE", 2e-10, 6.0, 260)
+    H.run_oracle(fa, os.path.join(tmp, "orc"), args, seed=4711)
+    want = [H.read_bytes(p) for p in H.fastq_names(os.path.join(tmp, "orc"), "PE")]
+    r = subprocess.run([EXE, "genreads", "-i", fa, "-o", os.path.join(tmp, "g1"), "--seed", "4711", "--gz"] + args, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for k, w in zip((1, 2), want):
+        assert subprocess.run(["gzip", "-dc", os.path.join(tmp, f"g1_{k}.fq.gz")], capture_output=True, check=True).stdout == w
+    r = subprocess.run([EXE, "genreads", "-i", fa, "-o", os.path.join(tmp, "g2"), "--seed", "4711", "--gz", "--gpus", "2"] + args, capture_output=True,
+                       env=dict(os.environ, SCS_CLI_SAME_DEVICE="1"))
+    assert r.returncode == 0, r.stderr.decode()
+    for k, w in zip((1, 2), want):
+        cat = b"".join(H.read_bytes(os.path.join(tmp, f"g2.rank{rk}_{k}.fq.gz")) for rk in (0, 1))
+        assert subprocess.run(["gzip", "-dc"], input=cat, capture_output=True, check=True).stdout == w

@@ -175,11 +175,11 @@ def test_polymerase_errors_of_free_running_amplification():
         g.load_profile(prof).set_genome(synth_genome(2, 200_000, seed=3, diploid=True)).create_frags().amplify()
         semis = g.dump(api.DUMP_SEMIS).astype(np.int64)
     lens, nerr = semis[:, 2], semis[:, 5]
-    assert len(semis) > 30_000
+    assert len(semis) > 15_000
     ber = 3.4e-4
     expect = float(((lens - 8) * ber).sum())
     assert abs(nerr.sum() - expect) < 4 * np.sqrt(expect), (int(nerr.sum()), expect)
     # per-amplicon counts: binomial with n ~ 1500, p = ber -> variance ~ mean once the spread of the lengths is taken out
     resid = nerr - (lens - 8) * ber
-    assert abs(resid.var() / nerr.mean() - 1.0) < 0.05, (resid.var(), nerr.mean())
+    assert abs(resid.var() / nerr.mean() - 1.0) < 0.06, (resid.var(), nerr.mean())   # sd of the ratio ~ sqrt(2/n + 1/(n*mean)) ~ 1.6 %
     assert nerr.max() <= 8

@@ -207,3 +207,59 @@ def test_file_sink_equals_the_oracle(tmp_path, layout, direct, monkeypatch):
     for i, (a, b) in enumerate(zip(H.fastq_names(os.path.join(tmp, "gpu"), layout), H.fastq_names(os.path.join(tmp, "orc"), layout))):
         assert H.read_bytes(a) == H.read_bytes(b)
         assert want[i] == os.path.getsize(b)             # the sizing pass predicts the file size exactly
+
+
+def _bgzf_members(data: bytes):
+    """Walk a BGZF stream: yields (member bytes, uncompressed size); checks the BC subfield and BSIZE of every member."""
+    import struct
+    out, i = [], 0
+    while i < len(data):
+        assert data[i:i + 4] == b"\x1f\x8b\x08\x04" and data[i + 12:i + 16] == b"BC\x02\x00", i
+        bsize = struct.unpack_from("<H", data, i + 16)[0] + 1
+        assert bsize <= 65536 and i + bsize <= len(data)
+        out.append((data[i:i + bsize], struct.unpack_from("<I", data, i + bsize - 4)[0]))
+        i += bsize
+    return out
+
+
+@pytest.mark.parametrize("layout,with_n,slab", [("PE", False, 1 << 20), ("SE", True, 1 << 20), ("PE", False, 64 << 20)])
+def test_gzip_output_decompresses_to_the_oracle(tmp_path, layout, with_n, slab):
+    """gzip = 1: the FASTQ leaves the device as BGZF (independent gzip members of <= 32 KiB of text, dynamic-Huffman literals,
+    CRC-32 combined across the CTA). Decompressed it must be the oracle's bytes; every member is well formed, none holds more
+    than 32 KiB, the stream ends with the BGZF end-of-file marker; the same through the file sink (.fq.gz) and `gzip -dc`."""
+    import gzip
+    import subprocess
+    from scssim_b200 import api
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome_with_n(fa, 300_000, 77) if with_n else H.write_genome(fa, 1, 400_000, 29)
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, layout, 3e-10, 20.0, 260)
+    H.run_oracle(fa, os.path.join(tmp, "orc"), args, seed=5150)
+    want = [H.read_bytes(p) for p in H.fastq_names(os.path.join(tmp, "orc"), layout)]
+    with api.GenReads(gamma=3e-10, coverage=20.0, layout=layout, seed=5150, slab_bytes=slab, gzip=True, ring_slabs=3) as g:
+        g.load_profile(prof).load_genome(fa).create_frags().amplify()
+        got = g.yield_reads_bytes()
+        st = g.stats()
+        g.yield_reads(os.path.join(tmp, "gpu"))
+    eof = bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    for f, w in enumerate(want):
+        assert gzip.decompress(got[f]) == w
+        members = _bgzf_members(got[f])
+        assert members[-1][0] == eof and max(n for _, n in members) <= 32768 and sum(n for _, n in members) == len(w)
+        assert st["plain_bytes"][f] == len(w) and st["fastq_bytes"][f] == len(got[f]) and len(w) / len(got[f]) > 1.9
+    names = [os.path.join(tmp, "gpu_1.fq.gz"), os.path.join(tmp, "gpu_2.fq.gz")] if layout == "PE" else [os.path.join(tmp, "gpu.fq.gz")]
+    for p, w, gb in zip(names, want, got):
+        assert H.read_bytes(p) == gb
+        assert subprocess.run(["gzip", "-dc", p], capture_output=True, check=True).stdout == w
+
+
+def test_gzip_of_an_empty_output_is_a_valid_stream(tmp_path):
+    import gzip
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_sequence
+    prof = H.profile_path("Illumina_HiSeq2500")
+    with api.GenReads(gamma=2e-10, coverage=0.001, layout="SE", seed=5, gzip=True) as g:
+        g.load_profile(prof).set_genome([("chrA_1_60000", synth_sequence(60000, 3))]).create_frags().amplify()
+        got = g.yield_reads_bytes()
+    assert gzip.decompress(got[0]) == b""

@@ -232,6 +232,44 @@ def test_async_file_sink_ranks_share_one_file(tmp_path):
         assert open(p, "rb").read() == b"".join(parts)
 
 
+def test_deflate_code_of_a_profile_is_a_valid_dynamic_block():
+    """Host side of the block-gzip output (deflate_host.cpp): for every shipped profile the library's canonical Huffman code is
+    complete and <= 15 bits, covers every byte FASTQ text can hold, and its constant block prefix (BGZF member header + dynamic
+    Huffman header) followed by codes encoded here in Python is accepted by zlib and decodes to the input."""
+    import gzip
+    import zlib
+    text = (b"@123456#78/1\nACGTNACGTTTGACCA\n+\n!\"#$%&'()*+,-./0123456789:;<=>?@ABCDEFGHIJ~\n" * 40)
+    for prof, paired in [("Illumina_HiSeq2500", True), ("Illumina_HiSeqXTen", True), ("Illumina_GenomeAnalyzerIIx", False)]:
+        g = api.GenReads(device=-1, layout="PE" if paired else "SE")
+        g.load_profile(H.profile_path(prof))
+        lens, words, nbits = g.deflate_code()
+        lens = lens.astype(int)
+        assert lens.max() <= 15 and abs(sum(2.0 ** -l for l in lens if l) - 1.0) < 1e-12          # complete prefix code
+        for ch in b"\n#+/0123456789@ACGTN" + bytes(range(33, 127)):
+            assert lens[ch] > 0
+        assert lens[256] > 0 and lens[ord("A")] <= 4 and nbits % 1 == 0
+        # canonical codes (RFC 1951 3.2.2)
+        bl = np.bincount(lens, minlength=16); bl[0] = 0
+        code, nxt = 0, [0] * 17
+        for l in range(1, 16):
+            code = (code + bl[l - 1]) << 1; nxt[l] = code
+        codes = [0] * 257
+        for sym in range(257):
+            if lens[sym]:
+                codes[sym] = nxt[lens[sym]]; nxt[lens[sym]] += 1
+        bits = [(int(words[i >> 5]) >> (i & 31)) & 1 for i in range(nbits)]
+        for b in list(text) + [256]:
+            bits += [(codes[b] >> i) & 1 for i in range(lens[b] - 1, -1, -1)]
+        bits += [0] * (-len(bits) % 8)
+        out = bytearray(len(bits) // 8)
+        for i, b in enumerate(bits):
+            out[i >> 3] |= b << (i & 7)
+        out += zlib.crc32(text).to_bytes(4, "little") + len(text).to_bytes(4, "little")
+        out[16:18] = (len(out) - 1).to_bytes(2, "little")
+        assert gzip.decompress(bytes(out)) == text
+        g.close()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the arm the driver times beside ours): one JSON line with the contract's keys, produced by
     the compiled reference when it exists, else by the CPU oracle — on a tiny debug genome here."""
