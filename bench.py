@@ -397,9 +397,16 @@ def main():
             return 0
         sink_cb = api.SINK_FN(sink)
 
+        e2e_parts = {}
+
         def step_e2e():
-            g.set_genome(named).create_frags().amplify().set_read_counts()
-            g._ck(api.lib().scs_yield_reads_sink(g._h, sink_cb, None))
+            t = [time.perf_counter()]
+            g.set_genome(named); t.append(time.perf_counter())
+            g.create_frags(); t.append(time.perf_counter())
+            g.amplify().set_read_counts(); t.append(time.perf_counter())
+            g._ck(api.lib().scs_yield_reads_sink(g._h, sink_cb, None)); t.append(time.perf_counter())
+            for name, a0, a1 in zip(("set_genome_h2d_pack", "create_frags", "amplify_alloc", "reads_d2h_sink"), t, t[1:]):
+                e2e_parts[name] = round((a1 - a0) * 1e3, 1)
 
         weights_hist = []
         for _ in range(warmup):
@@ -551,7 +558,7 @@ def main():
                        "device_map": devmap, "share_of_reads_per_rank": [round(s / max(reads_all, 1), 4) for s in shares],
                        "shard_weight_history": weights_hist[-3:]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": config["genome_bases"], "d2h_bytes_per_step": bytes_all, "steps": e2e_steps,
-                    "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9, "this_rank_h2d_bytes": h2d_bytes},
+                    "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9, "this_rank_h2d_bytes": h2d_bytes, "last_step_ms_rank0": e2e_parts},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "emit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_launch": (alg_step / emit_launches_per_step) if emit_launches_per_step else None, "peak_source": peak_src,

@@ -968,6 +968,16 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     }
 
     StageGuard G(c);   // from here on every return drains the streams and frees the events
+    if (R.nslots == 0) {   // gzip of an empty output: the 28-byte end-of-file member, so that the file is a valid (empty) gzip stream
+        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        cudaEvent_t landed = G.make(cudaEventDisableTiming);
+        if (sink.acquire(0)) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        char* p[2] = {nullptr, nullptr}; uint64_t tot[2] = {0, 0};
+        for (int f = 0; f < nfiles; f++) { p[f] = c->ring_host[f][0] + (sink.phase(f) & 4095); memcpy(p[f], eof, 28); tot[f] = 28; c->stats.fastq_bytes[f] = 28; }
+        SCS_CUDA(c, cudaEventRecord(landed, c->st_copy));
+        if (sink.submit(0, landed, p, tot) || sink.finish()) return c->fail(SCS_E_IO, "FASTQ sink failed");
+        return SCS_OK;
+    }
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
     cudaEvent_t e0 = G.make(cudaEventDefault), e1 = G.make(cudaEventDefault);
     cudaEvent_t ecopy[2], ekern[2], etotb[2], tq[2][4]; bool timed[2] = {false, false};
@@ -984,15 +994,6 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         timed[b] = false;
     };
     SCS_CUDA(c, cudaEventRecord(e0, c->st));
-    if (R.nslots == 0) {   // gzip of an empty output: the 28-byte end-of-file member, so that the file is a valid (empty) gzip stream
-        static const uint8_t eof[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (sink.acquire(0)) return c->fail(SCS_E_IO, "FASTQ sink failed");
-        char* p[2] = {nullptr, nullptr}; uint64_t tot[2] = {0, 0};
-        for (int f = 0; f < nfiles; f++) { p[f] = c->ring_host[f][0] + (sink.phase(f) & 4095); memcpy(p[f], eof, 28); tot[f] = 28; c->stats.fastq_bytes[f] = 28; }
-        SCS_CUDA(c, cudaEventRecord(eslot[0], c->st_copy));
-        if (sink.submit(0, eslot[0], p, tot) || sink.finish()) return c->fail(SCS_E_IO, "FASTQ sink failed");
-        return SCS_OK;
-    }
     // ---- per slab: emit (staging + sizes) -> scans -> compaction into the packed device slab -> D2H into a pinned ring slot.
     // Software-pipelined on the host: slab k is launched before the host waits for the byte totals of slab k-1, so the kernels
     // run back to back; the consumer is serviced in between.
