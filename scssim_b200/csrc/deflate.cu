@@ -15,7 +15,7 @@ namespace scs {
 constexpr int kGzPiece = 32768;                 // uncompressed bytes per BGZF block (the format allows < 64 KiB compressed)
 constexpr int kGzThreads = 256;
 constexpr int kGzPerThread = kGzPiece / kGzThreads;   // 128
-constexpr int kGzOutWords = 16384;              // 64 KiB bit buffer: worst case 15 bits per byte + prefix + trailer
+constexpr int kGzOutWords = 6144;               // 24 KiB bit buffer (FASTQ deflates to ~16 KiB per piece); a piece that does not fit is stored
 static_assert(kGzPerThread == 128, "thread tile");
 
 __device__ __forceinline__ uint32_t gf2_multmodp(uint32_t a, uint32_t b) {   // a(x) * b(x) mod p(x), reflected CRC-32 polynomial
@@ -43,13 +43,13 @@ __global__ void __launch_bounds__(kGzThreads) deflate_pieces_kernel(const char* 
     extern __shared__ __align__(16) uint32_t sm[];
     uint32_t* outw = sm;
     uint32_t* scode = outw + kGzOutWords;   // 257 entries (+3 pad)
-    uint32_t* scrc = scode + 260;           // 256
-    uint32_t* sx2n = scrc + 256;            // 32
+    uint32_t* scrc = scode + 260;           // 4 x 256 (slicing-by-4)
+    uint32_t* sx2n = scrc + 1024;           // 32 powers x^(2^n) + 256 tile shifts x^(1024 j)
     __shared__ uint32_t s_warp[kGzThreads / 32], s_crcw[kGzThreads / 32], s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 257; i += kGzThreads) scode[i] = code_g[i];
-    for (int i = tid; i < 256; i += kGzThreads) scrc[i] = crc_g[i];
-    if (tid < 32) sx2n[tid] = x2n_g[tid];
+    for (int i = tid; i < 1024; i += kGzThreads) scrc[i] = crc_g[i];
+    for (int i = tid; i < 32 + 256; i += kGzThreads) sx2n[i] = x2n_g[i];
     const uint64_t in_total = nrec ? offs[nrec - 1] + (uint64_t)sizes[nrec - 1] : 0;
     const uint64_t n_pieces = (in_total + kGzPiece - 1) / kGzPiece;
     const uint32_t prefix_words = (prefix_bits + 31) >> 5;
@@ -75,16 +75,24 @@ __global__ void __launch_bounds__(kGzThreads) deflate_pieces_kernel(const char* 
             const uint4 x = __ldg(src + v);
             const uint32_t w4[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (16 * v + j < cnt) {
-                    const uint32_t b = (w4[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-                    const uint32_t c = scode[b];
-                    bits += c >> 24; bad |= (c >> 24) == 0;
-                    crc = scrc[(crc ^ b) & 0xFFu] ^ (crc >> 8);
+            for (int q = 0; q < 4; q++) {
+                const int left = cnt - (16 * v + 4 * q);   // bytes of this word that belong to the piece
+                if (left >= 4) {   // CRC four bytes per step: one dependent table level instead of four
+                    const uint32_t t = crc ^ w4[q];
+                    crc = scrc[768 + (t & 0xFFu)] ^ scrc[512 + ((t >> 8) & 0xFFu)] ^ scrc[256 + ((t >> 16) & 0xFFu)] ^ scrc[t >> 24];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (j < left) {
+                        const uint32_t b = (w4[q] >> (j * 8)) & 0xFFu;
+                        const uint32_t c = scode[b];
+                        bits += c >> 24; bad |= (c >> 24) == 0;
+                        if (left < 4) crc = scrc[(crc ^ b) & 0xFFu] ^ (crc >> 8);
+                    }
                 }
             }
         }
-        if (bad) atomicOr(flags, 32);   // a byte the run's Huffman code cannot express (cannot happen for FASTQ text)
+        bad = __syncthreads_or((int)bad);   // a byte the run's Huffman code cannot express (cannot happen for FASTQ text): the piece is stored
         // ---- exclusive scan of the bit counts over the CTA
         uint32_t inc = bits;
 #pragma unroll
@@ -105,7 +113,34 @@ __global__ void __launch_bounds__(kGzThreads) deflate_pieces_kernel(const char* 
         const uint32_t end_bits = prefix_bits + data_bits + (eob >> 24);
         const uint32_t nbytes = (end_bits + 7) >> 3, size = nbytes + 8;
         const uint32_t nwords = (size + 3) >> 2;
-        if (size > 65536u || nwords + 2 > (uint32_t)kGzOutWords) { if (tid == 0) { atomicOr(flags, 32); sizes_out[k] = 0; } __syncthreads(); continue; }
+        // ---- CRC-32 of the piece: crc(A || B) = crc(A) * x^(8|B|) + crc(B) (mod p), so every thread shifts its own and the CTA xors
+        // (the bytes after thread t are `tail` bytes of the last active thread plus whole 128-byte tiles: one table entry, two products)
+        uint32_t part = 0;
+        {
+            const int nact = (n + kGzPerThread - 1) / kGzPerThread, tail = n - (nact - 1) * kGzPerThread;
+            const uint32_t xtail = tail == kGzPerThread ? sx2n[32 + 1] : gf2_x8n_modp((uint32_t)tail, sx2n);
+            if (tid == nact - 1) part = crc ^ 0xFFFFFFFFu;
+            else if (tid < nact - 1) part = gf2_multmodp(gf2_multmodp(sx2n[32 + nact - 2 - tid], xtail), crc ^ 0xFFFFFFFFu);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s_crcw[warp] = part;
+        __syncthreads();
+        uint32_t crc_all = 0;
+#pragma unroll
+        for (int i = 0; i < kGzThreads / 32; i++) crc_all ^= s_crcw[i];
+        if (bad || nwords + 2 > (uint32_t)kGzOutWords) {
+            // ---- does not fit the bit buffer (or holds a byte without a code): a STORED deflate block — valid for any input
+            const uint32_t ssize = 18u + 5u + (uint32_t)n + 8u;
+            uint8_t* db = reinterpret_cast<uint8_t*>(dst);
+            if (tid < 18) { const uint8_t gz[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, (uint8_t)((ssize - 1) & 0xFFu), (uint8_t)((ssize - 1) >> 8)}; db[tid] = gz[tid]; }
+            if (tid == 18) { db[18] = 1; db[19] = (uint8_t)(n & 0xFF); db[20] = (uint8_t)(n >> 8); db[21] = (uint8_t)(~n & 0xFF); db[22] = (uint8_t)((~n >> 8) & 0xFF); }
+            for (int i = tid; i < n; i += kGzThreads) db[23 + i] = (uint8_t)in[start + i];
+            if (tid < 4) { db[23 + n + tid] = (uint8_t)(crc_all >> (8 * tid)); db[27 + n + tid] = (uint8_t)((uint32_t)n >> (8 * tid)); }
+            if (tid == 0) sizes_out[k] = ssize;
+            __syncthreads();
+            continue;
+        }
         // ---- bit buffer: zero, constant prefix (member header + dynamic-block header), then every thread's codes
         for (uint32_t i = tid; i < nwords + 2; i += kGzThreads) outw[i] = i < prefix_words ? prefix_g[i] : 0u;
         __syncthreads();
@@ -135,18 +170,10 @@ __global__ void __launch_bounds__(kGzThreads) deflate_pieces_kernel(const char* 
                 if ((uint32_t)(e >> 32)) atomicOr(outw + (eo >> 5) + 1, (uint32_t)(e >> 32));
             }
         }
-        // ---- CRC-32 of the piece: crc(A || B) = crc(A) * x^(8|B|) + crc(B) (mod p), so every thread shifts its own and the CTA xors
-        uint32_t part = 0;
-        if (cnt > 0) part = gf2_multmodp(gf2_x8n_modp((uint32_t)(n - (beg + cnt)), sx2n), crc ^ 0xFFFFFFFFu);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) s_crcw[warp] = part;
         __syncthreads();
         if (tid == 0) {
-            uint32_t c = 0;
-            for (int i = 0; i < kGzThreads / 32; i++) c ^= s_crcw[i];
             uint8_t* ob = reinterpret_cast<uint8_t*>(outw);
-            for (int i = 0; i < 4; i++) { ob[nbytes + i] = (uint8_t)(c >> (8 * i)); ob[nbytes + 4 + i] = (uint8_t)((uint32_t)n >> (8 * i)); }
+            for (int i = 0; i < 4; i++) { ob[nbytes + i] = (uint8_t)(crc_all >> (8 * i)); ob[nbytes + 4 + i] = (uint8_t)((uint32_t)n >> (8 * i)); }
             ob[16] = (uint8_t)((size - 1) & 0xFFu); ob[17] = (uint8_t)((size - 1) >> 8);   // BSIZE
             sizes_out[k] = size;
         }
@@ -165,8 +192,8 @@ int gz_prepare(scs_ctx* c) {
     uint64_t hist[257]; DeflateCode D;
     fastq_model_histogram(c->prof, c->P.paired != 0, hist);
     if (!build_deflate_code(hist, D)) return c->fail(SCS_E_STATE, "gzip: could not build the Huffman code");
-    uint32_t table[256], x2n[32]; crc32_tables(table, x2n);
-    SCS_CUDA(c, Z.code.reserve(260)); SCS_CUDA(c, Z.prefix.reserve(D.prefix_words.size() + 4)); SCS_CUDA(c, Z.crc.reserve(256)); SCS_CUDA(c, Z.x2n.reserve(32));
+    uint32_t table[1024], x2n[32 + 256]; crc32_tables(table, x2n);
+    SCS_CUDA(c, Z.code.reserve(260)); SCS_CUDA(c, Z.prefix.reserve(D.prefix_words.size() + 4)); SCS_CUDA(c, Z.crc.reserve(1024)); SCS_CUDA(c, Z.x2n.reserve(32 + 256));
     SCS_CUDA(c, memcpy_sync(c, Z.code.p, D.code, 257 * 4, cudaMemcpyHostToDevice));
     SCS_CUDA(c, memcpy_sync(c, Z.prefix.p, D.prefix_words.data(), D.prefix_words.size() * 4, cudaMemcpyHostToDevice));
     SCS_CUDA(c, memcpy_sync(c, Z.crc.p, table, sizeof(table), cudaMemcpyHostToDevice));
@@ -177,7 +204,7 @@ int gz_prepare(scs_ctx* c) {
     return SCS_OK;
 }
 
-size_t gz_smem_bytes() { return (size_t)(kGzOutWords + 260 + 256 + 32) * 4; }
+size_t gz_smem_bytes() { return (size_t)(kGzOutWords + 260 + 1024 + 32 + 256) * 4; }
 uint64_t gz_max_pieces(uint64_t slab_bytes) { return (slab_bytes + kGzPiece - 1) / kGzPiece + 1; }   // + the end-of-file marker
 uint64_t gz_stage_stride() { return 65536; }
 

@@ -135,8 +135,10 @@ void fastq_model_histogram(const HostProfile& P, bool paired, uint64_t hist[257]
     for (int s = 0; s < 257; s++) hist[s] = h[s] > 0 ? (uint64_t)std::max(1.0, std::floor(h[s] * 1e6)) : 0;
 }
 
-void crc32_tables(uint32_t table[256], uint32_t x2n[32]) {
+void crc32_tables(uint32_t table[1024], uint32_t x2n[32 + 256]) {
+    // slicing-by-4: table[k*256 + i] = CRC of byte i followed by k zero bytes
     for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1; table[i] = c; }
+    for (int k = 1; k < 4; k++) for (uint32_t i = 0; i < 256; i++) table[k * 256 + i] = (table[(k - 1) * 256 + i] >> 8) ^ table[table[(k - 1) * 256 + i] & 0xFFu];
     auto multmodp = [](uint32_t a, uint32_t b) {
         uint32_t m = 1u << 31, p = 0;
         for (;;) { if (a & m) { p ^= b; if ((a & (m - 1)) == 0) break; } m >>= 1; b = (b & 1u) ? (b >> 1) ^ 0xEDB88320u : b >> 1; }
@@ -145,6 +147,10 @@ void crc32_tables(uint32_t table[256], uint32_t x2n[32]) {
     uint32_t p = 1u << 30;   // x^1
     x2n[0] = p;
     for (int n = 1; n < 32; n++) x2n[n] = p = multmodp(p, p);
+    // x2n[32 + j] = x^(8 * 128 * j) mod p: what a thread's CRC is multiplied with when j full 128-byte thread tiles follow it
+    x2n[32] = 1u << 31;   // x^0
+    const uint32_t x1024 = x2n[10];   // x^(2^10)
+    for (int j = 1; j < 256; j++) x2n[32 + j] = multmodp(x2n[32 + j - 1], x1024);
 }
 
 }  // namespace scs

@@ -25,7 +25,9 @@ struct DeflateCode {
 bool build_deflate_code(const uint64_t hist[257], DeflateCode& out);
 // expected byte histogram of one FASTQ record of this profile (scaled to integers); every byte a record can contain is > 0
 void fastq_model_histogram(const HostProfile& P, bool paired, uint64_t hist[257]);
-// the table behind the reflected CRC-32 (polynomial 0xEDB88320) and x^(2^n) mod p for the block combine (zlib's crc32_combine)
-void crc32_tables(uint32_t table[256], uint32_t x2n[32]);
+// slicing-by-4 tables of the reflected CRC-32 (polynomial 0xEDB88320; [0..255] is the classic byte table) and x^(2^n) mod p for
+// the block combine (zlib's crc32_combine)
+// ([0..31]; [32 + j] = x^(1024 j) mod p, the shift over j thread tiles of 128 bytes)
+void crc32_tables(uint32_t table[1024], uint32_t x2n[32 + 256]);
 
 }  // namespace scs
