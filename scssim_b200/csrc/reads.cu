@@ -36,12 +36,13 @@ constexpr int kEmitWarps = SCS_EMIT_WARPS;   // warps per persistent CTA of the 
 constexpr int kDiagW = 40;            // entries per compact quality row kept in shared memory (shipped profiles need <= 39)
 constexpr int kDiagStride = 44;       // words per row: 40 + 4 pad; 44*r mod 32 is a distinct multiple of 4 for 8 neighbouring rows,
                                       // so their 128-bit loads are bank-conflict free
-constexpr int kRLCap = 256;           // max profile read length handled by the kernels
-constexpr int kSrcCap = 384;          // max read length after insertions (overflow -> error flag)
-constexpr int kMaxEvents = 32;        // indel events per read kept in shared memory
+constexpr int kRLCap = 320;           // max profile read length handled by the kernels (Illumina tops out at 2 x 300)
+constexpr int kSrcCap = 480;          // max read length after insertions (overflow -> error flag)
+constexpr int kMaxEvents = 64;        // indel events per read kept in shared memory
 constexpr int kRecCap = 16 + 40 + 2 * kSrcCap + 8;
-constexpr int kWinBytes = 96;         // staged 2-bit window of one mate: kRLCap bases (64 B) + 16-byte alignment skirts on both sides
-constexpr int kWinNBytes = 64;        // staged N-mask window of one mate: kRLCap bits (32 B) + skirts
+constexpr int kWinBytes = 96;         // staged 2-bit window of one mate: kRLCap bases (80 B) + up to 15 B in front, rounded to 16
+constexpr int kWinNBytes = 64;        // staged N-mask window of one mate: kRLCap bits (40 B) + up to 15 B in front, rounded to 16
+static_assert(15 + (kRLCap + 2) / 4 + 16 <= kWinBytes + 15 && 15 + (kRLCap + 6) / 8 + 16 <= kWinNBytes + 15, "window staging too small for kRLCap");
 constexpr int kCoarseShift = 10;      // coarse slot -> amplicon index: one entry per 1024 slots
 constexpr int kISizeSmemCap = 4096;   // insert-size thresholds kept in shared memory (longer tables stay in global memory)
 
@@ -84,8 +85,8 @@ struct SlotPlan {
     int32_t valid;
 };
 
-struct WarpScratch {
-    uint8_t ref[kRLCap];
+struct __align__(16) WarpScratch {
+    uint8_t ref[kRLCap + 16];   // + slack: the 4-bases-per-lane decode stores whole words
     uint8_t src[kSrcCap];
     char rec[kRecCap];
     int16_t ev_pos[kMaxEvents]; int16_t ev_len[kMaxEvents]; uint32_t ev_ci[kMaxEvents];
@@ -550,16 +551,33 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         const uint8_t* __restrict__ win = st->win[buf][mate - 1];
         __syncwarp();
         bool myN = false;
-        if (need_bases) for (int i = lane; i < RL; i += 32) {
+        if (need_bases && !g.has_n) {
+            // four bases per lane and step: the (up to) two staged bytes that hold them, one shift, 8 bits spread into 4 bytes, one
+            // 32-bit store. Backwards windows take the four bases below their highest offset, reversed and complemented.
+            for (int i0 = 4 * lane; i0 < RL; i0 += 128) {
+                uint32_t t;
+                if (!rev) {
+                    const uint32_t q0 = off + (uint32_t)i0, B = q0 >> 2;
+                    SCS_CHECK(B < (uint32_t)kWinBytes);
+                    const uint32_t v = ((uint32_t)win[B] | ((uint32_t)win[B + 1] << 8)) >> ((q0 & 3u) * 2u);
+                    t = ((v & 0xFFu) | ((v & 0xFFu) << 12)) & 0x000F000Fu; t = (t | (t << 6)) & 0x03030303u;
+                } else {
+                    const uint32_t qh = off + (uint32_t)(RL - 1 - i0), B1 = qh >> 2, B0 = B1 ? B1 - 1 : 0;   // offsets below 0 only feed positions >= RL
+                    SCS_CHECK(B1 < (uint32_t)kWinBytes);
+                    const uint32_t v = (((uint32_t)win[B0] | ((uint32_t)win[B1] << 8)) >> ((qh & 3u) * 2u + 2u)) & 0xFFu;
+                    t = (v | (v << 12)) & 0x000F000Fu; t = (t | (t << 6)) & 0x03030303u;
+                    t = __byte_perm(t, 0, 0x0123) ^ 0x03030303u;
+                }
+                *reinterpret_cast<uint32_t*>(ws->ref + i0) = t;   // may run up to 3 bytes past RL inside ref[kRLCap]: never read
+            }
+        } else if (need_bases) for (int i = lane; i < RL; i += 32) {
             const uint32_t q = off + (uint32_t)(rev ? (RL - 1 - i) : i);
             SCS_CHECK((q >> 2) < (uint32_t)kWinBytes && i < kRLCap);
             uint32_t b = ((uint32_t)win[q >> 2] >> ((q & 3u) * 2u)) & 3u;
             if (rev) b ^= 3u;
-            if (g.has_n) {
-                const uint32_t qn = P.noff[mate - 1] + (uint32_t)(rev ? (RL - 1 - i) : i);
-                SCS_CHECK((qn >> 3) < (uint32_t)kWinNBytes);
-                if ((st->winn[buf][mate - 1][qn >> 3] >> (qn & 7u)) & 1u) { b = 4u; myN = true; }
-            }
+            const uint32_t qn = P.noff[mate - 1] + (uint32_t)(rev ? (RL - 1 - i) : i);
+            SCS_CHECK((qn >> 3) < (uint32_t)kWinNBytes);
+            if ((st->winn[buf][mate - 1][qn >> 3] >> (qn & 7u)) & 1u) { b = 4u; myN = true; }
             ws->ref[i] = (uint8_t)b;
         }
         __syncwarp();
@@ -611,11 +629,11 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
 template <bool SIZE_ONLY, bool REPLAY>
 __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, char* __restrict__ out1, char* __restrict__ out2,
                                                                   int* flags, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
-                                                                  unsigned long long* __restrict__ records, int isize_smem) {
+                                                                  unsigned long long* __restrict__ records, int isize_smem, int diag_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = (int)(blockDim.x >> 5);   // <= kEmitWarps: long-read profiles leave room for fewer warp scratch areas
-    const int nrows = 4 * T.RL;
+    const int nrows = diag_smem ? 4 * T.RL : 0;  // very long reads: the diagonal quality tables stay in global memory (L2)
     uint32_t* srows = reinterpret_cast<uint32_t*>(smem_raw);
     uint4* spiv = reinterpret_cast<uint4*>(srows + (size_t)nrows * kDiagStride);
     uint32_t* smeta = reinterpret_cast<uint32_t*>(spiv + nrows);
@@ -820,7 +838,7 @@ namespace {
 struct ReadRun {
     ReadTables T; Genome g; DrawSrc dsrc; SlabArgs A;
     uint64_t slot_lo = 0, slot_hi = 0, nslots = 0, slab = 0, stride = 0, batch = 0;
-    int nfiles = 1, sms = 148, emit_warps = kEmitWarps, isize_smem = 0; size_t emit_smem = 0;
+    int nfiles = 1, sms = 148, emit_warps = kEmitWarps, isize_smem = 0, diag_smem = 1; size_t emit_smem = 0;
 };
 }  // namespace
 
@@ -828,7 +846,7 @@ static int prepare_read_run(scs_ctx* c, ReadRun& R) {
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_yield_reads: no profile loaded");
     if (!c->have_counts) { if (int rc = set_read_counts(c)) return rc; }
     const HostProfile& P = c->prof;
-    if (P.readLength > kRLCap) return c->fail(SCS_E_UNSUPPORTED, "read length above 256 is not supported by the kernels");
+    if (P.readLength > kRLCap) return c->fail(SCS_E_UNSUPPORTED, "read length above 320 is not supported by the kernels");
     if (c->P.paired && !P.hasISize) return c->fail(SCS_E_ARG, "Error: unrecognized parameter name \"insertSize\"");   // Profile.cpp:1484 -> Config.cpp:71-78
     // what this rank reads from: its own amplicons and genome, or (balance = 1) the cell-wide copies and a slot range
     const bool gv = c->global_view;
@@ -836,7 +854,7 @@ static int prepare_read_run(scs_ctx* c, ReadRun& R) {
     R.nfiles = c->P.paired ? 2 : 1;
     R.slab = c->P.slab_bytes ? c->P.slab_bytes : (64ull << 20);
     R.stride = ((uint64_t)kRecCap + 15) & ~15ull;
-    if (R.slab < 64 * R.stride) return c->fail(SCS_E_ARG, "slab_bytes is too small (needs room for 64 records of the largest size, 53 KiB)");
+    if (R.slab < 64 * R.stride) return c->fail(SCS_E_ARG, "slab_bytes is too small (needs room for 64 records of the largest size, 64 KiB)");
     if (R.nslots == 0) return SCS_OK;
     // slots per slab: typical record = header (<= 30) + 2*(RL + a few inserted bases) + 4. A batch whose records are longer than
     // that on average (heavy insertion profiles) can exceed the slab: the compaction kernel then skips the records that do not
@@ -866,10 +884,14 @@ static int prepare_read_run(scs_ctx* c, ReadRun& R) {
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sms, cudaDevAttrMultiProcessorCount, dev);
     // shared memory of a persistent emit CTA: the diagonal quality tables, the insert-size thresholds, and per warp a scratch area
     // plus the TMA staging of its next two slots; as many warps (<= 24) as fit
-    const size_t table_smem = (size_t)4 * R.T.RL * kDiagStride * 4 + (size_t)4 * R.T.RL * 16 + (size_t)((4 * R.T.RL + 3) & ~3) * 4;
+    size_t table_smem = (size_t)4 * R.T.RL * kDiagStride * 4 + (size_t)4 * R.T.RL * 16 + (size_t)((4 * R.T.RL + 3) & ~3) * 4;
     int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     R.isize_smem = (c->P.paired && R.T.isizeEff <= kISizeSmemCap) ? R.T.isizeEff : 0;
-    const size_t fixed_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4, per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
+    const size_t per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
+    // read lengths whose diagonal quality tables leave room for fewer than 12 warps (beyond ~230 bases): the tables stay in L2
+    R.diag_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4 + 12 * per_warp <= (size_t)smem_max ? 1 : 0;
+    if (!R.diag_smem) table_smem = 0;
+    const size_t fixed_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4;
     R.emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(fixed_smem, (size_t)smem_max)) / per_warp);
     if (R.emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
     R.emit_smem = fixed_smem + per_warp * (size_t)R.emit_warps;
@@ -919,15 +941,15 @@ int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]) {
         R.A.slot0 = s0; R.A.nslots = m;
         SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
         if (R.nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
-        emit_kernel<true, false><<<R.sms, R.emit_warps * 32, R.emit_smem, c->st>>>(R.g, R.dsrc, R.T, R.A, nullptr, nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p, R.isize_smem);
+        emit_kernel<true, false><<<R.sms, R.emit_warps * 32, R.emit_smem, c->st>>>(R.g, R.dsrc, R.T, R.A, nullptr, nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p, R.isize_smem, R.diag_smem);
         SCS_LAUNCHED(c);
         sum_sizes_kernel<<<R.sms, 256, 0, c->st>>>(W.size1.p, R.nfiles == 2 ? W.size2.p : nullptr, m, reinterpret_cast<unsigned long long*>(W.totals.p)); SCS_LAUNCHED(c);
     }
     uint64_t h[2] = {0, 0}; int hflags = 0;
     SCS_CUDA(c, memcpy_sync(c, h, W.totals.p, 16, cudaMemcpyDeviceToHost));
     SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
-    if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
-    if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
+    if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 64 indel events in one read");
+    if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 480 bases through insertions");
     bytes[0] = h[0]; bytes[1] = h[1];
     return SCS_OK;
 }
@@ -1032,7 +1054,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         SCS_CUDA(c, cudaEventRecord(tq[b][1], c->st));
         auto kern = c->replay.on ? emit_kernel<false, true> : emit_kernel<false, false>;
         kern<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p,
-                                                         isize_smem);
+                                                         isize_smem, R.diag_smem);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
         uint64_t* plain_tot = W.dtotals_mapped + (gz ? 4 : 0) + 2 * b;   // with gzip the copy sizes (slots 0..3) are the compressed totals
@@ -1079,8 +1101,8 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     c->stats.ms_reads = ms; c->stats.ms_reads_kernels = msk; c->stats.ms_emit_kernel = mse;
     int hflags = 0; SCS_CUDA(c, memcpy_sync(c, &hflags, W.flags.p, 4, cudaMemcpyDeviceToHost));
     unsigned long long hrec = 0; SCS_CUDA(c, memcpy_sync(c, &hrec, W.records.p, 8, cudaMemcpyDeviceToHost)); c->stats.records = hrec;
-    if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 32 indel events in one read");
-    if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 384 bases through insertions");
+    if (hflags & 4) return c->fail(SCS_E_UNSUPPORTED, "more than 64 indel events in one read");
+    if (hflags & 8) return c->fail(SCS_E_UNSUPPORTED, "read grew beyond 480 bases through insertions");
     if (hflags & 16) return c->fail(SCS_E_NOMEM, "FASTQ slab overflow (raise slab_bytes)");
     if (hflags & 32) return c->fail(SCS_E_STATE, "gzip: a byte outside the FASTQ alphabet or an oversized block");
     return SCS_OK;
@@ -1123,7 +1145,7 @@ int test_predict(scs_ctx* c, const char* src, int n_reads, int is_read1, const u
     if (!c->have_device) return c->fail(SCS_E_CUDA, "no CUDA device");
     if (!c->have_profile) return c->fail(SCS_E_STATE, "scs_test_predict: no profile loaded");
     const int RL = c->prof.readLength;
-    if (RL > kRLCap) return c->fail(SCS_E_UNSUPPORTED, "read length above 256");
+    if (RL > kRLCap) return c->fail(SCS_E_UNSUPPORTED, "read length above 320");
     DevBuf<char> dsrc, dseq, dqual; DevBuf<uint32_t> dreal, dint; DevBuf<int> dlen, flags;
     SCS_CUDA(c, dsrc.reserve((size_t)n_reads * RL + 16)); SCS_CUDA(c, dseq.reserve((size_t)n_reads * out_stride + 16)); SCS_CUDA(c, dqual.reserve((size_t)n_reads * out_stride + 16));
     SCS_CUDA(c, dreal.reserve((size_t)n_reads * stride_real + 4096)); SCS_CUDA(c, dint.reserve((size_t)n_reads * stride_int + 4096));

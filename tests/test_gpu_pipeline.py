@@ -143,7 +143,8 @@ def test_slabs_with_n_genome_equal_the_oracle(tmp_path):
 # ---- the tables bench.py runs on (read length is a property of the .profile: the bench derives 150- / 100-bin profiles by
 # ---- nearest-bin resampling; the oracle reads the same derived file). RL 150 is also the largest shared-memory footprint.
 @pytest.mark.parametrize("src,rl,layout,isize", [("Illumina_HiSeq2500", 150, "PE", 260), ("Illumina_HiSeqXTen", 100, "PE", 260),
-                                                 ("Illumina_HiSeq2500", 150, "SE", 260), ("Illumina_HiSeq2500", 250, "PE", 400)])
+                                                 ("Illumina_HiSeq2500", 150, "SE", 260), ("Illumina_HiSeq2500", 250, "PE", 400),
+                                                 ("Illumina_HiSeqXTen", 300, "PE", 500)])   # 250 / 300: the quality tables no longer fit shared memory
 def test_resampled_bench_profiles_equal_the_oracle(tmp_path, src, rl, layout, isize):
     from scssim_b200.tools.resample_profile import resample
     prof = os.path.join(str(tmp_path), f"{src}_{rl}.profile")
