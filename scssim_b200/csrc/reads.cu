@@ -268,6 +268,7 @@ __device__ __forceinline__ int sample_quality(const PassTabs& X, uint32_t b0, ui
         }
     }
     const size_t row = (size_t)(b0 * 4u + k) * X.bins + bin;
+    SCS_CHECK(b0 < 4u && k < 4u && bin >= 0 && bin < X.bins && X.qualEff[row] <= kQualN);
     return count_le(X.qual + row * kQualN, (int)X.qualEff[row], xq);
 }
 
@@ -629,11 +630,11 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
 template <bool SIZE_ONLY, bool REPLAY>
 __global__ void __launch_bounds__(kEmitWarps * 32, 1) emit_kernel(Genome g, DrawSrc dsrc, ReadTables T, SlabArgs A, char* __restrict__ out1, char* __restrict__ out2,
                                                                   int* flags, uint32_t* __restrict__ size1, uint32_t* __restrict__ size2,
-                                                                  unsigned long long* __restrict__ records, int isize_smem, int diag_smem) {
+                                                                  unsigned long long* __restrict__ records, int isize_smem) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = (int)(blockDim.x >> 5);   // <= kEmitWarps: long-read profiles leave room for fewer warp scratch areas
-    const int nrows = diag_smem ? 4 * T.RL : 0;  // very long reads: the diagonal quality tables stay in global memory (L2)
+    const int nrows = 4 * T.RL;
     uint32_t* srows = reinterpret_cast<uint32_t*>(smem_raw);
     uint4* spiv = reinterpret_cast<uint4*>(srows + (size_t)nrows * kDiagStride);
     uint32_t* smeta = reinterpret_cast<uint32_t*>(spiv + nrows);
@@ -838,7 +839,7 @@ namespace {
 struct ReadRun {
     ReadTables T; Genome g; DrawSrc dsrc; SlabArgs A;
     uint64_t slot_lo = 0, slot_hi = 0, nslots = 0, slab = 0, stride = 0, batch = 0;
-    int nfiles = 1, sms = 148, emit_warps = kEmitWarps, isize_smem = 0, diag_smem = 1; size_t emit_smem = 0;
+    int nfiles = 1, sms = 148, emit_warps = kEmitWarps, isize_smem = 0; size_t emit_smem = 0;
 };
 }  // namespace
 
@@ -884,16 +885,14 @@ static int prepare_read_run(scs_ctx* c, ReadRun& R) {
     int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&R.sms, cudaDevAttrMultiProcessorCount, dev);
     // shared memory of a persistent emit CTA: the diagonal quality tables, the insert-size thresholds, and per warp a scratch area
     // plus the TMA staging of its next two slots; as many warps (<= 24) as fit
-    size_t table_smem = (size_t)4 * R.T.RL * kDiagStride * 4 + (size_t)4 * R.T.RL * 16 + (size_t)((4 * R.T.RL + 3) & ~3) * 4;
+    const size_t table_smem = (size_t)4 * R.T.RL * kDiagStride * 4 + (size_t)4 * R.T.RL * 16 + (size_t)((4 * R.T.RL + 3) & ~3) * 4;
     int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     R.isize_smem = (c->P.paired && R.T.isizeEff <= kISizeSmemCap) ? R.T.isizeEff : 0;
     const size_t per_warp = sizeof(WarpScratch) + sizeof(WarpStage);
-    // read lengths whose diagonal quality tables leave room for fewer than 12 warps (beyond ~230 bases): the tables stay in L2
-    R.diag_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4 + 12 * per_warp <= (size_t)smem_max ? 1 : 0;
-    if (!R.diag_smem) table_smem = 0;
     const size_t fixed_smem = table_smem + (size_t)((R.isize_smem + 3) & ~3) * 4;
+    // the diagonal quality tables grow with the read length: beyond ~190 bases fewer than 24 warps fit beside them, beyond ~275 none
     R.emit_warps = (int)std::min<size_t>(kEmitWarps, ((size_t)smem_max - std::min<size_t>(fixed_smem, (size_t)smem_max)) / per_warp);
-    if (R.emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "profile tables do not fit the shared memory of the read kernel");
+    if (R.emit_warps < 4) return c->fail(SCS_E_UNSUPPORTED, "read length too large: the quality tables of the profile do not fit the shared memory of the read kernel");
     R.emit_smem = fixed_smem + per_warp * (size_t)R.emit_warps;
     SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.emit_smem));
     SCS_CUDA(c, cudaFuncSetAttribute(emit_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R.emit_smem));
@@ -941,7 +940,7 @@ int plan_fastq_bytes(scs_ctx* c, uint64_t bytes[2]) {
         R.A.slot0 = s0; R.A.nslots = m;
         SCS_CUDA(c, cudaMemsetAsync(W.size1.p, 0, (m + 1) * 4, c->st));
         if (R.nfiles == 2) SCS_CUDA(c, cudaMemsetAsync(W.size2.p, 0, (m + 1) * 4, c->st));
-        emit_kernel<true, false><<<R.sms, R.emit_warps * 32, R.emit_smem, c->st>>>(R.g, R.dsrc, R.T, R.A, nullptr, nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p, R.isize_smem, R.diag_smem);
+        emit_kernel<true, false><<<R.sms, R.emit_warps * 32, R.emit_smem, c->st>>>(R.g, R.dsrc, R.T, R.A, nullptr, nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p, R.isize_smem);
         SCS_LAUNCHED(c);
         sum_sizes_kernel<<<R.sms, 256, 0, c->st>>>(W.size1.p, R.nfiles == 2 ? W.size2.p : nullptr, m, reinterpret_cast<unsigned long long*>(W.totals.p)); SCS_LAUNCHED(c);
     }
@@ -1054,7 +1053,7 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         SCS_CUDA(c, cudaEventRecord(tq[b][1], c->st));
         auto kern = c->replay.on ? emit_kernel<false, true> : emit_kernel<false, false>;
         kern<<<sms, emit_warps * 32, emit_smem, c->st>>>(g, dsrc, T, A, W.stage[0].p, nfiles == 2 ? W.stage[1].p : nullptr, W.flags.p, W.size1.p, W.size2.p, W.records.p,
-                                                         isize_smem, R.diag_smem);
+                                                         isize_smem);
         SCS_LAUNCHED(c); c->stats.emit_launches++;
         SCS_CUDA(c, cudaEventRecord(tq[b][2], c->st));
         uint64_t* plain_tot = W.dtotals_mapped + (gz ? 4 : 0) + 2 * b;   // with gzip the copy sizes (slots 0..3) are the compressed totals

@@ -143,14 +143,27 @@ def test_slabs_with_n_genome_equal_the_oracle(tmp_path):
 # ---- the tables bench.py runs on (read length is a property of the .profile: the bench derives 150- / 100-bin profiles by
 # ---- nearest-bin resampling; the oracle reads the same derived file). RL 150 is also the largest shared-memory footprint.
 @pytest.mark.parametrize("src,rl,layout,isize", [("Illumina_HiSeq2500", 150, "PE", 260), ("Illumina_HiSeqXTen", 100, "PE", 260),
-                                                 ("Illumina_HiSeq2500", 150, "SE", 260), ("Illumina_HiSeq2500", 250, "PE", 400),
-                                                 ("Illumina_HiSeqXTen", 300, "PE", 500)])   # 250 / 300: the quality tables no longer fit shared memory
+                                                 ("Illumina_HiSeq2500", 150, "SE", 260), ("Illumina_HiSeq2500", 250, "PE", 400)])   # 250: fewer warps per CTA
 def test_resampled_bench_profiles_equal_the_oracle(tmp_path, src, rl, layout, isize):
     from scssim_b200.tools.resample_profile import resample
     prof = os.path.join(str(tmp_path), f"{src}_{rl}.profile")
     resample(H.profile_path(src), prof, rl)
     st = _run_case(str(tmp_path), f"res{rl}{layout}", 1, 400_000, 13, prof, layout, 2e-10, 6.0, isize, seed=150 + rl, slab_bytes=256 << 10, min_slabs=3)
     assert st["records"] > 0
+
+
+def test_read_length_beyond_the_kernel_limit_is_a_clean_error(tmp_path):
+    """Profiles whose quality tables do not fit shared memory (read length ~275+; the shipped profiles are 74-151) are refused."""
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_sequence
+    from scssim_b200.tools.resample_profile import resample
+    prof = os.path.join(str(tmp_path), "p300.profile")
+    resample(H.profile_path("Illumina_HiSeqXTen"), prof, 300)
+    with api.GenReads(gamma=2e-10, coverage=4.0, isize=500, layout="PE", seed=3) as g:
+        g.load_profile(prof).set_genome([("chrA_1_200000", synth_sequence(200_000, 5))]).create_frags().amplify()
+        with pytest.raises(api.ScsError) as e:
+            g.yield_reads_bytes()
+        assert e.value.code == api.SCS_E_UNSUPPORTED
 
 
 def test_slab_limits_are_clean_errors(tmp_path):
