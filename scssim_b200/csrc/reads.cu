@@ -30,7 +30,7 @@ __device__ __noinline__ void philox4x32_10_call(uint32_t c0, uint32_t c1, uint32
 
 constexpr int kReadWarps = 8;         // warps per CTA (test kernels)
 #ifndef SCS_EMIT_WARPS
-#define SCS_EMIT_WARPS 24
+#define SCS_EMIT_WARPS 28
 #endif
 constexpr int kEmitWarps = SCS_EMIT_WARPS;   // warps per persistent CTA of the emit kernel (one CTA per SM); tuning: profiles/ab_warps.sh
 constexpr int kDiagW = 40;            // entries per compact quality row kept in shared memory (shipped profiles need <= 39)
