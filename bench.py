@@ -198,66 +198,72 @@ def synth_chromosome_cuda(torch, length, seed, device, out_h1, out_h2):
     torch.cuda.empty_cache()
 
 
-def probe_host_pipes(torch, ndev):
-    """Which GPUs share a host link? Concurrent pinned D2H from device 0 and device j: if the pair moves clearly more than device
-    0 alone, j sits behind another host pipe. Returns (device order that alternates between the groups, probe record)."""
+def probe_host_links(torch, ndev):
+    """Pinned D2H rate of every GPU's host link, each GPU alone and all GPUs at once (one process, one stream per device). Returns
+    (device order: best-connected first, probe record). On this pool's 8-GPU boxes the links are far from equal: GPUs 4-7 keep
+    44 GB/s each when they copy together, GPUs 0-3 share ~73 GB/s and drag the whole box down to ~123 GB/s when all eight copy."""
     nb = 128 << 20
     bufs = {}
     for j in range(ndev):
         with torch.cuda.device(j):
-            bufs[j] = (torch.empty(nb, dtype=torch.uint8, device=f"cuda:{j}"), torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.cuda.Stream(device=j))
+            bufs[j] = (torch.empty(nb, dtype=torch.uint8, device=f"cuda:{j}"), torch.empty(nb, dtype=torch.uint8, pin_memory=True), torch.cuda.Stream(device=j),
+                       torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
     def run(devs, reps=3):
         for j in devs:
-            d, h, s = bufs[j]
-            with torch.cuda.stream(s):
+            d, h, s, _, _ = bufs[j]
+            with torch.cuda.device(j), torch.cuda.stream(s):
                 h.copy_(d, non_blocking=True)
         for j in devs:
             bufs[j][2].synchronize()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            for j in devs:
-                d, h, s = bufs[j]
-                with torch.cuda.stream(s):
+        for j in devs:
+            d, h, s, e0, e1 = bufs[j]
+            with torch.cuda.device(j), torch.cuda.stream(s):
+                e0.record(s)
+                for _ in range(reps):
                     h.copy_(d, non_blocking=True)
+                e1.record(s)
+        out = {}
         for j in devs:
             bufs[j][2].synchronize()
-        return reps * nb * len(devs) / (time.perf_counter() - t0) / 1e9
-    single = run([0])
-    pair = {j: run([0, j]) for j in range(1, ndev)}
-    other = [j for j in range(1, ndev) if pair[j] > 1.5 * single]
-    same = [0] + [j for j in range(1, ndev) if j not in other]
-    order = []
-    for i in range(max(len(same), len(other))):
-        if i < len(same):
-            order.append(same[i])
-        if i < len(other):
-            order.append(other[i])
-    rec = {"single_GBps": round(single, 1), "pair_with_gpu0_GBps": {str(j): round(v, 1) for j, v in pair.items()}, "groups": [same, other]}
+            out[j] = reps * nb / (bufs[j][3].elapsed_time(bufs[j][4]) / 1e3) / 1e9
+        return out
+    single = {j: run([j])[j] for j in range(ndev)}
+    together = run(list(range(ndev)))
+    order = sorted(range(ndev), key=lambda j: (-round(together[j]), -round(single[j]), j))
+    rec = {"alone_GBps": [round(single[j], 1) for j in range(ndev)], "all_at_once_GBps": [round(together[j], 1) for j in range(ndev)]}
     del bufs
     torch.cuda.empty_cache()
     return order, rec
 
 
 def device_for_rank(torch, local, world):
-    """Topology-aware device order for N < all GPUs: local ranks alternate between the host pipes that the probe finds, so two or
-    four ranks do not crowd behind one of them. Rank 0 probes and publishes the order; the other ranks read it."""
+    """Device order by measured host-link quality (the path is bound by the D2H copy of its output): local rank r runs on the r-th
+    best-connected GPU. Local rank 0 probes and publishes the order; the other ranks read it."""
     ndev = torch.cuda.device_count()
-    if world <= 1 or world >= ndev or os.environ.get("SCS_BENCH_NO_DEVMAP"):
+    if ndev <= 1 or world > ndev or os.environ.get("SCS_BENCH_NO_DEVMAP"):
         return local, {"order": list(range(ndev)), "probe": None}
-    path = os.path.join(tempfile.gettempdir(), f"scs_devmap_{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}.json")
+    if world == 1:
+        order, rec = probe_host_links(torch, ndev)
+        return order[0], {"order": order, "probe": rec}
+    path = os.path.join(tempfile.gettempdir(), f"scs_devmap_{os.environ.get('MASTER_PORT', '0')}_{world}_{os.environ.get('TORCHELASTIC_RUN_ID', 'x')}.json")
     if local == 0:
-        order, rec = probe_host_pipes(torch, ndev)
+        order, rec = probe_host_links(torch, ndev)
         with open(path + ".tmp", "w") as f:
-            json.dump({"order": order, "probe": rec}, f)
+            json.dump({"order": order, "probe": rec, "t": time.time()}, f)
         os.replace(path + ".tmp", path)
     t0 = time.time()
-    while not os.path.exists(path) and time.time() - t0 < 120:
+    m = None
+    while time.time() - t0 < 180:
+        try:
+            with open(path) as f:
+                m = json.load(f)
+            if time.time() - m.get("t", 0) < 600:   # not a leftover of an earlier run on this box
+                break
+        except (OSError, ValueError):
+            pass
         time.sleep(0.05)
-    try:
-        with open(path) as f:
-            m = json.load(f)
-    except (OSError, ValueError):
+    if m is None:
         m = {"order": list(range(ndev)), "probe": "unavailable"}
     return m["order"][local], m
 
@@ -273,6 +279,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="(debug) skip the CPU leg")
     ap.add_argument("--no-extras", action="store_true", help="(debug) skip the configs[1] and e2e_files legs")
     ap.add_argument("--no-balance", action="store_true", help="(debug) N > 1: every rank writes the reads of its own amplicons")
+    ap.add_argument("--no-relay", action="store_true", help="(debug) never route a GPU's output through a better-connected peer GPU")
     ap.add_argument("--slab-mb", type=int, default=64, help="FASTQ staging slab per file and buffer (MiB)")
     ap.add_argument("--files-dir", default=None, help="directory for the e2e_files leg (default: the system temp dir)")
     ap.add_argument("--gz", action="store_true", help="(not the headline) block-gzip output on the device: compressed FASTQ lands in the pinned ring")
@@ -366,14 +373,26 @@ def main():
         d2h_single = gather_f64(d2h_rate(rank == 0))[0]
         d2h_per_rank = gather_f64(d2h_rate(True))
         d2h_peak = sum(d2h_per_rank)
+        # GPUs behind a clearly slower host link (on this pool's 8-GPU boxes: GPUs 0-3 when all eight copy) hand their FASTQ slabs
+        # over NVLink to a better-connected peer, whose link then carries both (scs_params.relay_device)
+        relay_device, relay_map, d2h_relay_peak = -1, {}, None
+        order = devmap.get("order") or list(range(torch.cuda.device_count()))
+        fast = [r for r in range(world) if d2h_per_rank[r] >= 0.75 * max(d2h_per_rank)]
+        slow = [r for r in range(world) if r not in fast]
+        if world > 1 and slow and fast and not a.no_relay and not a.no_balance:
+            relay_map = {r: fast[i % len(fast)] for i, r in enumerate(slow)}
+            if rank in relay_map:
+                relay_device = order[relay_map[rank]]
+            per = gather_f64(d2h_rate(rank in fast))   # what the links that will carry the output sustain together
+            d2h_relay_peak = sum(per)
         del dbuf, hbuf
 
         # ---- one cell sharded over the ranks: same seed everywhere, global ids key every Philox stream. With several GPUs the read
         # ---- slots are cut in proportion to a per-GPU weight (balance = 1): first its measured D2H rate, then refined after every
         # ---- warm-up step from the measured read-stage times, so that all GPUs finish together
         g = api.GenReads(gamma=GAMMA, coverage=a.coverage, isize=ISIZE, layout="PE", seed=0x5C55, device=device, rank=rank, world=world,
-                         slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance), gzip=a.gz)
-        weight = d2h_per_rank[rank]
+                         slab_bytes=a.slab_mb << 20, balance=(world > 1 and not a.no_balance), gzip=a.gz, relay_device=relay_device)
+        weight = 1.0 if relay_map else d2h_per_rank[rank]
         if world > 1:
             # the library's own NCCL communicator (scs_nccl_init): rank 0's id reaches the other ranks through the process group that
             # torchrun set up; from here on no collective of the hot path goes through Python
@@ -555,7 +574,9 @@ def main():
                        "reads_stage_ms_max_rank": reads_ms_max / a.steps,
                        "parallelism": (f"one cell over {world} GPUs: sequences sharded for the amplification, packed genome + amplicon table all-gathered "
                                        f"over NCCL inside the library (v{api.lib().scs_nccl_version()}), read slots cut into {world} contiguous ranges") if world > 1 else "one GPU",
-                       "device_map": devmap, "share_of_reads_per_rank": [round(s / max(reads_all, 1), 4) for s in shares],
+                       "device_map": devmap, "relay": {"rank_via_rank": {str(k): v for k, v in relay_map.items()},
+                                                         "note": "these ranks copy their FASTQ slabs over NVLink to the peer's GPU, which copies them to the host"} if relay_map else None,
+                       "share_of_reads_per_rank": [round(s / max(reads_all, 1), 4) for s in shares],
                        "shard_weight_history": weights_hist[-3:]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": config["genome_bases"], "d2h_bytes_per_step": bytes_all, "steps": e2e_steps,
                     "fastq_GBps": bytes_all * e2e_steps / e2e_s / 1e9, "this_rank_h2d_bytes": h2d_bytes, "last_step_ms_rank0": e2e_parts},
@@ -568,6 +589,7 @@ def main():
                                  "peak": d2h_peak, "frac": (gbps / d2h_peak) if d2h_peak else None,
                                  "peak_n_x_single_link": world * d2h_single, "frac_of_n_x_single_link": gbps / (world * d2h_single) if d2h_single else None,
                                  "single_gpu_link": d2h_single, "per_gpu_concurrent": [round(x, 1) for x in d2h_per_rank],
+                                 "peak_of_links_used_with_relay": d2h_relay_peak, "frac_of_links_used_with_relay": (gbps / d2h_relay_peak) if d2h_relay_peak else None,
                                  "note": "FASTQ bytes landing in pinned host memory over the whole step. `peak` = pinned D2H copy rate measured in this run with all "
                                          "ranks copying at once (what this box's host side can absorb); `peak_n_x_single_link` = N x the rate of one GPU copying "
                                          "alone. This, not HBM, is the binding roof of the path"}},

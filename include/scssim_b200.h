@@ -63,7 +63,9 @@ typedef struct scs_params {
                              dynamic-Huffman block of literals each, ~2.1x smaller). Sinks receive the compressed bytes; scs_yield_reads
                              writes <prefix>_1.fq.gz/_2.fq.gz or <prefix>.fq.gz (world > 1: one shard <prefix>.rank<r>... per rank,
                              `cat` of the shards in rank order is the whole output). Extra flag --gz; the reference writes plain text */
-    int32_t reserved;
+    int32_t relay_device; /* -1 (default): FASTQ slabs are copied to the host over this GPU's own link. >= 0: over NVLink to that peer
+                             GPU first and from there to the host — for boxes where some GPUs sit behind a slow or shared host link
+                             (bench.py measures the links and lets the GPUs of the slow group relay through the fast group) */
 } scs_params;
 
 void scs_default_params(scs_params* p);

@@ -35,7 +35,7 @@ class Params(C.Structure):
     _fields_ = [("primers", C.c_int64), ("gamma", C.c_double), ("coverage", C.c_double), ("isize", C.c_int32),
                 ("paired", C.c_int32), ("seed", C.c_uint64), ("device", C.c_int32), ("rank", C.c_int32),
                 ("world", C.c_int32), ("balance", C.c_int32), ("slab_bytes", C.c_uint64), ("io_threads", C.c_int32),
-                ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("reserved", C.c_int32)]
+                ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("relay_device", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -56,7 +56,7 @@ class Stats(C.Structure):
 
 
 class SimuVarsParams(C.Structure):
-    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("ploidy", C.c_int32), ("libc_seed", C.c_uint32), ("line_width", C.c_int32), ("ring_slabs", C.c_int32), ("gzip", C.c_int32), ("relay_device", C.c_int32)]
 
 
 class SimuVarsStats(C.Structure):
@@ -232,7 +232,7 @@ class GenReads:
 
     def __init__(self, primers: int = 100000, gamma: float = 1e-9, coverage: float = 5.0, isize: int = 260,
                  layout: str = "PE", seed: int = 0x5C55, device: int = 0, rank: int = 0, world: int = 1,
-                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0, ring_slabs: int = 0, gzip: bool = False):
+                 slab_bytes: int = 0, balance: bool = False, io_threads: int = 0, ring_slabs: int = 0, gzip: bool = False, relay_device: int = -1):
         if layout not in ("SE", "PE"):
             raise ScsError(SCS_E_ARG, "Error: sequence layout incorrectly specified!\nshould be SE (single end) or PE (paired-end)")
         L = lib()
@@ -244,6 +244,7 @@ class GenReads:
         p.io_threads = io_threads
         p.ring_slabs = ring_slabs
         p.gzip = int(gzip)
+        p.relay_device = relay_device
         self._h = C.c_void_p()
         rc = L.scs_create(C.byref(p), C.byref(self._h))
         if rc != SCS_OK:

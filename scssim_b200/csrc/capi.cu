@@ -23,7 +23,7 @@ int scs_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSucces
 void scs_default_params(scs_params* p) {
     memset(p, 0, sizeof(*p));
     p->primers = 100000; p->gamma = 1e-9; p->coverage = 5; p->isize = 260; p->paired = 1;   // src/scssim.cpp:289-293
-    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0; p->ring_slabs = 0; p->gzip = 0; p->reserved = 0;
+    p->seed = 0x5C55ull; p->device = 0; p->rank = 0; p->world = 1; p->balance = 0; p->slab_bytes = 0; p->io_threads = 0; p->ring_slabs = 0; p->gzip = 0; p->relay_device = -1;
 }
 
 int scs_create(const scs_params* p, scs_ctx** out) {
@@ -63,6 +63,12 @@ void scs_destroy(scs_ctx* c) {
         cudaSetDevice(c->P.device); alloc_stream() = c->st;
         cudaDeviceSynchronize();
         if (c->comm) { nccl_api().CommDestroy(c->comm); c->comm = nullptr; }
+        if (c->st_relay) {   // relay buffers and stream live on the peer device
+            cudaSetDevice(c->relay_dev);
+            for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) if (c->relay_buf[b][f]) cudaFree(c->relay_buf[b][f]);
+            cudaStreamDestroy(c->st_relay); c->st_relay = nullptr;
+            cudaSetDevice(c->P.device);
+        }
         for (int f = 0; f < 2; f++) for (char* q : c->ring_host[f]) cudaFreeHost(q);
         if (c->rscratch.htotals) cudaFreeHost(c->rscratch.htotals);
         for (int b = 0; b < 2; b++) if (c->sv_pinned[b]) cudaFreeHost(c->sv_pinned[b]);

@@ -222,6 +222,9 @@ struct scs_ctx {
     scs_stats stats{};
     scs_simuvars_stats sv_stats{}; std::string sv_warnings;
 
+    // NVLink relay of the FASTQ slabs through a peer GPU's host link (scs_params.relay_device)
+    int relay_dev = -1; cudaStream_t st_relay = nullptr; char* relay_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}; uint64_t relay_cap = 0;
+
     // FASTQ slabs
     scs::DevBuf<char> slab_dev[2][2];   // [buffer][file] packed device slabs
     std::vector<char*> ring_host[2];    // [file] ring of pinned host slots the slabs are copied into (slab_sink.h)

@@ -787,6 +787,7 @@ struct StageGuard {
     cudaEvent_t make(unsigned flags) { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, flags); evs.push_back(e); return e; }
     ~StageGuard() {
         cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st_copy);
+        if (c->st_relay) cudaStreamSynchronize(c->st_relay);
         for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     }
 };
@@ -980,6 +981,32 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         c->ring_host[f].push_back(q);
     }
     for (int f = 0; f < nfiles; f++) SCS_CUDA(c, W.stage[f].reserve(batch * stride + 64));
+    // NVLink relay: the packed slab goes to a buffer on a peer GPU and from there over THAT GPU's host link into the pinned ring
+    const int dev_self = c->P.device, relay = (c->P.relay_device >= 0 && c->P.relay_device != c->P.device) ? c->P.relay_device : -1;
+    if (relay >= 0) {
+        if (!c->st_relay || c->relay_dev != relay) {
+            if (c->st_relay) return c->fail(SCS_E_STATE, "relay_device cannot change during the life of a context");
+            int can = 0; SCS_CUDA(c, cudaDeviceCanAccessPeer(&can, dev_self, relay));
+            if (!can) return c->fail(SCS_E_UNSUPPORTED, "relay_device: no peer access between the two GPUs");
+            cudaError_t e = cudaDeviceEnablePeerAccess(relay, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SCS_CUDA(c, e);
+            (void)cudaGetLastError();
+            SCS_CUDA(c, cudaSetDevice(relay));
+            e = cudaStreamCreateWithFlags(&c->st_relay, cudaStreamNonBlocking);
+            cudaSetDevice(dev_self);
+            SCS_CUDA(c, e);
+            c->relay_dev = relay;
+        }
+        if (c->relay_cap != slab) {
+            cudaSetDevice(relay);
+            cudaError_t e = cudaSuccess;
+            for (int b = 0; b < 2; b++) for (int f = 0; f < 2; f++) { if (c->relay_buf[b][f]) { cudaFree(c->relay_buf[b][f]); c->relay_buf[b][f] = nullptr; } }
+            for (int b = 0; b < 2 && e == cudaSuccess; b++) for (int f = 0; f < nfiles && e == cudaSuccess; f++) e = cudaMalloc((void**)&c->relay_buf[b][f], slab + 64);
+            cudaSetDevice(dev_self);
+            SCS_CUDA(c, e);
+            c->relay_cap = slab;
+        }
+    }
     // block-gzip output: members of one slab at a fixed stride, their sizes / offsets, and the packed compressed slabs
     const uint32_t gz_pieces = gz ? (uint32_t)gz_max_pieces(slab) : 0;
     if (gz) for (int f = 0; f < nfiles; f++) {
@@ -1001,12 +1028,17 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
     }
     SCS_CUDA(c, cudaMemsetAsync(W.flags.p, 0, 4, c->st)); SCS_CUDA(c, cudaMemsetAsync(W.records.p, 0, 8, c->st));
     cudaEvent_t e0 = G.make(cudaEventDefault), e1 = G.make(cudaEventDefault);
-    cudaEvent_t ecopy[2], ekern[2], etotb[2], tq[2][4]; bool timed[2] = {false, false};
+    cudaEvent_t ecopy[2], ekern[2], etotb[2], ep2p[2], tq[2][4]; bool timed[2] = {false, false};
     for (int b = 0; b < 2; b++) {
-        ecopy[b] = G.make(cudaEventDisableTiming); ekern[b] = G.make(cudaEventDisableTiming); etotb[b] = G.make(cudaEventDisableTiming);
+        ekern[b] = G.make(cudaEventDisableTiming); etotb[b] = G.make(cudaEventDisableTiming); ep2p[b] = G.make(cudaEventDisableTiming);
         for (int q = 0; q < 4; q++) tq[b][q] = G.make(cudaEventDefault);
     }
+    // the events recorded on the stream that performs the D2H copy belong to that stream's device
+    if (relay >= 0) cudaSetDevice(relay);
+    for (int b = 0; b < 2; b++) ecopy[b] = G.make(cudaEventDisableTiming);
     std::vector<cudaEvent_t> eslot(Rn); for (int i = 0; i < Rn; i++) eslot[i] = G.make(cudaEventDisableTiming);
+    if (relay >= 0) cudaSetDevice(dev_self);
+    cudaStream_t st_d2h = relay >= 0 ? c->st_relay : c->st_copy;
     double msk = 0, mse = 0;
     auto harvest = [&](int b) {   // kernel times of the slab that used buffer b (its events are complete: a later event was waited for)
         if (!timed[b]) return;
@@ -1030,12 +1062,24 @@ int yield_reads(scs_ctx* c, SlabConsumer& sink) {
         if (sink.acquire(slot)) return c->fail(SCS_E_IO, "FASTQ sink failed");
         SCS_CUDA(c, cudaStreamWaitEvent(c->st_copy, ekern[b], 0));
         char* p[2] = {nullptr, nullptr};
-        for (int f = 0; f < nfiles; f++) {
-            p[f] = c->ring_host[f][slot] + (sink.phase(f) & 4095);
-            if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(p[f], gz ? c->gz.slab[b][f].p : c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
+        for (int f = 0; f < nfiles; f++) p[f] = c->ring_host[f][slot] + (sink.phase(f) & 4095);
+        if (relay < 0) {
+            for (int f = 0; f < nfiles; f++)
+                if (tot[f]) SCS_CUDA(c, cudaMemcpyAsync(p[f], gz ? c->gz.slab[b][f].p : c->slab_dev[b][f].p, tot[f], cudaMemcpyDeviceToHost, c->st_copy));
+        } else {
+            // slab -> peer GPU over NVLink (this GPU's copy engine), then peer GPU -> host over the peer's link (the peer's copy engine)
+            for (int f = 0; f < nfiles; f++)
+                if (tot[f]) SCS_CUDA(c, cudaMemcpyPeerAsync(c->relay_buf[b][f], relay, gz ? c->gz.slab[b][f].p : c->slab_dev[b][f].p, dev_self, tot[f], c->st_copy));
+            SCS_CUDA(c, cudaEventRecord(ep2p[b], c->st_copy));
+            SCS_CUDA(c, cudaSetDevice(relay));
+            cudaError_t e = cudaStreamWaitEvent(st_d2h, ep2p[b], 0);
+            for (int f = 0; f < nfiles && e == cudaSuccess; f++) if (tot[f]) e = cudaMemcpyAsync(p[f], c->relay_buf[b][f], tot[f], cudaMemcpyDeviceToHost, st_d2h);
+            if (e != cudaSuccess) { cudaSetDevice(dev_self); SCS_CUDA(c, e); }
         }
-        SCS_CUDA(c, cudaEventRecord(ecopy[b], c->st_copy));
-        SCS_CUDA(c, cudaEventRecord(eslot[slot], c->st_copy));
+        cudaError_t er = cudaEventRecord(ecopy[b], st_d2h);
+        if (er == cudaSuccess) er = cudaEventRecord(eslot[slot], st_d2h);
+        if (relay >= 0) cudaSetDevice(dev_self);
+        SCS_CUDA(c, er);
         c->stats.fastq_bytes[0] += tot[0]; c->stats.fastq_bytes[1] += tot[1];
         c->stats.plain_bytes[0] += plain[0]; c->stats.plain_bytes[1] += plain[1];
         if (sink.submit(slot, eslot[slot], p, tot)) return c->fail(SCS_E_IO, "FASTQ sink failed");

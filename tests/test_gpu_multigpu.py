@@ -45,3 +45,26 @@ def test_cli_more_gpus_than_present_is_an_error(tmp_path):
     prof = H.profile_path("Illumina_HiSeq2500")
     r = subprocess.run([EXE, "genreads", "-i", fa, "-m", prof, "-o", os.path.join(str(tmp_path), "x"), "--gpus", str(_ngpu() + 1)], capture_output=True, timeout=120)
     assert r.returncode != 0 and b"CUDA devices" in r.stderr
+
+
+@pytest.mark.parametrize("gzip", [False, True])
+def test_relay_through_a_peer_gpu_changes_nothing(tmp_path, gzip):
+    """relay_device: the packed slabs travel over NVLink to GPU 1 and from there to the host (for boxes where some GPUs sit behind a
+    slow host link); the bytes that land are those of the direct route — many slabs, callback sink and file sink."""
+    if _ngpu() < 2:
+        pytest.skip("needs two GPUs")
+    from scssim_b200 import api
+    from scssim_b200.synth import synth_genome
+    prof = H.profile_path("Illumina_HiSeq2500")
+    genome = synth_genome(1, 300_000, seed=71, diploid=True)
+    out = {}
+    for relay in (-1, 1):
+        with api.GenReads(gamma=3e-10, coverage=20.0, layout="PE", seed=5, slab_bytes=1 << 20, ring_slabs=3, gzip=gzip, device=0, relay_device=relay) as g:
+            g.load_profile(prof).set_genome(genome).create_frags().amplify()
+            a = g.yield_reads_bytes()
+            g.yield_reads(os.path.join(str(tmp_path), f"r{relay}"))
+            assert g.stats()["emit_launches"] >= 10
+        ext = ".fq.gz" if gzip else ".fq"
+        out[relay] = (a, [H.read_bytes(os.path.join(str(tmp_path), f"r{relay}_{k}{ext}")) for k in (1, 2)])
+    assert out[1][0] == out[-1][0] and len(out[1][0][0]) > 100_000
+    assert out[1][1] == out[-1][1] and out[1][1][0] == out[1][0][0]
