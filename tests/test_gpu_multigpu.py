@@ -59,7 +59,7 @@ def test_relay_through_a_peer_gpu_changes_nothing(tmp_path, gzip):
     genome = synth_genome(1, 300_000, seed=71, diploid=True)
     out = {}
     for relay in (-1, 1):
-        with api.GenReads(gamma=3e-10, coverage=20.0, layout="PE", seed=5, slab_bytes=1 << 20, ring_slabs=3, gzip=gzip, device=0, relay_device=relay) as g:
+        with api.GenReads(gamma=3e-10, coverage=40.0, layout="PE", seed=5, slab_bytes=1 << 20, ring_slabs=3, gzip=gzip, device=0, relay_device=relay) as g:
             g.load_profile(prof).set_genome(genome).create_frags().amplify()
             a = g.yield_reads_bytes()
             g.yield_reads(os.path.join(str(tmp_path), f"r{relay}"))
