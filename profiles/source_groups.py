@@ -8,7 +8,8 @@ for g in sys.argv[3:]:
     f, r = rng.split(":")
     lo, hi = r.split("-")
     groups.append((f, int(lo), int(hi), name))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", kern, "--launch-count", "1"],
+sel = ["--launch-skip", kern[5:]] if kern.startswith("skip:") else ["--kernel-name", kern]   # "skip:N" = the (N+1)-th launch of the report
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel + ["--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 cur, acc, tot_s, tot_i = "", {}, 0, 0

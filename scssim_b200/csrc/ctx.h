@@ -218,6 +218,7 @@ struct scs_ctx {
     bool global_view = false; uint64_t g_n_amp = 0, g_slot_lo = 0, g_slot_hi = 0, g_bases = 0; int g_has_n = 0;
     scs::DevBuf<uint64_t> g_gather;     // all ranks' (desc, errref, global index) triples before they are scattered into g_desc / g_errref
     uint64_t genome_version = 0;        // bumped by every genome load
+    scs::DevBuf<uint32_t> gc_pref, n_pref; uint64_t gcidx_version = ~0ull;   // GC index of the local genome (build_gc_index)
     uint64_t g_genome_version = ~0ull, g_genome_stride = 0;   // what the replicated genome was built from: skipped while unchanged
     scs_stats stats{};
     scs_simuvars_stats sv_stats{}; std::string sv_warnings;
@@ -318,5 +319,7 @@ int allreduce_dev_f64(scs_ctx* c, double* dev, size_t n);
 int allgather_dev(scs_ctx* c, void* buf, size_t count, size_t elem);
 int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* total_host);
 // same for n <= 2048*2048 without allocation or synchronisation: scratch holds 2048+8 u64, the total is left in *total_dev
+// per-word prefix counts of C/G and N bases of the local packed genome (c->gc_pref, c->n_pref); cached by genome version
+int build_gc_index(scs_ctx* c);
 int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t* scratch, uint64_t* total_dev);
 }  // namespace scs

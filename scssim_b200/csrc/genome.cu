@@ -38,8 +38,9 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* t
     return warp_sums[warp] + inc - v;
 }
 
-template <class TIn>
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const TIn* __restrict__ in, uint64_t n, uint64_t* __restrict__ tile_sums) {
+// `In` is a pointer or a by-value accessor with operator[] (the GC index below counts bases of packed words on the fly)
+template <class In>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(In in, uint64_t n, uint64_t* __restrict__ tile_sums) {
     __shared__ uint64_t ws[kScanThreads / 32]; __shared__ uint64_t tot;
     uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint64_t s = 0;
@@ -49,9 +50,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const TIn* __rest
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
 
-template <class TIn>
-__global__ void __launch_bounds__(kScanThreads) scan_tiles(const TIn* __restrict__ in, uint64_t n, const uint64_t* __restrict__ tile_offs,
-                                                           uint64_t* __restrict__ out) {
+template <class In, class TOut>
+__global__ void __launch_bounds__(kScanThreads) scan_tiles(In in, uint64_t n, const uint64_t* __restrict__ tile_offs, TOut* __restrict__ out) {
     __shared__ uint64_t ws[kScanThreads / 32]; __shared__ uint64_t tot;
     uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     uint64_t v[kScanItems]; uint64_t s = 0;
@@ -59,25 +59,44 @@ __global__ void __launch_bounds__(kScanThreads) scan_tiles(const TIn* __restrict
     for (int k = 0; k < kScanItems; k++) { v[k] = (base + k < n) ? (uint64_t)in[base + k] : 0; s += v[k]; }
     uint64_t off = block_exclusive_scan(s, &tot, ws) + (tile_offs ? tile_offs[blockIdx.x] : 0);
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+    for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = (TOut)off; off += v[k]; }
 }
 
 // recursive reduce-then-scan; no inter-block waiting
-template <class TIn> static int scan_rec(scs_ctx* c, const TIn* in, uint64_t* out, uint64_t n, uint64_t* total_dev) {
+template <class In, class TOut> static int scan_rec(scs_ctx* c, In in, TOut* out, uint64_t n, uint64_t* total_dev) {
     if (n == 0) return SCS_OK;
     uint64_t tiles = (n + kScanTile - 1) / kScanTile;
     DevBuf<uint64_t> sums, offs;
     SCS_CUDA(c, sums.reserve(tiles + 1));
-    scan_tile_sums<TIn><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, sums.p); SCS_LAUNCHED(c);
+    scan_tile_sums<In><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, sums.p); SCS_LAUNCHED(c);
     if (tiles > 1) {
         SCS_CUDA(c, offs.reserve(tiles + 1));
-        int rc = scan_rec<uint64_t>(c, sums.p, offs.p, tiles, total_dev);
+        int rc = scan_rec<const uint64_t*, uint64_t>(c, sums.p, offs.p, tiles, total_dev);
         if (rc) return rc;
-        scan_tiles<TIn><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, offs.p, out); SCS_LAUNCHED(c);
+        scan_tiles<In, TOut><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, offs.p, out); SCS_LAUNCHED(c);
     } else {
-        scan_tiles<TIn><<<1, kScanThreads, 0, c->st>>>(in, n, nullptr, out); SCS_LAUNCHED(c);
+        scan_tiles<In, TOut><<<1, kScanThreads, 0, c->st>>>(in, n, nullptr, out); SCS_LAUNCHED(c);
         if (total_dev) SCS_CUDA(c, cudaMemcpyAsync(total_dev, sums.p, 8, cudaMemcpyDeviceToDevice, c->st));
     }
+    return SCS_OK;
+}
+
+// GC index of the packed genome (amplify.cu: the GC content of a product window in four loads instead of a pass over its 32-63
+// words): gc[w] = number of C/G bases in words [0, w), n[w] = number of N bases in words [0, w). Wrapping u32: only differences
+// of two entries are ever used. Rebuilt when the genome changes.
+struct GcCountIn { const uint64_t* w; __device__ __forceinline__ uint64_t operator[](uint64_t i) const { const uint64_t x = w[i]; return (uint64_t)__popcll((x ^ (x >> 1)) & 0x5555555555555555ull); } };
+struct NCountIn { const uint32_t* m; __device__ __forceinline__ uint64_t operator[](uint64_t i) const { return (uint64_t)__popc(m[i]); } };
+
+int build_gc_index(scs_ctx* c) {
+    if (c->gcidx_version == c->genome_version) return SCS_OK;
+    const uint64_t nw = c->genome_bases / 32 + 1;
+    SCS_CUDA(c, c->gc_pref.reserve(nw + 1));
+    if (int rc = scan_rec<GcCountIn, uint32_t>(c, GcCountIn{c->genome_words.p}, c->gc_pref.p, nw, nullptr)) return rc;
+    if (c->genome_has_n) {
+        SCS_CUDA(c, c->n_pref.reserve(nw + 1));
+        if (int rc = scan_rec<NCountIn, uint32_t>(c, NCountIn{c->genome_nmask.p}, c->n_pref.p, nw, nullptr)) return rc;
+    }
+    c->gcidx_version = c->genome_version;
     return SCS_OK;
 }
 
@@ -85,7 +104,7 @@ int exclusive_scan_u32(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n
     DevBuf<uint64_t> tot;
     SCS_CUDA(c, tot.reserve(1));
     SCS_CUDA(c, cudaMemsetAsync(tot.p, 0, 8, c->st));
-    int rc = scan_rec<uint32_t>(c, in, out, n, tot.p);
+    int rc = scan_rec<const uint32_t*, uint64_t>(c, in, out, n, tot.p);
     if (rc) return rc;
     if (total_host) { SCS_CUDA(c, cudaMemcpyAsync(total_host, tot.p, 8, cudaMemcpyDeviceToHost, c->st)); SCS_CUDA(c, cudaStreamSynchronize(c->st)); }
     return SCS_OK;
@@ -107,9 +126,9 @@ int scan_u32_noalloc(scs_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, 
     if (n == 0) { SCS_CUDA(c, cudaMemsetAsync(total_dev, 0, 8, c->st)); return SCS_OK; }
     const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
     if (tiles > (uint64_t)kScanTile) return c->fail(SCS_E_ARG, "scan_u32_noalloc: too many items");
-    scan_tile_sums<uint32_t><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch); SCS_LAUNCHED(c);
+    scan_tile_sums<const uint32_t*><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch); SCS_LAUNCHED(c);
     scan_single_tile<<<1, kScanThreads, 0, c->st>>>(scratch, tiles, scratch, total_dev); SCS_LAUNCHED(c);
-    scan_tiles<uint32_t><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch, out); SCS_LAUNCHED(c);
+    scan_tiles<const uint32_t*, uint64_t><<<(unsigned)tiles, kScanThreads, 0, c->st>>>(in, n, scratch, out); SCS_LAUNCHED(c);
     return SCS_OK;
 }
 

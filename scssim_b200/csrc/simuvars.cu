@@ -317,7 +317,7 @@ int simuvars_run(scs_ctx* c, const scs_simuvars_params& sp, const char* ref, con
         if (names.empty()) {
             c->seq_names.clear(); c->seq_len.clear(); c->seq_goff.clear(); c->ref_len_sum = 0; c->ref_len_half = 0; c->genome_bases = 0;
             SCS_CUDA(c, c->genome_words.reserve(2)); SCS_CUDA(c, c->genome_nmask.reserve(2));
-            c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false;
+            c->genome_has_n = 0; c->have_genome = true; c->have_frags = false; c->amplified = false; c->have_counts = false; c->genome_version++;
         } else rc = genome_from_sources(c, (int)names.size(), names.data(), srcs.data());
         SCS_CUDA(c, cudaStreamSynchronize(c->st));
     }
