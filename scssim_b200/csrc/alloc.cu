@@ -232,8 +232,9 @@ int set_read_counts(scs_ctx* c) {
         SCS_CUDA(c, cudaStreamSynchronize(c->st));   // pref (host) is read by the copy above
     }
     DevBuf<uint32_t> tmp; SCS_CUDA(c, tmp.reserve(N + 1));
-    DevBuf<uint64_t> oddp, sbase_g; SCS_CUDA(c, oddp.reserve(N + 1));
+    DevBuf<uint64_t> oddp, sbase_g;
     if (c->P.paired) {
+        SCS_CUDA(c, oddp.reserve(N + 1));
         odd_flags_kernel<<<nb, 256, 0, c->st>>>(cg, N, tmp.p); SCS_LAUNCHED(c);
         if (int rc = exclusive_scan_u32(c, tmp.p, oddp.p, N, nullptr)) return rc;
     }

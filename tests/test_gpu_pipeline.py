@@ -78,6 +78,13 @@ def test_se_many_primers_per_fragment(tmp_path):
     assert st["n_fulls"] > 50_000
 
 
+def test_se_more_primers_than_a_lane_holds(tmp_path):
+    # gamma 5e-9: ~30 primers per semi amplicon, so most templates of the semi-amplicon passes exceed the 24 attached sites a lane
+    # of amplify_semis_lanes_kernel keeps and are amplified by the warp kernel in the same pass; the rest by the lane kernel
+    st = _run_case(str(tmp_path), "lanecap", 1, 30_000, 43, "Illumina_HiSeq2000", "SE", 5e-9, 1.0, 260, seed=6, diploid=False)
+    assert st["n_fulls"] > 20_000
+
+
 @pytest.mark.parametrize("layout", ["PE", "SE"])
 def test_genome_with_n_iupac_and_lowercase(tmp_path, layout):
     # N runs / scattered N / IUPAC codes (all "N" after the reference's complement) / soft-masked bases: primer sites over N
