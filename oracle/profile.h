@@ -242,12 +242,58 @@ struct Profile {
         return minInsert + (int)rand_index(iSizeCdf.row(0), iSizeCdf.cols, d.next(E_REAL));
     }
 
+    /* Free-running streams only (no tape): the indel stage of predict() draws the DISTANCE to the next indel event instead of
+     * two draws per read position. Per position the reference decides "insertion" with probability pI = P(p <= insertRate),
+     * else "deletion" with probability pD = P(p2 < delRate / (1 - insertRate)) — the same at every position, so the number of
+     * event-free positions before the next event is geometric with q = (1 - pI)(1 - pD), and the event is an insertion with
+     * probability pI / (1 - q). pI and pD are taken as the exact rationals T / 2^32 of the 32-bit draws that satisfy the
+     * reference's comparisons, so that the CUDA path (integer thresholds) forms bit-identical constants. Same distribution as
+     * Profile.cpp:1603-1630 at ~1 draw per read instead of 2 per base; replay keeps the reference's consumption. */
+    struct IndelGeom { bool any = false; double logQ = 0; uint64_t thrInsType = 0; };
+    static uint64_t count_unit_le(double c) { if (c < 0) return 0; double t = floor(ldexp(c, 32)) + 1; return t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t; }
+    static uint64_t count_unit_lt(double c) { if (c <= 0) return 0; double t = ceil(ldexp(c, 32)); return t >= 4294967296.0 ? (1ull << 32) : (uint64_t)t; }
+    IndelGeom indel_geom() const {
+        IndelGeom g;
+        const uint64_t tI = count_unit_le(insertRate), tD = count_unit_lt(delRate / (1 - insertRate));
+        const double pI = (double)tI / 4294967296.0, pD = (double)tD / 4294967296.0;
+        const double q = (1.0 - pI) * (1.0 - pD);
+        g.any = q < 1.0;
+        g.logQ = det_log(q);
+        g.thrInsType = tD == 0 ? (1ull << 32) : tI == 0 ? 0 : count_unit_lt(pI / (1.0 - q));
+        return g;
+    }
+
     /* Profile::predict(char*, int), Profile.cpp:1582-1697. Returns bases and qualities (equal length). */
     void predict(const std::string& ref, bool isRead1, Draws& d, std::string& outSeq, std::string& outQual) const {
         int n = (int)ref.size();
         std::vector<std::vector<int>> ins(n);
         std::vector<int> indelLens; indelLens.reserve(n + 8);
         int indelLength = 0;
+        if (!d.is_tape()) {
+            const IndelGeom G = indel_geom();
+            for (int j = 0; G.any && j < n;) {
+                const double u = ((double)d.next(E_REAL) + 0.5) / 4294967296.0;
+                const double gd = floor(det_log(u) / G.logQ);
+                if (!(gd < (double)(n - j))) break;
+                for (int i = 0; i < (int)gd; i++) indelLens.push_back(0);
+                j += (int)gd;
+                int k; std::vector<int>& bi = ins[j];
+                if ((uint64_t)d.next(E_REAL) < G.thrInsType) {
+                    k = (int)rand_index(insCdf.row(0), insCdf.cols, d.next(E_REAL));
+                    for (int i = 0; i < k; i++) bi.push_back((int)uni_int(d.next(E_INT), 0, N - 1));
+                } else k = (int)rand_index(delCdf.row(0), delCdf.cols, d.next(E_REAL));
+                if (bi.empty() && k > 0) {
+                    k = std::min(n - j, k);
+                    indelLength -= k;
+                    indelLens.push_back(k);
+                    for (int i = 1; i < k; i++) indelLens.push_back(0);
+                    j += k;
+                } else {
+                    indelLength += k; j++; indelLens.push_back(k);
+                }
+            }
+            indelLens.resize(n, 0);
+        } else
         for (int j = 0; j < n;) {
             /* getIndelSeq, Profile.cpp:1552-1570 */
             int k = 0; std::vector<int>& bi = ins[j];

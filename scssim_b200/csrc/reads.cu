@@ -52,6 +52,11 @@ struct ReadTables {
     const uint32_t* ins; const uint32_t* del; const uint32_t* isize;
     int insEff, delEff, isizeEff, minInsert, maxInsert;
     uint64_t thrIns, thrDel;                         // insertion iff x < thrIns ; else deletion iff x2 < thrDel
+    // free-running streams: the distance to the next indel event is drawn directly (see indel_pass). q = P(no event at a position)
+    double indelLogQ;                                // det_log(q)
+    uint64_t thrInsType;                             // the event is an insertion iff x < thrInsType  (pI / (1 - q))
+    uint32_t thrNoEvent;                             // x < thrNoEvent: certainly no event within RL positions (0.99 q^RL: skips the logarithm)
+    int indelAny;                                    // q < 1
     int RL, paired;
     // compact copies of the 4 diagonal (no substitution) quality tables for shared memory
     const uint32_t* diagRows; const uint4* diagPiv; const uint32_t* diagMeta;   // [4][bins][36], [4][bins], [4][bins] lo | cnt<<8 | global<<16
@@ -172,6 +177,41 @@ template <class SX>
 __device__ __forceinline__ int indel_pass(const SX& S, const ReadTables& T, int n, uint32_t& cr, uint32_t& ci, int lane, WarpScratch* ws,
                                           int* nev_out, int* flags) {
     int j = 0, delta = 0, nev = 0;
+    if (!S.replay()) {
+        // Free-running streams: per position the reference decides "insertion" with probability pI, else "deletion" with
+        // probability pD, the same at every position — so the number of event-free positions before the next event is
+        // geometric, q = (1 - pI)(1 - pD), and the event is an insertion with probability pI / (1 - q). One draw per read (89 %
+        // of the reads have no event: x < thrNoEvent answers that without the logarithm) instead of 2 per base; the oracle's
+        // free-running predict() draws the same way (oracle/profile.h), replay keeps the reference's consumption below.
+        SCS_CHECK(n <= T.RL);
+        while (T.indelAny && j < n) {
+            const uint32_t x = S.at(E_REAL, cr++);
+            if (x < T.thrNoEvent) break;
+            const double u = __ddiv_rn(__dadd_rn((double)x, 0.5), 4294967296.0);
+            const double gd = floor(__ddiv_rn(det_log(u), T.indelLogQ));
+            if (!(gd < (double)(n - j))) break;
+            const int p = j + (int)gd;
+            const bool insertion = (uint64_t)S.at(E_REAL, cr++) < T.thrInsType;
+            const uint32_t xl = S.at(E_REAL, cr++);
+            if (insertion) {   // insertion after base p: k base draws on the int engine
+                const int k = min(count_le(T.ins, T.insEff, xl), T.insEff);
+                if (k > 0) {
+                    if (nev < kMaxEvents) { if (lane == 0) { ws->ev_pos[nev] = (int16_t)p; ws->ev_len[nev] = (int16_t)k; ws->ev_ci[nev] = ci; } }
+                    else if (lane == 0) atomicOr(flags, 4);
+                    nev++; delta += k; ci += (uint32_t)k;
+                }
+                j = p + 1;
+            } else {           // deletion of k bases starting at p
+                int k = min(count_le(T.del, T.delEff, xl), T.delEff);
+                k = min(n - p, k);
+                if (k > 0) {
+                    if (nev < kMaxEvents) { if (lane == 0) { ws->ev_pos[nev] = (int16_t)p; ws->ev_len[nev] = (int16_t)(-k); ws->ev_ci[nev] = 0; } }
+                    else if (lane == 0) atomicOr(flags, 4);
+                    nev++; delta -= k; j = p + k;
+                } else j = p + 1;
+            }
+        }
+    } else
     while (j < n) {
         uint32_t x[4];
         const int P = warp_draws4(S, E_REAL, cr, lane, x) >> 1;   // positions covered by this step (2 draws each)
@@ -772,6 +812,15 @@ static ReadTables make_tables(const scs_ctx* c) {
     T.minInsert = P.minInsert; T.maxInsert = P.maxInsert;
     T.thrIns = P.thrInsertAll ? (1ull << 32) : P.thrInsert; T.thrDel = P.thrDeleteAll ? (1ull << 32) : P.thrDelete;
     T.RL = P.readLength; T.paired = c->P.paired;
+    {   // constants of the free-running indel stage: formed exactly as oracle/profile.h indel_geom() forms them
+        const double pI = (double)T.thrIns / 4294967296.0, pD = (double)T.thrDel / 4294967296.0;
+        const double q = (1.0 - pI) * (1.0 - pD);
+        T.indelAny = q < 1.0;
+        T.indelLogQ = det_log(q);
+        T.thrInsType = T.thrDel == 0 ? (1ull << 32) : T.thrIns == 0 ? 0 : count_unit_lt(pI / (1.0 - q));
+        const double none = (q > 0.0 && q < 1.0) ? floor(0.99 * exp((double)T.RL * T.indelLogQ) * 4294967296.0) : 0.0;
+        T.thrNoEvent = (uint32_t)std::min(none, 4294967295.0);
+    }
     T.diagRows = D.qualDiag.p; T.diagPiv = reinterpret_cast<const uint4*>(D.qualDiagPiv.p); T.diagMeta = D.qualDiagMeta.p;
     return T;
 }
