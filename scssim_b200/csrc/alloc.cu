@@ -169,7 +169,8 @@ int set_read_counts(scs_ctx* c) {
     SCS_CUDA(c, c->full_gidx.reserve(n + 1)); SCS_CUDA(c, c->slot_gbase.reserve(n + 1));
     c->n_slots = 0;
     if (N == 0) { c->have_counts = true; return SCS_OK; }   // the reference crashes on an empty amplicon list; we emit nothing
-    DevBuf<double> gcm; SCS_CUDA(c, gcm.reserve(101));
+    AllocScratch& LS = c->lscratch;
+    DevBuf<double>& gcm = LS.gcm; SCS_CUDA(c, gcm.reserve(101));
     SCS_CUDA(c, cudaMemcpyAsync(gcm.p, c->prof.gcMeans, 101 * 8, cudaMemcpyHostToDevice, c->st));
     const unsigned nbl = (unsigned)((n + 255) / 256), nb = (unsigned)((N + 255) / 256);
     if (n) {
@@ -179,7 +180,7 @@ int set_read_counts(scs_ctx* c) {
     }
     // The allocation itself is defined on the whole cell's list. With several ranks every rank gets the full weight vector
     // (one all-reduce of a scattered copy) and runs the identical allocation, so the result does not depend on the rank count.
-    DevBuf<double> wg_buf; DevBuf<uint32_t> cg_buf;
+    DevBuf<double>& wg_buf = LS.wg_buf; DevBuf<uint32_t>& cg_buf = LS.cg_buf;
     double* wg = c->weights.p; uint32_t* cg = c->counts.p;
     if (multi) {
         SCS_CUDA(c, wg_buf.reserve(N + 1)); SCS_CUDA(c, cg_buf.reserve(N + 1));
@@ -189,13 +190,13 @@ int set_read_counts(scs_ctx* c) {
         if (int rc = allreduce_dev_f64(c, wg, N)) return rc;   // NCCL over NVLink (or the caller's hook)
     }
     const uint64_t nch = (N + kChunk - 1) / kChunk;
-    DevBuf<double> dsums; SCS_CUDA(c, dsums.reserve(nch + 1));
+    DevBuf<double>& dsums = LS.dsums; SCS_CUDA(c, dsums.reserve(nch + 1));
     std::vector<double> hs(nch);
     chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p); SCS_LAUNCHED(c);
     SCS_CUDA(c, cudaMemcpyAsync(hs.data(), dsums.p, nch * 8, cudaMemcpyDeviceToHost, c->st));
     SCS_CUDA(c, cudaStreamSynchronize(c->st));
     double S = 0; for (uint64_t k = 0; k < nch; k++) S += hs[k];
-    DevBuf<unsigned long long> dtot; SCS_CUDA(c, dtot.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(dtot.p, 0, 8, c->st));
+    DevBuf<unsigned long long>& dtot = LS.dtot; SCS_CUDA(c, dtot.reserve(1)); SCS_CUDA(c, cudaMemsetAsync(dtot.p, 0, 8, c->st));
     normalize_floor_kernel<<<nb, 256, 0, c->st>>>(wg, N, kEpsH + S, (double)(long)c->reads_requested, cg, dtot.p); SCS_LAUNCHED(c);
     chunk_sum_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p); SCS_LAUNCHED(c);
     unsigned long long floorSum = 0;
@@ -224,15 +225,15 @@ int set_read_counts(scs_ctx* c) {
     for (uint64_t k = 0; k < nch; k++) { pref[k] = nsamp; nsamp += ns[k]; }
     pref[nch] = nsamp;
     if (nsamp) {
-        DevBuf<double> cdf; SCS_CUDA(c, cdf.reserve(N + 1));
-        DevBuf<uint64_t> dpref; SCS_CUDA(c, dpref.reserve(nch + 1));
+        DevBuf<double>& cdf = LS.cdf; SCS_CUDA(c, cdf.reserve(N + 1));
+        DevBuf<uint64_t>& dpref = LS.dpref; SCS_CUDA(c, dpref.reserve(nch + 1));
         SCS_CUDA(c, cudaMemcpyAsync(dpref.p, pref.data(), (nch + 1) * 8, cudaMemcpyHostToDevice, c->st));
         chunk_cdf_kernel<<<(unsigned)((nch + 127) / 128), 128, 0, c->st>>>(wg, N, dsums.p, cdf.p); SCS_LAUNCHED(c);
         chunk_sample_kernel<<<(unsigned)((nsamp + 255) / 256), 256, 0, c->st>>>(draw_src(c, D_MULTC), 0, N, nch, dpref.p, nsamp, cdf.p, cg); SCS_LAUNCHED(c);
         SCS_CUDA(c, cudaStreamSynchronize(c->st));   // pref (host) is read by the copy above
     }
-    DevBuf<uint32_t> tmp; SCS_CUDA(c, tmp.reserve(N + 1));
-    DevBuf<uint64_t> oddp, sbase_g;
+    DevBuf<uint32_t>& tmp = LS.tmp; SCS_CUDA(c, tmp.reserve(N + 1));
+    DevBuf<uint64_t>&oddp = LS.oddp, &sbase_g = LS.sbase_g;
     if (c->P.paired) {
         SCS_CUDA(c, oddp.reserve(N + 1));
         odd_flags_kernel<<<nb, 256, 0, c->st>>>(cg, N, tmp.p); SCS_LAUNCHED(c);
@@ -245,7 +246,7 @@ int set_read_counts(scs_ctx* c) {
     } else {
         SCS_CUDA(c, sbase_g.reserve(N + 1));
         if (int rc = exclusive_scan_u32(c, tmp.p, sbase_g.p, N, nullptr)) return rc;
-        DevBuf<uint32_t> lslots; SCS_CUDA(c, lslots.reserve(n + 1));
+        DevBuf<uint32_t>& lslots = LS.lslots; SCS_CUDA(c, lslots.reserve(n + 1));
         if (n) {
             gather_counts_kernel<<<nbl, 256, 0, c->st>>>(wg, cg, sbase_g.p, c->full_gidx.p, n, c->P.paired, c->weights.p, c->counts.p, c->slot_gbase.p, lslots.p);
             SCS_LAUNCHED(c);

@@ -388,6 +388,10 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, GcIndex g
 // the list holds are left to the warp kernel (flag 4 tells the host that there are any). Results are identical to the warp
 // kernel's: the draws are addressed by (template, engine, index), not by who evaluates them.
 constexpr int kLaneSites = 24;
+#ifndef SCS_LANE_PEND_NUM   // a product step runs once NUM/DEN of the lanes in work hold an accepted site (A/B: profiles/NOTES_r02.md)
+#define SCS_LANE_PEND_NUM 1
+#define SCS_LANE_PEND_DEN 2
+#endif
 constexpr int kLaneWarps = 8;
 
 __global__ void __launch_bounds__(kLaneWarps * 32) amplify_semis_lanes_kernel(Genome g, GcIndex gcx, DrawSrc src, AmpParams ap, uint64_t n_tmpl, const uint64_t* __restrict__ desc,
@@ -469,7 +473,7 @@ __global__ void __launch_bounds__(kLaneWarps * 32) amplify_semis_lanes_kernel(Ge
         // ---- product step, once half of the lanes in work hold an accepted site
         const uint32_t pend = __ballot_sync(0xffffffffu, pending);
         const uint32_t act2 = __ballot_sync(0xffffffffu, active);
-        if (pend == 0 || 2 * __popc(pend) < __popc(act2)) continue;
+        if (pend == 0 || SCS_LANE_PEND_DEN * __popc(pend) < SCS_LANE_PEND_NUM * __popc(act2)) continue;
         uint32_t ntot = 0; int gc = 0;
         if (pending) {
             // GC content of the window (countGC, MyDefine.cpp:434-452)

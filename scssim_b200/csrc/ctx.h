@@ -147,6 +147,13 @@ struct AmpScratch {
     DevBuf<uint64_t> slot_off, cprefix, tdesc, terr; DevBuf<uint32_t> tgc, created, gbitmaps;
 };
 
+// temporaries of the allocation stage: kept between calls (mapping fresh device memory costs 1-100 ms per GB here, erratically —
+// with per-call buffers the stage took 3 ms per step on one box and 158 ms on another)
+struct AllocScratch {
+    DevBuf<double> gcm, wg_buf, dsums, cdf; DevBuf<uint32_t> cg_buf, tmp, lslots;
+    DevBuf<unsigned long long> dtot; DevBuf<uint64_t> dpref, oddp, sbase_g;
+};
+
 // persistent scratch of the read stage (no allocation inside the slab loop)
 struct ReadScratch {
     DevBuf<uint32_t> size1, size2, nfail, hdrno, coarse;
@@ -204,6 +211,7 @@ struct scs_ctx {
     scs::ReadScratch rscratch;
     scs::GzState gz;
     scs::AmpScratch ascratch;
+    scs::AllocScratch lscratch;
     // staging buffers that keep their capacity between calls (cold device allocations are slow and erratic on this platform)
     scs::DevBuf<uint8_t> genome_stage, sv_stage, sv_ref, sv_text[2];
     char* sv_pinned[2] = {nullptr, nullptr};   // simuvars output slabs (pinned), kept between calls
