@@ -81,3 +81,36 @@ def test_det_log_accuracy():
         want = math.log(x)
         assert abs(got - want) <= 4e-16 * max(1.0, abs(want)), (x, got, want)
     assert L.orc_det_log(0.0) == -math.inf
+
+
+def _length_hist(fastq: bytes, rl: int):
+    lines = fastq.split(b"\n")
+    lens = np.array([len(s) for s in lines[1::4]], dtype=np.int64)
+    return np.bincount(np.clip(lens - (rl - 40), 0, 80), minlength=81) / max(1, len(lens)), len(lens)
+
+
+def test_oracle_free_running_indel_stage_keeps_the_read_length_spectrum(tmp_path):
+    """Free-running streams draw the distance to the next indel event instead of the reference's two draws per read position
+    (oracle/profile.h indel_geom; Profile.cpp:1603-1630). The read-length spectrum must stay what the per-position process gives:
+    P(no event in 125 positions) = ((1 - pI)(1 - pD))^125 = 0.887 for HiSeq2500, and — when the compiled reference is here —
+    every length bin within 0.6 % absolute of the seeded reference's."""
+    tmp = str(tmp_path)
+    fa = os.path.join(tmp, "cell.fa")
+    H.write_genome(fa, 1, 300_000, seed=29)
+    prof = H.profile_path("Illumina_HiSeq2500")
+    args = H.genreads_args(prof, "PE", 2e-10, 30.0, 260)
+    H.run_oracle(fa, os.path.join(tmp, "orc"), args, seed=987)
+    rl = 125
+    ho, n = _length_hist(H.read_bytes(os.path.join(tmp, "orc_1.fq")) + H.read_bytes(os.path.join(tmp, "orc_2.fq")), rl)
+    assert n > 50_000
+    assert abs(ho[40] - 0.887) < 0.01, ho[40]
+    assert ho[:40].sum() > 0.02 and ho[41:].sum() > 0.02          # deletions and insertions both occur
+    exe = H.ref_replay_bin()
+    if exe is None:
+        return
+    import subprocess
+    subprocess.run([exe, "genreads", "-i", fa, "-t", "1", "-o", os.path.join(tmp, "ref")] + args, check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, env=dict(os.environ, SCS_SEED="1234"))
+    hr, nr = _length_hist(H.read_bytes(os.path.join(tmp, "ref_1.fq")) + H.read_bytes(os.path.join(tmp, "ref_2.fq")), rl)
+    assert abs(n - nr) <= 4
+    assert np.abs(ho - hr).max() < 0.006, (np.abs(ho - hr).argmax(), ho[38:43], hr[38:43])
