@@ -388,13 +388,19 @@ __global__ void __launch_bounds__(WARPS * 32) amplify_kernel(Genome g, GcIndex g
 // the list holds are left to the warp kernel (flag 4 tells the host that there are any). Results are identical to the warp
 // kernel's: the draws are addressed by (template, engine, index), not by who evaluates them.
 constexpr int kLaneSites = 24;
+#ifdef SCS_LANE_CTAS        // A/B builds: resident CTAs per SM the lane kernel is compiled and launched for (profiles/NOTES_r02.md)
+#define SCS_LANE_BOUNDS __launch_bounds__(kLaneWarps * 32, SCS_LANE_CTAS)
+#else                       // shipped: 64 registers without a cap, 4 CTAs per SM
+#define SCS_LANE_CTAS 4
+#define SCS_LANE_BOUNDS __launch_bounds__(kLaneWarps * 32)
+#endif
 #ifndef SCS_LANE_PEND_NUM   // a product step runs once NUM/DEN of the lanes in work hold an accepted site (A/B: profiles/NOTES_r02.md)
 #define SCS_LANE_PEND_NUM 1
 #define SCS_LANE_PEND_DEN 2
 #endif
 constexpr int kLaneWarps = 8;
 
-__global__ void __launch_bounds__(kLaneWarps * 32) amplify_semis_lanes_kernel(Genome g, GcIndex gcx, DrawSrc src, AmpParams ap, uint64_t n_tmpl, const uint64_t* __restrict__ desc,
+__global__ void SCS_LANE_BOUNDS amplify_semis_lanes_kernel(Genome g, GcIndex gcx, DrawSrc src, AmpParams ap, uint64_t n_tmpl, const uint64_t* __restrict__ desc,
                                                                               const uint32_t* __restrict__ primers, const uint64_t* __restrict__ errref,
                                                                               const uint64_t* __restrict__ slot_off, uint64_t* __restrict__ out_desc,
                                                                               uint32_t* __restrict__ out_gc, uint64_t* __restrict__ out_errref,
@@ -664,7 +670,7 @@ struct Round {
                     kern<<<sms * 8, W * 32, sm, c->st>>>(g, gcx, draw_src(c, D_AMPS), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p, terr.p, created.p,
                                                          c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p, c->primer_counts.p, ticket.p, nullptr, lanes ? (uint32_t)kLaneSites : 0u);
                 };
-                if (lanes) amplify_semis_lanes_kernel<<<sms * 4, kLaneWarps * 32, 0, c->st>>>(g, gcx, draw_src(c, D_AMPS), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p,
+                if (lanes) amplify_semis_lanes_kernel<<<sms * SCS_LANE_CTAS, kLaneWarps * 32, 0, c->st>>>(g, gcx, draw_src(c, D_AMPS), ap, n, desc, primers, errref, slot_off.p, tdesc.p, tgc.p,
                                                                                              terr.p, created.p, c->err_pool.p, c->err_top.p, c->err_pool.cap, flags.p,
                                                                                              c->primer_counts.p, ticket.p);
                 else semis_warp_pass();
