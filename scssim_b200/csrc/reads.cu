@@ -37,6 +37,9 @@ constexpr int kDiagW = 40;            // entries per compact quality row kept in
 constexpr int kDiagStride = 44;       // words per row: 40 + 4 pad; 44*r mod 32 is a distinct multiple of 4 for 8 neighbouring rows,
                                       // so their 128-bit loads are bank-conflict free
 constexpr int kRLCap = 320;           // max profile read length handled by the kernels (Illumina tops out at 2 x 300)
+#ifndef SCS_EMIT_BATCH_DRAWS   // 1: plan_slot evaluates the slot's four warp-uniform single draws in one Philox pass (A/B in profiles/NOTES_r02.md)
+#define SCS_EMIT_BATCH_DRAWS 1
+#endif
 constexpr int kSrcCap = 480;          // max read length after insertions (overflow -> error flag)
 constexpr int kMaxEvents = 64;        // indel events per read kept in shared memory
 constexpr int kRecCap = 16 + 40 + 2 * kSrcCap + 8;
@@ -88,6 +91,7 @@ struct SlotPlan {
     uint32_t woff[2];         // window of mate m starts woff[m] bases into win[m]; bit 31: read it backwards and complemented
     uint32_t noff[2];         // same for the N mask (bases into winn[m])
     int32_t valid;
+    uint32_t gap[2], gap_idx[2];   // free-running: first indel-stage draw of each mate, precomputed with the slot's other single draws
 };
 
 struct __align__(16) WarpScratch {
@@ -175,7 +179,8 @@ __device__ __forceinline__ int warp_draws4(const SX& S, int eng, uint32_t base, 
 // "< 50 bases" guard discarded them.
 template <class SX>
 __device__ __forceinline__ int indel_pass(const SX& S, const ReadTables& T, int n, uint32_t& cr, uint32_t& ci, int lane, WarpScratch* ws,
-                                          int* nev_out, int* flags) {
+                                          int* nev_out, int* flags, uint32_t pre_idx = 0xFFFFFFFFu, uint32_t pre_x = 0) {
+    // pre_x: real draw number pre_idx of this stream, if the caller already has it (plan_slot computes the slot's single draws together)
     int j = 0, delta = 0, nev = 0;
     if (!S.replay()) {
         // Free-running streams: per position the reference decides "insertion" with probability pI, else "deletion" with
@@ -185,7 +190,8 @@ __device__ __forceinline__ int indel_pass(const SX& S, const ReadTables& T, int 
         // free-running predict() draws the same way (oracle/profile.h), replay keeps the reference's consumption below.
         SCS_CHECK(n <= T.RL);
         while (T.indelAny && j < n) {
-            const uint32_t x = S.at(E_REAL, cr++);
+            const uint32_t x = (cr == pre_idx) ? pre_x : S.at(E_REAL, cr);
+            cr++;
             if (x < T.thrNoEvent) break;
             const double u = __ddiv_rn(__dadd_rn((double)x, 0.5), 4294967296.0);
             const double gd = floor(__ddiv_rn(det_log(u), T.indelLogQ));
@@ -506,16 +512,34 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
     const bool need_bases = !SIZE_ONLY || g.has_n;    // record sizes depend on the bases only through the draws an N consumes
     uint32_t cr = 0, ci = 0; int pos = 0, isz = RL;
     uint32_t woff[2] = {0, 0}, noff[2] = {0, 0};
+    uint32_t gap_x[2] = {0, 0}, gap_i[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
     __syncwarp();   // every lane is done reading this buffer's previous windows and plan
     if (valid) {
         RStream<REPLAY> S; S.init(dsrc, D_READ, entity, entity);
+        if (T.paired && A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
+        uint32_t x_isz = 0, x_pos;
+#if SCS_EMIT_BATCH_DRAWS
+        if (!REPLAY) {
+            // The slot's warp-uniform single draws in ONE Philox evaluation: lane 0 the block of the insert-size draw, lane 1 of the
+            // position draw, lanes 2 / 3 of the first indel-stage draw of mate 1 / mate 2 (mate 2's index assumes that mate 1
+            // consumes 1 + 2 RL draws — no indel event, no N; indel_pass checks the index and draws itself otherwise)
+            const uint32_t i1 = cr + (T.paired ? 1u : 0u), i2 = i1 + 1u + 2u * (uint32_t)RL;
+            const uint32_t want = lane == 1 ? 0u : lane == 2 ? i1 : lane == 3 ? i2 : cr;
+            uint32_t o[4];
+            philox4x32_10_call(S.e0, S.e1, want >> 2, S.dom2 + (uint32_t)(lane == 1 ? E_INT : E_REAL), S.k0, S.k1, o);
+            const uint32_t v = (want & 2u) ? ((want & 1u) ? o[3] : o[2]) : ((want & 1u) ? o[1] : o[0]);
+            x_isz = __shfl_sync(0xffffffffu, v, 0); x_pos = __shfl_sync(0xffffffffu, v, 1);
+            gap_x[0] = __shfl_sync(0xffffffffu, v, 2); gap_x[1] = __shfl_sync(0xffffffffu, v, 3);
+            gap_i[0] = i1; gap_i[1] = i2;
+        } else
+#endif
+        { if (T.paired) x_isz = S.at(E_REAL, cr); x_pos = S.at(E_INT, ci); }
         if (T.paired) {
-            if (A.nfail) cr = A.nfail[slot - A.fail_base];   // failed attempts each consumed one real draw (Amplicon.cpp:483-490)
-            isz = T.minInsert + warp_count_le(isize_row, T.isizeEff, S.at(E_REAL, cr), lane);
+            isz = T.minInsert + warp_count_le(isize_row, T.isizeEff, x_isz, lane);
             cr += 1;
-            pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
+            pos = (int)uni_trunc(x_pos, 0, (uint32_t)(ampLen - isz + 1)); ci += 1;
         } else {
-            pos = (int)uni_trunc(S.at(E_INT, ci), 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
+            pos = (int)uni_trunc(x_pos, 0, (uint32_t)(ampLen - RL + 1)); ci += 1;
         }
         // genome interval [lo, lo + RL) of each mate and its reading direction. Window base i of the amplicon is
         // rc ? comp(G[gstart - i]) : G[gstart + i]; mate 1 reads window bases pos .. pos+RL-1, mate 2 the reverse complement of
@@ -559,6 +583,7 @@ __device__ __forceinline__ void plan_slot(const Genome& g, const DrawSrc& dsrc, 
         P.entity = entity; P.errs = A.err_pool + (er >> 16); P.ampIdx = ampIdx; P.fragNo = fragNo; P.nerr = (uint32_t)(er & 0xFFFF);
         P.cr = cr; P.ci = ci; P.pos = pos; P.isz = isz; P.woff[0] = woff[0]; P.woff[1] = woff[1]; P.noff[0] = noff[0]; P.noff[1] = noff[1];
         P.valid = valid ? 1 : 0;
+        P.gap[0] = gap_x[0]; P.gap[1] = gap_x[1]; P.gap_idx[0] = gap_i[0]; P.gap_idx[1] = gap_i[1];
     }
     __syncwarp();
 }
@@ -633,7 +658,7 @@ __device__ __forceinline__ uint32_t emit_slot(const Genome& g, const DrawSrc& ds
         const bool hasN = g.has_n && __any_sync(0xffffffffu, myN);   // conservative when an overlay replaced the only N: the N path is exact for any window
         __syncwarp();
         int nev = 0;
-        const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags);
+        const int np = indel_pass(S, T, RL, cr, ci, lane, ws, &nev, flags, P.gap_idx[mate - 1], P.gap[mate - 1]);
         if (np > kSrcCap) { if (lane == 0) atomicOr(flags, 8); return made; }
         __syncwarp();
         const int total = hl + 2 * np + 4;
