@@ -606,6 +606,7 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
         }
         if (ok && segStart <= chrLen) add(segStart, chrLen, ploidy, mCN);
     }
+    const double ms_pass1 = ms_since(t0);
     // Pass 2, one task per chromosome on a few threads: variants -> piece tables -> runs and substitutions. A chromosome whose
     // draws failed in pass 1 still gets its earlier segments applied: the reference would have died at the first problem in
     // file order, and that may be an indel of an earlier segment.
@@ -631,6 +632,7 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
             for (auto& t : ts) t.join();
         }
     }
+    const double ms_pass2 = ms_since(t0);
     for (size_t c = 0; c < n_apply; c++) if (!apply_err[c].empty()) { P.err = apply_err[c]; return false; }
     if (draw_err_chrom < nc) { P.err = draw_err; return false; }
     for (size_t c = 0; c < nc; c++) {
@@ -648,7 +650,7 @@ bool build_plan(Plan& P, const std::vector<ChromIn>& chroms, const char* snp_fil
         std::vector<HapBuild>().swap(hap);
     }
     P.ms_segments = ms_since(t0);
-    if (getenv("SCS_TRACE")) fprintf(stderr, "[scs trace] simuvars plan: parse var %.1f ms, parse snp %.1f ms, segments %.1f ms\n", P.ms_parse_var, P.ms_parse_snp, P.ms_segments);
+    if (getenv("SCS_TRACE")) fprintf(stderr, "[scs trace] simuvars plan: parse var %.1f ms, parse snp %.1f ms, segments %.1f ms (draws %.1f, apply %.1f, merge %.1f)\n", P.ms_parse_var, P.ms_parse_snp, P.ms_segments, ms_pass1, ms_pass2 - ms_pass1, P.ms_segments - ms_pass2);
     return true;
 }
 
